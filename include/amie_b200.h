@@ -1,0 +1,179 @@
+/* amie_b200.h -- C-ABI of the B200-native block-sparse Krylov solve for AMIE.
+ *
+ * This is the drop-in boundary for ONE path of the reference (CyrilleDunant/xfem-amie):
+ *   Assembly::cgsolve -> ConjugateGradient::solve / BiConjugateGradientStabilized::solve
+ *   (solvers/assembly.cpp:1829-1953, solvers/conjugategradient.cpp:69-318,
+ *    solvers/biconjugategradientstabilized.cpp:12-148)
+ * over Assembly's CoordinateIndexedSparseMatrix (sparse/sparse_matrix.h:129-136) with the
+ * InverseDiagonal preconditioner (solvers/inversediagonal.cpp:48-67).
+ *
+ * All pointers are HOST memory owned by the caller unless a function says "device".  The
+ * context owns the device memory.  One context per Assembly; calls are serialised by the
+ * caller (the reference solver is single-caller, not re-entrant).  There is no CPU fallback:
+ * every compute entry point fails with AMIE_B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Return convention: solver entry points return 1 (converged) / 0 (not converged) exactly like
+ * the reference's `bool solve(...)`, or a negative AMIE_B200_ERR_* code.  Other entry points
+ * return 0 on success or a negative code.
+ */
+#ifndef AMIE_B200_H
+#define AMIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMIE_B200_OK              0
+#define AMIE_B200_ERR_CUDA       -1   /* CUDA runtime / no device / kernel failure            */
+#define AMIE_B200_ERR_ARG        -2   /* bad argument                                         */
+#define AMIE_B200_ERR_STATE      -3   /* call order (e.g. pcg before set_values)              */
+#define AMIE_B200_ERR_NAN        -4   /* NaN initial residual: the reference prints the       */
+                                      /* assembly and exit(0)s (conjugategradient.cpp:160-165) */
+#define AMIE_B200_ERR_UNSUPPORTED -5  /* stride / preconditioner kind not on the device path   */
+#define AMIE_B200_ERR_NCCL       -6
+
+/* precond_kind: what the caller passed as `Preconditionner * precond` */
+#define AMIE_B200_PRECOND_JACOBI 0    /* nullptr -> InverseDiagonal (conjugategradient.cpp:80-84)           */
+#define AMIE_B200_PRECOND_NULL   1    /* NullPreconditionner: precondition() is a no-op (preconditionners.cpp) */
+
+typedef struct amie_b200_ctx amie_b200_ctx ;
+
+/* ------------------------------------------------------------------ context */
+
+/* devices: CUDA ordinals; ndev == 1 (single device) in this round.  NULL/0 -> device 0
+ * (or env AMIE_B200_DEVICE).  Returns NULL on failure (see amie_b200_global_error). */
+amie_b200_ctx * amie_b200_create(const int * devices, int ndev) ;
+void            amie_b200_destroy(amie_b200_ctx * ctx) ;
+const char *    amie_b200_last_error(const amie_b200_ctx * ctx) ;
+const char *    amie_b200_global_error(void) ;
+const char *    amie_b200_version(void) ;
+
+/* ------------------------------------------------------------------ matrix
+ * Replaces the reads the reference solver does through assembly->getMatrix()
+ * (CoordinateIndexedSparseMatrix: stride, row_size, column_index, array;
+ *  sparse/sparse_matrix.h:129-136, ctor sparse/sparse_matrix.cpp:59-66).           */
+
+/* Once per topology change (Assembly::clear(), solvers/assembly.cpp:1380-1391).
+ * row_size[nb], column_index[nnzb] sorted ascending inside each block row.           */
+int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb,
+                            const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb) ;
+
+/* Every solve whose values changed.  `array` is the reference layout: block k at
+ * array[k*s*cl], element (r,c) at + c*cl + r, cl = s + s%2 (pad slots ignored).      */
+int amie_b200_set_values(amie_b200_ctx * ctx, const double * array_padded_colmajor) ;
+
+/* ------------------------------------------------------------------ solvers */
+
+/* ConjugateGradient::solve(x0, precond, eps, maxit) with members nssor/rowstart/colstart
+ * (solvers/conjugategradient.h:22-43).  b = assembly->getForces().
+ * x0 may be NULL / shorter than N (conjugategradient.cpp:95-104).
+ * x_out[N]; nit_out = cg.nit; err_out = the "Error :" value of the final cerr line;
+ * rho_out = "last rho".  Returns 1/0 or <0.                                              */
+int amie_b200_pcg(amie_b200_ctx * ctx, const double * b, const double * x0, uint64_t nx0,
+                  int precond_kind, double eps, int maxit, uint64_t nssor,
+                  uint64_t rowstart, uint64_t colstart,
+                  double * x_out, uint64_t * nit_out, double * err_out, double * rho_out) ;
+
+/* BiConjugateGradientStabilized::solve (solvers/biconjugategradientstabilized.cpp:12-148).
+ * Ignores rowstart/colstart like the reference.                                          */
+int amie_b200_bicgstab(amie_b200_ctx * ctx, const double * b, const double * x0, uint64_t nx0,
+                       int precond_kind, double eps, int maxit,
+                       double * x_out, uint64_t * nit_out, double * err_out) ;
+
+/* assign(y, A*x [- b], rowstart, colstart)  (sparse/sparse_matrix.cpp:462-547):
+ * rows < rowstart are 0, block columns < colstart/stride are skipped.  b may be NULL.   */
+int amie_b200_spmv(amie_b200_ctx * ctx, const double * x, const double * b,
+                   uint64_t rowstart, uint64_t colstart, double * y_out) ;
+
+/* CoordinateIndexedSparseMatrix::inverseDiagonal (sparse/sparse_matrix.cpp:216-231)      */
+int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out) ;
+
+/* ------------------------------------------------------------------ device-resident variants
+ * Same algorithms with b / x0 / x kept in HBM (no host<->device copies in the call): used to
+ * separate kernel throughput from PCIe time, and by callers that keep x on the device
+ * between the CG, CG, BiCGStab triple of one FeatureTree::step.   */
+int amie_b200_upload_rhs(amie_b200_ctx * ctx, const double * b) ;                 /* b  -> device */
+int amie_b200_upload_x0(amie_b200_ctx * ctx, const double * x0, uint64_t nx0) ;   /* x0 -> device (zero-filled) */
+int amie_b200_download_x(amie_b200_ctx * ctx, double * x_out) ;
+int amie_b200_pcg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t nssor,
+                           uint64_t rowstart, uint64_t colstart,
+                           uint64_t * nit_out, double * err_out, double * rho_out) ;
+int amie_b200_bicgstab_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit,
+                                uint64_t * nit_out, double * err_out) ;
+/* `reps` launches of the block-row SpMV y = A*x on resident vectors; average device
+ * milliseconds per launch (CUDA events on the launch stream) in *ms_out.                  */
+int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double * ms_out) ;
+
+/* ------------------------------------------------------------------ statistics */
+typedef struct amie_b200_stats
+{
+    uint64_t stride, nb, nnzb, ndof ;
+    uint64_t spmv_launches ;         /* block-row SpMV launches in the last solve (incl. smoothing/residual) */
+    uint64_t kernel_launches ;       /* all kernels launched by the last solve                               */
+    uint64_t smoothing_spmv ;        /* of which pre/post-smoothing + residual SpMVs                          */
+    uint64_t iterations ;            /* inner iterations (the reference's nit)                                */
+    uint64_t restarts ;
+    double   spmv_ms_total ;         /* sum of CUDA-event durations of the timed SpMV launches                */
+    uint64_t spmv_timed ;            /* number of SpMV launches that carried events                           */
+    double   solve_ms ;              /* device time of the last solve (events)                                */
+    double   h2d_ms, d2h_ms ;        /* copies done by the last host-buffer call                              */
+    uint64_t h2d_bytes, d2h_bytes ;
+    double   structure_ms, values_ms ; /* last set_structure / set_values (wall)                              */
+    uint64_t spmv_algorithmic_bytes ;  /* nnzb*(8 s^2 + 4) + 4 (nb+1) + 16 N                 */
+    uint64_t device_bytes ;          /* HBM held by the context                                               */
+} amie_b200_stats ;
+int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
+
+/* option keys: "time_spmv" (0/1: record an event pair around every SpMV launch),
+ * "spmv_variant" (kernel selection), "compensated" (0/1),
+ * "iters_per_graph" (iterations captured per CUDA-graph launch), "verbose" (0/1:
+ * print the reference's cerr lines).                                                     */
+int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value) ;
+
+/* ------------------------------------------------------------------ synthetic problems
+ * Structured 2D/3D elastic systems in the reference's storage layout:
+ * preset in {"S3-hex","S3-tet","S2-tri","ASR-hex"}; n = nodes per side.  Host-only
+ * (no GPU needed) except amie_b200_synth_to_device.                                       */
+typedef struct amie_b200_synth amie_b200_synth ;
+amie_b200_synth * amie_b200_synth_create(const char * preset, int n, uint64_t seed) ;
+void amie_b200_synth_destroy(amie_b200_synth * s) ;
+int  amie_b200_synth_sizes(const amie_b200_synth * s, int * stride, uint64_t * nb, uint64_t * nnzb) ;
+/* rows [row0,row1): row_size[row1-row0]; nnzb of the range in *nnzb_out                   */
+int  amie_b200_synth_count(const amie_b200_synth * s, uint64_t row0, uint64_t row1,
+                           uint32_t * row_size, uint64_t * nnzb_out) ;
+/* fills column_index (global block columns), array (reference padded layout) and b for
+ * rows [row0,row1); any of the three may be NULL.                                         */
+int  amie_b200_synth_fill(const amie_b200_synth * s, uint64_t row0, uint64_t row1,
+                          uint32_t * column_index, double * array_padded, double * b) ;
+/* Generates structure + values + rhs of the whole system directly in HBM (same generator
+ * compiled for the device; no host arrays): for sizes where the padded host array (43 GB at
+ * 50 M DOF) is impractical.  Afterwards the ctx is as after set_structure+set_values+upload_rhs. */
+int  amie_b200_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s) ;
+
+/* ------------------------------------------------------------------ row partition (multi-GPU, host-only)
+ * Contiguous block-row ranges balanced by stored blocks.
+ * bounds_out[nparts+1].                                                                    */
+int amie_b200_partition_rows(uint64_t nb, const uint32_t * row_size, int nparts, uint64_t * bounds_out) ;
+/* For part [r0,r1): the distinct off-range block columns its rows reference, ascending
+ * (= the halo it must receive).  Pass halo_out == NULL to get the count.                  */
+int amie_b200_partition_halo(uint64_t r0, uint64_t r1, const uint32_t * row_size_local,
+                             const uint32_t * column_index_local, uint32_t * halo_out, uint64_t * nhalo_out) ;
+
+/* ------------------------------------------------------------------ distributed context (one process per GPU)
+ * Rank r owns block rows [bounds[r], bounds[r+1]).  The NCCL communicator is created inside the
+ * library from a 128-byte ncclUniqueId the caller broadcasts (e.g. with torch.distributed).   */
+int amie_b200_nccl_unique_id(void * id128_out) ;
+int amie_b200_dist_init(amie_b200_ctx * ctx, int rank, int world, const void * id128,
+                        const uint64_t * bounds /* world+1 */) ;
+/* local rows of this rank, GLOBAL block column indices                                      */
+int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_global,
+                                 const uint32_t * row_size_local, const uint32_t * column_index_local,
+                                 uint64_t nnzb_local) ;
+int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s) ;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

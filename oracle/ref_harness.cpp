@@ -1,0 +1,194 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never on the product path).
+//
+// A C-ABI around the UNMODIFIED reference solver, compiled by oracle/build_ref.py against the
+// sources under /root/reference into oracle/_ref/libamie_ref_oracle.so.  It drives the reference
+// exactly the way SURVEY.md §8(c) "primary oracle" describes: a hand-filled Amie::Assembly
+// (all members public, solvers/assembly.h:230-264; getForces() skips make_final when the matrix
+// pointer is set, solvers/assembly.cpp:90-96), then
+//   Amie::ConjugateGradient::solve            (solvers/conjugategradient.cpp:69-318)
+//   Amie::BiConjugateGradientStabilized::solve (solvers/biconjugategradientstabilized.cpp:12-148)
+//   Amie::assign(y, A*x[-b], rowstart, colstart) (sparse/sparse_matrix.cpp:462-547)
+//   CoordinateIndexedSparseMatrix::inverseDiagonal (sparse/sparse_matrix.cpp:216-231)
+// No reference source is copied here; only its public headers are included.
+
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <chrono>
+#include <string>
+#ifdef HAVE_OPENMP
+#include <omp.h>
+#endif
+
+#include "solvers/assembly.h"
+#include "solvers/conjugategradient.h"
+#include "solvers/biconjugategradientstabilized.h"
+#include "solvers/inversediagonal.h"
+#include "sparse/sparse_matrix.h"
+
+namespace {
+
+struct CerrCapture
+{
+    std::streambuf * old ;
+    std::ostringstream sink ;
+    CerrCapture() : old(std::cerr.rdbuf(sink.rdbuf())) {}
+    ~CerrCapture() { std::cerr.rdbuf(old) ; }
+} ;
+
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() ;
+}
+
+void fill_assembly(Amie::Assembly & a, int stride, uint64_t nb, const uint32_t * row_size,
+                   const uint32_t * column_index, uint64_t nnzb, const double * array_padded,
+                   const double * b)
+{
+    std::valarray<unsigned int> rs(row_size, nb) ;
+    std::valarray<unsigned int> ci(column_index, nnzb) ;
+    a.coordinateIndexedMatrix = new Amie::CoordinateIndexedSparseMatrix(rs, ci, (size_t)stride) ;
+    Vector & arr = a.coordinateIndexedMatrix->array ;
+    std::memcpy(&arr[0], array_padded, arr.size()*sizeof(double)) ;
+    a.externalForces.resize(nb*stride) ;
+    if(b)
+        std::memcpy(&a.externalForces[0], b, nb*stride*sizeof(double)) ;
+    else
+        a.externalForces = 0. ;
+    a.displacements.resize(nb*stride) ;
+    a.displacements = 0. ;
+}
+
+void copy_log(const std::string & s, char * log, uint64_t logcap)
+{
+    if(!log || !logcap) return ;
+    size_t n = std::min<size_t>(s.size(), logcap-1) ;
+    // keep the tail: the "converged after" line is printed last
+    std::memcpy(log, s.data()+(s.size()-n), n) ;
+    log[n] = 0 ;
+}
+
+}
+
+extern "C" {
+
+int amie_ref_max_threads()
+{
+#ifdef HAVE_OPENMP
+    return omp_get_max_threads() ;
+#else
+    return 1 ;
+#endif
+}
+
+// returns 1 converged / 0 not converged.  precond_kind: 0 = nullptr (InverseDiagonal), 1 = NullPreconditionner
+int amie_ref_cg(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                const double * array_padded, const double * b, const double * x0, uint64_t nx0,
+                int precond_kind, double eps, int maxit, uint64_t nssor, uint64_t rowstart, uint64_t colstart,
+                int nthreads, double * x_out, uint64_t * nit_out, double * wall_s_out, char * log, uint64_t logcap)
+{
+#ifdef HAVE_OPENMP
+    if(nthreads > 0) omp_set_num_threads(nthreads) ;
+#endif
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, b) ;
+    CerrCapture cap ;
+    Amie::ConjugateGradient cg(&a) ;
+    cg.nssor = nssor ;
+    cg.rowstart = rowstart ;
+    cg.colstart = colstart ;
+    Vector vx0(0., nx0) ;
+    if(nx0) std::memcpy(&vx0[0], x0, nx0*sizeof(double)) ;
+    Amie::NullPreconditionner np ;
+    double t0 = now() ;
+    bool ok = cg.solve(vx0, precond_kind == 1 ? &np : nullptr, eps, maxit, false) ;
+    double t1 = now() ;
+    std::memcpy(x_out, &cg.x[0], cg.x.size()*sizeof(double)) ;
+    if(nit_out) *nit_out = cg.nit ;
+    if(wall_s_out) *wall_s_out = t1-t0 ;
+    copy_log(cap.sink.str(), log, logcap) ;
+    return ok ? 1 : 0 ;
+}
+
+int amie_ref_bicgstab(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                      const double * array_padded, const double * b, const double * x0, uint64_t nx0,
+                      int precond_kind, double eps, int maxit, int nthreads,
+                      double * x_out, uint64_t * nit_out, double * wall_s_out, char * log, uint64_t logcap)
+{
+#ifdef HAVE_OPENMP
+    if(nthreads > 0) omp_set_num_threads(nthreads) ;
+#endif
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, b) ;
+    CerrCapture cap ;
+    Amie::BiConjugateGradientStabilized cg(&a) ;
+    Vector vx0(0., nx0) ;
+    if(nx0) std::memcpy(&vx0[0], x0, nx0*sizeof(double)) ;
+    Amie::NullPreconditionner np ;
+    double t0 = now() ;
+    bool ok = cg.solve(vx0, precond_kind == 1 ? &np : nullptr, eps, maxit, true) ;
+    double t1 = now() ;
+    std::memcpy(x_out, &cg.x[0], cg.x.size()*sizeof(double)) ;
+    if(wall_s_out) *wall_s_out = t1-t0 ;
+    std::string s = cap.sink.str() ;
+    if(nit_out)
+    {
+        // the reference keeps nit local; it only appears in the verbose cerr line
+        // " BiCGStab <n> converged after <nit> iterations" / "did not converge after <nit>"
+        *nit_out = 0 ;
+        size_t pos = s.rfind(" after ") ;
+        if(pos != std::string::npos)
+            *nit_out = std::strtoull(s.c_str()+pos+7, nullptr, 10) ;
+    }
+    copy_log(s, log, logcap) ;
+    return ok ? 1 : 0 ;
+}
+
+// mode 0: assign(y, A*x, rowstart, colstart)          (Kahan, OpenMP tasks)
+// mode 1: assign(y, A*x - b, rowstart, colstart)
+// mode 2: y = A*x      via operator Vector()           (serial, non-Kahan)
+// mode 3: y = A*x - b  via operator const Vector()     (serial, non-Kahan)
+int amie_ref_spmv(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                  const double * array_padded, const double * x, const double * b, int mode,
+                  uint64_t rowstart, uint64_t colstart, int nthreads, int reps, double * y_out, double * wall_s_out)
+{
+#ifdef HAVE_OPENMP
+    if(nthreads > 0) omp_set_num_threads(nthreads) ;
+#endif
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, b) ;
+    const Amie::CoordinateIndexedSparseMatrix & A = *a.coordinateIndexedMatrix ;
+    Vector vx(0., nb*stride) ;
+    std::memcpy(&vx[0], x, nb*stride*sizeof(double)) ;
+    Vector y(0., nb*stride) ;
+    if(reps < 1) reps = 1 ;
+    double t0 = now() ;
+    for(int r = 0 ; r < reps ; r++)
+    {
+        switch(mode)
+        {
+        case 0: Amie::assign(y, A*vx, (int)rowstart, (int)colstart) ; break ;
+        case 1: Amie::assign(y, A*vx-a.externalForces, (int)rowstart, (int)colstart) ; break ;
+        case 2: y = (Vector)(A*vx) ; break ;
+        case 3: y = (Vector)(A*vx-a.externalForces) ; break ;
+        default: return -1 ;
+        }
+    }
+    double t1 = now() ;
+    std::memcpy(y_out, &y[0], nb*stride*sizeof(double)) ;
+    if(wall_s_out) *wall_s_out = (t1-t0)/reps ;
+    return 0 ;
+}
+
+int amie_ref_inverse_diagonal(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                              const double * array_padded, double * d_out)
+{
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, nullptr) ;
+    Vector d = a.coordinateIndexedMatrix->inverseDiagonal() ;
+    std::memcpy(d_out, &d[0], d.size()*sizeof(double)) ;
+    return 0 ;
+}
+
+}

@@ -1,0 +1,186 @@
+"""ctypes bindings of the CHECKERS (test infrastructure only):
+
+  * oracle/libamie_oracle.so          -- the C restatement (oracle/amie_oracle.c), always available;
+  * oracle/_ref/libamie_ref_oracle.so -- the unmodified reference compiled from /root/reference by
+                                         oracle/build_ref.py (present where it was prebuilt).
+
+Nothing in the product package imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+u64 = ctypes.c_uint64
+f64 = ctypes.c_double
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CgInfo(ctypes.Structure):
+    _fields_ = [("nit", u64), ("err", f64), ("last_rho", f64), ("spmv", u64), ("restarts", u64),
+                ("status", ctypes.c_int)]
+
+
+class BicgInfo(ctypes.Structure):
+    _fields_ = [("nit", u64), ("err", f64), ("rho", f64), ("spmv", u64)]
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    """The C restatement; built on demand (gcc only)."""
+    global _oracle
+    if _oracle is None:
+        so = os.path.join(ORACLE_DIR, "libamie_oracle.so")
+        src = os.path.join(ORACLE_DIR, "amie_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "libamie_oracle.so"], stdout=subprocess.DEVNULL)
+        _oracle = ctypes.CDLL(so)
+        _oracle.amie_oracle_dot.restype = f64
+    return _oracle
+
+
+def ref():
+    """The real reference solver, or None when oracle/_ref was not prebuilt."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(ORACLE_DIR, "_ref", "libamie_ref_oracle.so")
+        if not os.path.exists(so):
+            return None
+        _ref = ctypes.CDLL(so)
+    return _ref
+
+
+class Sys:
+    """A block-sparse system in the reference layout (numpy arrays)."""
+
+    def __init__(self, stride, nb, row_size, column_index, array, b):
+        self.stride, self.nb = int(stride), int(nb)
+        self.row_size = np.ascontiguousarray(row_size, np.uint32)
+        self.column_index = np.ascontiguousarray(column_index, np.uint32)
+        self.array = np.ascontiguousarray(array, np.float64)
+        self.b = np.ascontiguousarray(b, np.float64)
+        self.nnzb = int(self.column_index.size)
+        self.n = self.nb * self.stride
+
+    def head(self):
+        return (self.stride, u64(self.nb), _vp(self.row_size), _vp(self.column_index), u64(self.nnzb), _vp(self.array))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        s = self.stride
+        cl = s + s % 2
+        blocks = self.array.reshape(self.nnzb, s, cl)[:, :, :s].transpose(0, 2, 1).copy()
+        indptr = np.concatenate([[0], np.cumsum(self.row_size, dtype=np.int64)])
+        return sp.bsr_matrix((blocks, self.column_index.astype(np.int64), indptr), shape=(self.n, self.n)).tocsr()
+
+
+# ------------------------------------------------------------------ C restatement
+
+def oracle_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None):
+    b = S.b if b is None else np.ascontiguousarray(b, np.float64)
+    x = np.zeros(S.n)
+    info = CgInfo()
+    x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    ret = oracle().amie_oracle_cg(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond),
+                                  f64(eps), int(maxit), u64(nssor), u64(rowstart), u64(colstart), int(nthreads),
+                                  _vp(x), ctypes.byref(info))
+    return ret, x, info
+
+
+def oracle_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None):
+    b = S.b if b is None else np.ascontiguousarray(b, np.float64)
+    x = np.zeros(S.n)
+    info = BicgInfo()
+    x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    ret = oracle().amie_oracle_bicgstab(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond),
+                                        f64(eps), int(maxit), int(nthreads), _vp(x), ctypes.byref(info))
+    return ret, x, info
+
+
+def oracle_assign(S, v, b=None, rowstart=0, colstart=0):
+    y = np.zeros(S.n)
+    v = np.ascontiguousarray(v, np.float64)
+    b = None if b is None else np.ascontiguousarray(b, np.float64)
+    oracle().amie_oracle_assign(*S.head(), _vp(v), _vp(b), u64(rowstart), u64(colstart), _vp(y))
+    return y
+
+
+def oracle_spmv_serial(S, v, b=None):
+    y = np.zeros(S.n)
+    v = np.ascontiguousarray(v, np.float64)
+    b = None if b is None else np.ascontiguousarray(b, np.float64)
+    oracle().amie_oracle_spmv_serial(*S.head(), _vp(v), _vp(b), _vp(y))
+    return y
+
+
+def oracle_inverse_diagonal(S):
+    d = np.zeros(S.n)
+    oracle().amie_oracle_inverse_diagonal(*S.head(), _vp(d))
+    return d
+
+
+def oracle_dot(a, b, nthreads=1):
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    return oracle().amie_oracle_dot(_vp(a), _vp(b), ctypes.c_int64(a.size), int(nthreads))
+
+
+# ------------------------------------------------------------------ the real reference (oracle/_ref)
+
+def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None):
+    R = ref()
+    b = S.b if b is None else np.ascontiguousarray(b, np.float64)
+    x = np.zeros(S.n)
+    nit = u64()
+    wall = f64()
+    log = ctypes.create_string_buffer(8192)
+    x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    ret = R.amie_ref_cg(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond), f64(eps),
+                        int(maxit), u64(nssor), u64(rowstart), u64(colstart), int(nthreads), _vp(x),
+                        ctypes.byref(nit), ctypes.byref(wall), log, u64(8192))
+    return ret, x, nit.value, wall.value, log.value.decode(errors="replace")
+
+
+def ref_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None):
+    R = ref()
+    b = S.b if b is None else np.ascontiguousarray(b, np.float64)
+    x = np.zeros(S.n)
+    nit = u64()
+    wall = f64()
+    log = ctypes.create_string_buffer(8192)
+    x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    ret = R.amie_ref_bicgstab(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond),
+                              f64(eps), int(maxit), int(nthreads), _vp(x), ctypes.byref(nit), ctypes.byref(wall),
+                              log, u64(8192))
+    return ret, x, nit.value, wall.value, log.value.decode(errors="replace")
+
+
+def ref_spmv(S, v, b=None, mode=0, rowstart=0, colstart=0, nthreads=1, reps=1):
+    R = ref()
+    y = np.zeros(S.n)
+    wall = f64()
+    v = np.ascontiguousarray(v, np.float64)
+    b = None if b is None else np.ascontiguousarray(b, np.float64)
+    rc = R.amie_ref_spmv(*S.head(), _vp(v), _vp(b), int(mode), u64(rowstart), u64(colstart), int(nthreads),
+                         int(reps), _vp(y), ctypes.byref(wall))
+    assert rc == 0
+    return y, wall.value
+
+
+def ref_inverse_diagonal(S):
+    d = np.zeros(S.n)
+    ref().amie_ref_inverse_diagonal(*S.head(), _vp(d))
+    return d
+
+
+def ref_max_threads():
+    return ref().amie_ref_max_threads()
