@@ -97,6 +97,10 @@ int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out) ;
 int amie_b200_upload_rhs(amie_b200_ctx * ctx, const double * b) ;                 /* b  -> device */
 int amie_b200_upload_x0(amie_b200_ctx * ctx, const double * x0, uint64_t nx0) ;   /* x0 -> device (zero-filled) */
 int amie_b200_download_x(amie_b200_ctx * ctx, double * x_out) ;
+int amie_b200_download_rhs(amie_b200_ctx * ctx, double * b_out) ;
+/* the matrix as held on the device, converted back to the reference layout (tests; any pointer may be NULL) */
+int amie_b200_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out,
+                              double * array_padded_out) ;
 int amie_b200_pcg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t nssor,
                            uint64_t rowstart, uint64_t colstart,
                            uint64_t * nit_out, double * err_out, double * rho_out) ;

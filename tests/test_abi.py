@@ -1,0 +1,50 @@
+"""The C-ABI shared library loads and exports every symbol include/amie_b200.h declares (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "amie_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(amie_b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    L = ctypes.CDLL(pkg.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_version_and_no_silent_cpu_path(pkg):
+    assert b"sm_100a" in pkg.lib().amie_b200_version()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure path is only observable without one")
+    # without a device the context cannot be created and the mirror raises: no fallback
+    asm = pkg.Synth("S2-tri", 4).assembly()
+    with pytest.raises(pkg.AmieB200Error):
+        pkg.ConjugateGradient(asm).solve()
+
+
+def test_stats_struct_layout_matches_header(pkg):
+    txt = open(os.path.join(ROOT, "include", "amie_b200.h")).read()
+    body = re.search(r"typedef struct amie_b200_stats\s*\{(.*?)\}\s*amie_b200_stats", txt, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        typ, names = decl.split(None, 1)
+        for n in names.split(","):
+            fields.append((n.strip(), typ))
+    assert [f for f, _ in fields] == [f for f, _ in pkg.Stats._fields_]
+    assert ctypes.sizeof(pkg.Stats) == 8 * len(fields)

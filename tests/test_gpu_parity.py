@@ -1,0 +1,345 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle, on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CG iteration count within +-2 of the reference for the same eps,
+displacement field within relative L2 1e-8 (FP64).  SpMV results are compared at 1e-13 relative
+(the GPU reduces a row in a different order than the reference's sequential Kahan sum).
+BiCGStab's iteration count is rounding-chaotic in the reference itself (57/83/89 iterations at
+8/3/1 threads on one system): it is judged on convergence and solution error.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-8          # relative L2 on the displacement field (north_star)
+NIT_TOL = 2           # iterations
+SPMV_TOL = 1e-13
+
+CASES = [("S3-hex", 12), ("S3-hex", 20), ("S3-tet", 14), ("S2-tri", 40), ("ASR-hex", 12)]
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def assembly_of(pkg, S):
+    return pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+
+
+@pytest.fixture(scope="module")
+def asm_cache(pkg, systems):
+    cache = {}
+
+    def get(preset, n):
+        if (preset, n) not in cache:
+            cache[(preset, n)] = assembly_of(pkg, systems(preset, n))
+        return cache[(preset, n)]
+    yield get
+    for a in cache.values():
+        a.close()
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_spmv_matches_oracle(pkg, ol, systems, asm_cache, preset, n):
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    v = np.random.default_rng(11).standard_normal(S.n)
+    scale = np.abs(S.to_scipy()).dot(np.abs(v)).max()
+    y = asm.spmv(v)
+    assert np.abs(y - ol.oracle_assign(S, v)).max() <= SPMV_TOL * scale
+    y = asm.spmv(v, minus_b=S.b)
+    assert np.abs(y - ol.oracle_assign(S, v, S.b)).max() <= SPMV_TOL * (scale + np.abs(S.b).max())
+    rs = S.stride * (S.nb // 3)
+    y = asm.spmv(v, minus_b=S.b, rowstart=rs, colstart=rs)
+    yo = ol.oracle_assign(S, v, S.b, rs, rs)
+    assert not y[:rs].any()
+    assert np.abs(y - yo).max() <= SPMV_TOL * (scale + np.abs(S.b).max())
+    # colstart without rowstart (the final-residual call passes rowstart as colstart, :266)
+    y = asm.spmv(v, rowstart=0, colstart=rs)
+    assert np.abs(y - ol.oracle_assign(S, v, None, 0, rs)).max() <= SPMV_TOL * scale
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_inverse_diagonal_bit_exact(pkg, ol, systems, asm_cache, preset, n):
+    S = systems(preset, n)
+    assert np.array_equal(asm_cache(preset, n).inverse_diagonal(), ol.oracle_inverse_diagonal(S))
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_pcg_parity(pkg, ol, systems, asm_cache, preset, n):
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+    # the values the reference prints on its final cerr line
+    assert cg.last_error == pytest.approx(info.err, rel=0.5, abs=1e-12)
+    # true residual of the returned field
+    A = S.to_scipy()
+    assert np.linalg.norm(A @ cg.x - S.b) <= 10 * max(np.linalg.norm(A @ x_ref - S.b), 1e-10)
+
+
+@pytest.mark.parametrize("kw", [dict(nssor=0), dict(nssor=128), dict(nssor=32, eps=1e-6), dict(nssor=32, eps=1e-13),
+                                dict(nssor=5, maxit=3)], ids=str)
+def test_pcg_options(pkg, ol, systems, asm_cache, kw):
+    S = systems("S3-hex", 12)
+    asm = asm_cache("S3-hex", 12)
+    eps, maxit, nssor = kw.get("eps", 1e-10), kw.get("maxit", -1), kw["nssor"]
+    ret, x_ref, info = ol.oracle_cg(S, nssor=nssor, eps=eps, maxit=maxit)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = nssor
+    ok = cg.solve(None, None, eps, maxit)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= max(X_TOL, 100 * eps if eps > 1e-9 else 0)
+
+
+def test_pcg_warm_start_and_short_x0(pkg, ol, systems, asm_cache):
+    S = systems("S3-tet", 14)
+    asm = asm_cache("S3-tet", 14)
+    _, xs, _ = ol.oracle_cg(S, nssor=32)
+    for x0 in (0.9 * xs, xs[: S.n // 2], xs):
+        ret, x_ref, info = ol.oracle_cg(S, x0=x0, nssor=32)
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor = 32
+        ok = cg.solve(x0, None, 1e-10, -1)
+        assert ok == bool(ret)
+        assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+        assert rel_l2(cg.x, x_ref) <= X_TOL
+
+
+@pytest.mark.parametrize("preset,n", [("S2-tri", 40), ("S3-hex", 12)])
+def test_pcg_rowstart(pkg, ol, systems, asm_cache, preset, n):
+    """rowstart = colstart > 0: the space-time planes of tension_benchmark --space-time
+    (solvers/assembly.cpp:327-343): x[0:rowstart) = b[0:rowstart), rows/columns before it skipped."""
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    rs = S.stride * (S.nb // 4)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32, rowstart=rs, colstart=rs)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor, cg.rowstart, cg.colstart = 32, rs, rs
+    ok = cg.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert np.array_equal(cg.x[:rs], S.b[:rs])
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+
+
+def test_pcg_null_preconditionner(pkg, ol, systems, asm_cache):
+    """NullPreconditionner::precondition is a no-op, so z keeps its restart value (a reference
+    quirk, Assembly::cgnpsolve): reproduced, not repaired."""
+    S = systems("S3-hex", 12)
+    asm = asm_cache("S3-hex", 12)
+    ret, x_ref, info = ol.oracle_cg(S, precond=1, nssor=32, eps=1e-4)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, pkg.NullPreconditionner(), 1e-4, -1)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= max(NIT_TOL, info.nit // 50), (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= 1e-6
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_bicgstab_parity(pkg, ol, systems, asm_cache, preset, n):
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    ret, x_ref, info = ol.oracle_bicgstab(S)
+    _, x_cg, _ = ol.oracle_cg(S, nssor=32)
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    ok = bi.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert rel_l2(bi.x, x_ref) <= X_TOL
+    assert 0.5 * info.nit <= bi.nit <= 1.6 * info.nit + 5, (bi.nit, info.nit)
+    # the way FeatureTree::step reaches it: third solve, warm-started from the CG answer
+    ret, x_ref, info = ol.oracle_bicgstab(S, x0=x_cg)
+    ok = bi.solve(x_cg, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert rel_l2(bi.x, x_ref) <= X_TOL
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_against_reference_golden_vectors(pkg, path):
+    """Directly against outputs of the real reference (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(g["row_size"], g["column_index"], int(g["stride"]), g["array"]),
+                       g["b"], device=0)
+    v = g["v"]
+    rs = int(g["rowstart"])
+    scale = np.abs(g["assign"]).max() + 1e-300
+    assert np.abs(asm.spmv(v) - g["assign"]).max() <= 1e-12 * scale
+    assert np.abs(asm.spmv(v, minus_b=g["b"], rowstart=rs, colstart=rs) - g["assign_minus_b_rowstart"]).max() <= 1e-12 * (scale + np.abs(g["b"]).max())
+    assert np.array_equal(asm.inverse_diagonal(), g["inverse_diagonal"])
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    assert cg.solve() == bool(g["cg_ok"])
+    assert abs(int(cg.nit) - int(g["cg_nit"])) <= NIT_TOL
+    assert rel_l2(cg.x, g["cg_x"]) <= X_TOL
+    cg.rowstart = cg.colstart = rs
+    assert cg.solve() == bool(g["cg_rs_ok"])
+    assert abs(int(cg.nit) - int(g["cg_rs_nit"])) <= NIT_TOL
+    assert rel_l2(cg.x, g["cg_rs_x"]) <= X_TOL
+    cg.rowstart = cg.colstart = 0
+    cg.nssor = 0
+    assert cg.solve(0.5 * g["cg_x"]) == bool(g["cg_warm_ok"])
+    assert abs(int(cg.nit) - int(g["cg_warm_nit"])) <= NIT_TOL
+    assert rel_l2(cg.x, g["cg_warm_x"]) <= X_TOL
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    assert bi.solve() == bool(g["bicg_ok"])
+    assert rel_l2(bi.x, g["bicg_x"]) <= X_TOL
+    asm.close()
+
+
+def test_edge_cases(pkg, ol, systems, asm_cache):
+    S = systems("S3-hex", 12)
+    asm = asm_cache("S3-hex", 12)
+    # homogeneous right-hand side: true, x untouched (= 0)   (conjugategradient.cpp:74-78)
+    a0 = assembly_of(pkg, ol.Sys(S.stride, S.nb, S.row_size, S.column_index, S.array, np.zeros(S.n)))
+    cg = pkg.ConjugateGradient(a0)
+    assert cg.solve(np.ones(S.n)) is True and cg.nit == 0 and not cg.x.any()
+    a0.close()
+    # exact start: leaves through err0 < realeps with nit = 0  (:170-175)
+    _, xs, _ = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 0
+    ret, x_ref, info = ol.oracle_cg(S, x0=xs, nssor=0)
+    assert cg.solve(xs) == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= NIT_TOL
+    # NaN in the matrix: the reference prints the assembly and exit(0)s; the C-ABI returns ERR_NAN
+    bad = S.array.copy()
+    bad[4] = np.nan
+    an = assembly_of(pkg, ol.Sys(S.stride, S.nb, S.row_size, S.column_index, bad, S.b))
+    cgn = pkg.ConjugateGradient(an)
+    cgn.nssor = 0
+    with pytest.raises(pkg.AmieB200Error) as e:
+        cgn.solve()
+    assert e.value.code == pkg.ERR_NAN
+    an.close()
+    # unsupported stride and malformed structure are refused, not mis-computed
+    a1 = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(np.array([1, 1], np.uint32), np.array([0, 1], np.uint32), 1), np.ones(2), device=0)
+    with pytest.raises(pkg.AmieB200Error) as e:
+        a1.sync_matrix()
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    a1.close()
+    a2 = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(np.array([2, 1], np.uint32), np.array([1, 0, 1], np.uint32), 2), np.ones(4), device=0)
+    with pytest.raises(pkg.AmieB200Error) as e:
+        a2.sync_matrix()
+    assert e.value.code == pkg.ERR_ARG
+    a2.close()
+
+
+def test_ragged_rows_and_long_rows(pkg, ol):
+    """Rows longer than one 27-block chunk, empty-ish rows, random unstructured pattern (both strides)."""
+    rng = np.random.default_rng(5)
+    for stride in (2, 3):
+        nb = 300
+        cl = stride + stride % 2
+        rows = []
+        for r in range(nb):
+            k = int(rng.choice([1, 2, 5, 27, 28, 40, 64, 70]))
+            cols = set(rng.integers(0, nb, k).tolist()) | {r}
+            rows.append(sorted(cols))
+        rs = np.array([len(c) for c in rows], np.uint32)
+        ci = np.array([c for row in rows for c in row], np.uint32)
+        arr = rng.standard_normal(ci.size * stride * cl)
+        arr.reshape(-1, stride, cl)[:, :, stride:] = 0
+        b = rng.standard_normal(nb * stride)
+        S = ol.Sys(stride, nb, rs, ci, arr, b)
+        asm = assembly_of(pkg, S)
+        v = rng.standard_normal(S.n)
+        yo = ol.oracle_assign(S, v, b, 0, 0)
+        assert np.abs(asm.spmv(v, minus_b=b) - yo).max() <= 1e-12 * np.abs(yo).max()
+        cs = stride * 100
+        yo = ol.oracle_assign(S, v, None, cs, cs)
+        assert np.abs(asm.spmv(v, rowstart=cs, colstart=cs) - yo).max() <= 1e-12 * np.abs(yo).max()
+        assert np.array_equal(asm.inverse_diagonal(), ol.oracle_inverse_diagonal(S))
+        asm.close()
+
+
+def test_values_update_keeps_structure(pkg, ol, systems):
+    """Damage stepping (main_tripoint): same topology, new values every step -> set_values only."""
+    S = systems("S2-tri", 40)
+    asm = assembly_of(pkg, S)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    cg.solve()
+    t_struct = asm.stats().structure_ms
+    A = asm.getMatrix()
+    for step in range(2):
+        A.array *= 0.9                      # uniform damage: x scales by 1/0.9
+        asm.values_changed()
+        S2 = ol.Sys(S.stride, S.nb, S.row_size, S.column_index, A.array, S.b)
+        ret, x_ref, info = ol.oracle_cg(S2, nssor=32)
+        assert cg.solve() == bool(ret)
+        assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL
+        assert rel_l2(cg.x, x_ref) <= X_TOL
+        assert asm.stats().structure_ms == t_struct      # structure was not re-uploaded
+    asm.close()
+
+
+def test_device_generator_equals_host_generator(pkg):
+    for preset, n in [("S3-hex", 9), ("S3-tet", 8), ("S2-tri", 17), ("ASR-hex", 9)]:
+        syn = pkg.Synth(preset, n)
+        rs, ci, arr, b = syn.rows()
+        asm = pkg.Assembly(device=0)
+        syn.to_device(asm)
+        rs_d, ci_d, arr_d, b_d = asm.download_matrix()
+        assert np.array_equal(rs, rs_d) and np.array_equal(ci, ci_d)
+        assert np.array_equal(arr, arr_d), preset
+        assert np.array_equal(b, b_d), preset
+        asm.close()
+
+
+def test_resident_solve_equals_host_call(pkg, ol, systems):
+    S = systems("S3-hex", 20)
+    asm = assembly_of(pkg, S)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    cg.solve()
+    asm.upload_rhs(S.b)
+    asm.upload_x0(None)
+    ok, nit, err, rho = asm.pcg_resident(nssor=32)
+    assert ok and nit == cg.nit
+    assert np.array_equal(asm.download_x(), cg.x)        # deterministic reductions: same bits, run to run
+    st = asm.stats()
+    assert st.iterations == nit and st.spmv_launches >= nit + 3 and st.kernel_launches >= 3 * nit
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 128), ("S3-tet", 128), ("S2-tri", 2048)])
+def test_full_size_properties(pkg, preset, n):
+    """Sizes the CPU oracle cannot finish in seconds: size-independent properties on the
+    device-generated system -- sampled rows against the host generator, symmetry
+    u.(A v) = v.(A u), linearity, and the true residual after a converged solve."""
+    syn = pkg.Synth(preset, n)
+    asm = pkg.Assembly(device=0)
+    syn.to_device(asm)
+    st = asm.stats()
+    N, s = st.ndof, st.stride
+    rng = np.random.default_rng(2)
+    u, v = rng.standard_normal(N), rng.standard_normal(N)
+    Au, Av = asm.spmv(u), asm.spmv(v)
+    assert abs(u @ Av - v @ Au) <= 1e-11 * (np.abs(u) @ np.abs(Av))
+    Aw = asm.spmv(2.0 * u - 3.0 * v)
+    assert rel_l2(Aw, 2.0 * Au - 3.0 * Av) <= 1e-13
+    cl = s + s % 2
+    for row in rng.integers(0, syn.nb, 64):
+        rs, ci, arr, b = syn.rows(int(row), int(row) + 1)
+        blocks = arr.reshape(-1, s, cl)[:, :, :s]                    # (k, c, r)
+        xs = u.reshape(-1, s)[ci]                                    # (k, c)
+        y = np.einsum("kcr,kc->r", blocks, xs)
+        assert np.abs(y - Au[row * s:(row + 1) * s]).max() <= 1e-12 * (np.abs(blocks).sum() * np.abs(u).max())
+    # converged solve: the residual of the returned field, computed independently
+    asm.upload_x0(None)
+    ok, nit, err, rho = asm.pcg_resident(nssor=32)
+    assert ok and nit > 0
+    x = asm.download_x()
+    rhs = asm.download_rhs()
+    res = asm.spmv(x, minus_b=rhs)
+    assert np.linalg.norm(res) <= 1e-5 * max(1.0, np.linalg.norm(rhs))
+    assert np.sqrt(abs(rho)) <= 1e-10
+    asm.close()

@@ -1,0 +1,422 @@
+"""Python mirror of the reference's solver interface over the C-ABI of libamie_b200.so.
+
+The product is the CUDA library (csrc/, C-ABI in include/amie_b200.h).  This module is the thin
+host-side mirror used by tests and bench.py: the same names, argument meaning and error behaviour
+as the reference's solver classes,
+
+    Amie::CoordinateIndexedSparseMatrix      sparse/sparse_matrix.h:129-136
+    Amie::Assembly  (getMatrix / getForces)  solvers/assembly.h:228-450
+    Amie::ConjugateGradient                  solvers/conjugategradient.h:22-43
+    Amie::BiConjugateGradientStabilized      solvers/biconjugategradientstabilized.h:19-24
+    Amie::NullPreconditionner                solvers/preconditionners.h:28-32
+
+There is NO CPU fallback: without the built extension (or without an sm_100 GPU) every compute
+call raises.  The directory name has a hyphen, so load it with ``load_package()`` of
+``__graft_entry__`` (importlib), which registers it as ``xfem_amie_b200``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libamie_b200.so")
+
+u64 = ctypes.c_uint64
+f64 = ctypes.c_double
+
+ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NAN, ERR_UNSUPPORTED, ERR_NCCL = -1, -2, -3, -4, -5, -6
+PRECOND_JACOBI, PRECOND_NULL = 0, 1
+default_solver_precision = 1e-10          # polynomial/variable.h:14
+
+
+class AmieB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"amie_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("stride", u64), ("nb", u64), ("nnzb", u64), ("ndof", u64),
+                ("spmv_launches", u64), ("kernel_launches", u64), ("smoothing_spmv", u64),
+                ("iterations", u64), ("restarts", u64),
+                ("spmv_ms_total", f64), ("spmv_timed", u64), ("solve_ms", f64),
+                ("h2d_ms", f64), ("d2h_ms", f64), ("h2d_bytes", u64), ("d2h_bytes", u64),
+                ("structure_ms", f64), ("values_ms", f64),
+                ("spmv_algorithmic_bytes", u64), ("device_bytes", u64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """The CUDA extension.  Fails loudly when it was not built: there is no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, cp, ci = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int
+        L.amie_b200_create.restype = vp
+        L.amie_b200_create.argtypes = [vp, ci]
+        L.amie_b200_destroy.argtypes = [vp]
+        for n in ("amie_b200_last_error", "amie_b200_global_error", "amie_b200_version"):
+            getattr(L, n).restype = cp
+        L.amie_b200_last_error.argtypes = [vp]
+        L.amie_b200_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
+        L.amie_b200_set_values.argtypes = [vp, vp]
+        L.amie_b200_pcg.argtypes = [vp, vp, vp, u64, ci, f64, ci, u64, u64, u64, vp, vp, vp, vp]
+        L.amie_b200_bicgstab.argtypes = [vp, vp, vp, u64, ci, f64, ci, vp, vp, vp]
+        L.amie_b200_spmv.argtypes = [vp, vp, vp, u64, u64, vp]
+        L.amie_b200_inverse_diagonal.argtypes = [vp, vp]
+        L.amie_b200_upload_rhs.argtypes = [vp, vp]
+        L.amie_b200_upload_x0.argtypes = [vp, vp, u64]
+        L.amie_b200_download_x.argtypes = [vp, vp]
+        L.amie_b200_download_rhs.argtypes = [vp, vp]
+        L.amie_b200_download_matrix.argtypes = [vp, vp, vp, vp]
+        L.amie_b200_pcg_resident.argtypes = [vp, ci, f64, ci, u64, u64, u64, vp, vp, vp]
+        L.amie_b200_bicgstab_resident.argtypes = [vp, ci, f64, ci, vp, vp]
+        L.amie_b200_spmv_resident.argtypes = [vp, ci, ci, vp]
+        L.amie_b200_get_stats.argtypes = [vp, vp]
+        L.amie_b200_set_option.argtypes = [vp, cp, ctypes.c_int64]
+        L.amie_b200_synth_create.restype = vp
+        L.amie_b200_synth_create.argtypes = [cp, ci, u64]
+        L.amie_b200_synth_destroy.argtypes = [vp]
+        L.amie_b200_synth_sizes.argtypes = [vp, vp, vp, vp]
+        L.amie_b200_synth_count.argtypes = [vp, u64, u64, vp, vp]
+        L.amie_b200_synth_fill.argtypes = [vp, u64, u64, vp, vp, vp]
+        L.amie_b200_synth_to_device.argtypes = [vp, vp]
+        L.amie_b200_partition_rows.argtypes = [u64, vp, ci, vp]
+        L.amie_b200_partition_halo.argtypes = [u64, u64, vp, vp, vp, vp]
+        L.amie_b200_nccl_unique_id.argtypes = [vp]
+        L.amie_b200_dist_init.argtypes = [vp, ci, ci, vp, vp]
+        L.amie_b200_dist_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
+        L.amie_b200_dist_synth_to_device.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------- reference-shaped host objects
+
+class CoordinateIndexedSparseMatrix:
+    """Block-CSR in the reference's layout: stride, array (padded column-major blocks),
+    column_index, row_size, accumulated_row_size (sparse/sparse_matrix.h:129-136)."""
+
+    def __init__(self, row_size, column_index, stride, array=None):
+        self.stride = int(stride)
+        self.row_size = np.ascontiguousarray(row_size, np.uint32)
+        self.column_index = np.ascontiguousarray(column_index, np.uint32)
+        cl = self.stride + self.stride % 2
+        n = self.column_index.size * self.stride * cl
+        self.array = np.zeros(n) if array is None else np.ascontiguousarray(array, np.float64)
+        if self.array.size != n:
+            raise ValueError("array size does not match column_index.size*stride*(stride+stride%2)")
+        self.accumulated_row_size = np.concatenate([[0], np.cumsum(self.row_size[:-1], dtype=np.uint64)]).astype(np.uint32) \
+            if self.row_size.size else np.zeros(0, np.uint32)
+
+
+class Assembly:
+    """The two things the solvers pull from an Assembly: getMatrix() and getForces()
+    (solvers/assembly.cpp:90-96), plus the knobs Assembly::cgsolve forwards
+    (nssor, rowstart, colstart, epsilon; solvers/assembly.cpp:1829-1850).
+    Owns the device context (one per Assembly)."""
+
+    def __init__(self, matrix=None, forces=None, device=None):
+        self.coordinateIndexedMatrix = matrix
+        self.externalForces = None if forces is None else np.ascontiguousarray(forces, np.float64)
+        self.displacements = np.zeros(0)
+        self.nssor = 32
+        self.rowstart = 0
+        self.colstart = 0
+        self.epsilon = default_solver_precision
+        self._device = device
+        self._ctx = None
+        self._structure_key = None
+        self._values_dirty = True
+
+    # -- device context
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            L = lib()
+            if self._device is None:
+                h = L.amie_b200_create(None, 0)
+            else:
+                d = (ctypes.c_int * 1)(int(self._device))
+                h = L.amie_b200_create(d, 1)
+            if not h:
+                raise AmieB200Error(ERR_CUDA, L.amie_b200_global_error().decode())
+            self._ctx = ctypes.c_void_p(h)
+        return self._ctx
+
+    def close(self):
+        if self._ctx is not None:
+            lib().amie_b200_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc < 0:
+            raise AmieB200Error(rc, lib().amie_b200_last_error(self.ctx).decode())
+        return rc
+
+    def getMatrix(self):
+        return self.coordinateIndexedMatrix
+
+    def getForces(self):
+        return self.externalForces
+
+    def setEpsilon(self, e):
+        self.epsilon = e
+
+    def set_option(self, key, value):
+        self.check(lib().amie_b200_set_option(self.ctx, key.encode(), int(value)))
+
+    def values_changed(self):
+        """Tell the context the matrix values were re-assembled (every damage step)."""
+        self._values_dirty = True
+
+    def sync_matrix(self):
+        """Upload structure once per topology, values whenever they changed."""
+        A = self.coordinateIndexedMatrix
+        L = lib()
+        key = (A.stride, A.row_size.size, A.column_index.size, A.column_index.ctypes.data)
+        if key != self._structure_key:
+            self.check(L.amie_b200_set_structure(self.ctx, A.stride, A.row_size.size, _ptr(A.row_size),
+                                                 _ptr(A.column_index), A.column_index.size))
+            self._structure_key = key
+            self._values_dirty = True
+        if self._values_dirty:
+            self.check(L.amie_b200_set_values(self.ctx, _ptr(A.array)))
+            self._values_dirty = False
+
+    def stats(self):
+        s = Stats()
+        self.check(lib().amie_b200_get_stats(self.ctx, ctypes.byref(s)))
+        return s
+
+    def download_matrix(self):
+        """(row_size, column_index, array_padded, b) as held on the device (tests)."""
+        st = self.stats()
+        cl = st.stride + st.stride % 2
+        rs = np.zeros(st.nb, np.uint32)
+        ci = np.zeros(st.nnzb, np.uint32)
+        arr = np.zeros(st.nnzb * st.stride * cl)
+        b = np.zeros(st.ndof)
+        self.check(lib().amie_b200_download_matrix(self.ctx, _ptr(rs), _ptr(ci), _ptr(arr)))
+        self.check(lib().amie_b200_download_rhs(self.ctx, _ptr(b)))
+        return rs, ci, arr, b
+
+    # -- device-resident calls (no host<->device copies inside)
+    def upload_rhs(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        self.check(lib().amie_b200_upload_rhs(self.ctx, _ptr(b)))
+
+    def upload_x0(self, x0=None):
+        x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
+        self.check(lib().amie_b200_upload_x0(self.ctx, _ptr(x0) if x0.size else None, x0.size))
+
+    def download_rhs(self):
+        b = np.zeros(self.stats().ndof)
+        self.check(lib().amie_b200_download_rhs(self.ctx, _ptr(b)))
+        return b
+
+    def download_x(self):
+        x = np.zeros(self.stats().ndof)
+        self.check(lib().amie_b200_download_x(self.ctx, _ptr(x)))
+        return x
+
+    def pcg_resident(self, precond=PRECOND_JACOBI, eps=default_solver_precision, maxit=-1, nssor=32, rowstart=0, colstart=0):
+        nit, err, rho = u64(), f64(), f64()
+        rc = self.check(lib().amie_b200_pcg_resident(self.ctx, precond, eps, int(maxit), int(nssor), int(rowstart), int(colstart),
+                                                     ctypes.byref(nit), ctypes.byref(err), ctypes.byref(rho)))
+        return bool(rc), nit.value, err.value, rho.value
+
+    def bicgstab_resident(self, precond=PRECOND_JACOBI, eps=default_solver_precision, maxit=-1):
+        nit, err = u64(), f64()
+        rc = self.check(lib().amie_b200_bicgstab_resident(self.ctx, precond, eps, int(maxit), ctypes.byref(nit), ctypes.byref(err)))
+        return bool(rc), nit.value, err.value
+
+    def spmv_resident(self, reps=10, variant=0):
+        ms = f64()
+        self.check(lib().amie_b200_spmv_resident(self.ctx, int(reps), int(variant), ctypes.byref(ms)))
+        return ms.value
+
+    def spmv(self, x, minus_b=None, rowstart=0, colstart=0):
+        """assign(y, A*x [- b], rowstart, colstart)"""
+        self.sync_matrix()
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros_like(x)
+        b = None if minus_b is None else np.ascontiguousarray(minus_b, np.float64)
+        self.check(lib().amie_b200_spmv(self.ctx, _ptr(x), _ptr(b), rowstart, colstart, _ptr(y)))
+        return y
+
+    def inverse_diagonal(self):
+        self.sync_matrix()
+        d = np.zeros(self.coordinateIndexedMatrix.row_size.size * self.coordinateIndexedMatrix.stride)
+        self.check(lib().amie_b200_inverse_diagonal(self.ctx, _ptr(d)))
+        return d
+
+    def cgsolve(self, maxit=-1, verbose=False):
+        """Assembly::cgsolve for an assembled symmetric system (solvers/assembly.cpp:1841-1858)."""
+        cg = ConjugateGradient(self)
+        cg.nssor = self.nssor
+        if self.rowstart > 0 or self.colstart > 0:
+            cg.rowstart, cg.colstart = self.rowstart, self.colstart
+        ret = cg.solve(self.displacements, None, self.epsilon, -1, verbose)
+        self.displacements = cg.x
+        return ret
+
+
+class Preconditionner:
+    kind = None
+
+
+class NullPreconditionner(Preconditionner):
+    kind = PRECOND_NULL
+
+
+class LinearSolver:
+    def __init__(self, assembly):
+        self.assembly = assembly
+        self.rowstart = 0
+        self.colstart = 0
+        n = 0 if assembly.getForces() is None else assembly.getForces().size
+        self.x = np.zeros(n)          # Solver::Solver, solvers/solver.cpp:15
+
+    @staticmethod
+    def _kind(precond):
+        if precond is None:
+            return PRECOND_JACOBI
+        if isinstance(precond, NullPreconditionner):
+            return PRECOND_NULL
+        raise AmieB200Error(ERR_UNSUPPORTED, "only nullptr (InverseDiagonal) and NullPreconditionner run on the device")
+
+
+class ConjugateGradient(LinearSolver):
+    def __init__(self, assembly):
+        super().__init__(assembly)
+        self.nit = 0
+        self.nssor = 128              # conjugategradient.h:34
+        self.last_error = 0.0
+        self.last_rho = 0.0
+
+    def solve(self, x0=None, precond=None, eps=default_solver_precision, maxit=-1, verbose=False):
+        A = self.assembly
+        A.sync_matrix()
+        if verbose:
+            A.set_option("verbose", 1)
+        b = A.getForces()
+        x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
+        x = np.zeros(b.size)
+        nit, err, rho = u64(), f64(), f64()
+        rc = lib().amie_b200_pcg(A.ctx, _ptr(b), _ptr(x0) if x0.size else None, x0.size, self._kind(precond),
+                                 eps, int(maxit), int(self.nssor), int(self.rowstart), int(self.colstart),
+                                 _ptr(x), ctypes.byref(nit), ctypes.byref(err), ctypes.byref(rho))
+        A.check(rc)
+        self.x, self.nit, self.last_error, self.last_rho = x, nit.value, err.value, rho.value
+        return bool(rc)
+
+
+class BiConjugateGradientStabilized(LinearSolver):
+    def __init__(self, assembly):
+        super().__init__(assembly)
+        self.nit = 0                  # the reference keeps it local; exposed here for the tests
+        self.last_error = 0.0
+
+    def solve(self, x0=None, precond=None, eps=default_solver_precision, maxit=-1, verbose=False):
+        A = self.assembly
+        A.sync_matrix()
+        if verbose:
+            A.set_option("verbose", 1)
+        b = A.getForces()
+        x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
+        x = np.zeros(b.size)
+        nit, err = u64(), f64()
+        rc = lib().amie_b200_bicgstab(A.ctx, _ptr(b), _ptr(x0) if x0.size else None, x0.size, self._kind(precond),
+                                      eps, int(maxit), _ptr(x), ctypes.byref(nit), ctypes.byref(err))
+        A.check(rc)
+        self.x, self.nit, self.last_error = x, nit.value, err.value
+        return bool(rc)
+
+
+# --------------------------------------------------------------------------- synthetic structured meshes (host-only)
+
+class Synth:
+    """S3-hex / S3-tet / S2-tri / ASR-hex systems of SURVEY.md §8(d) in the reference layout."""
+
+    def __init__(self, preset, n, seed=1):
+        self.preset, self.n = preset, int(n)
+        h = lib().amie_b200_synth_create(preset.encode(), int(n), int(seed))
+        if not h:
+            raise ValueError(f"unknown synthetic preset {preset!r} or n < 2")
+        self.handle = ctypes.c_void_p(h)
+        st, nb = ctypes.c_int(), u64()
+        lib().amie_b200_synth_sizes(self.handle, ctypes.byref(st), ctypes.byref(nb), None)
+        self.stride, self.nb = st.value, nb.value
+
+    def __del__(self):
+        try:
+            lib().amie_b200_synth_destroy(self.handle)
+        except Exception:
+            pass
+
+    def row_sizes(self, row0=0, row1=None):
+        row1 = self.nb if row1 is None else row1
+        rs = np.zeros(row1 - row0, np.uint32)
+        tot = u64()
+        lib().amie_b200_synth_count(self.handle, row0, row1, _ptr(rs), ctypes.byref(tot))
+        return rs, tot.value
+
+    def rows(self, row0=0, row1=None):
+        """(row_size, column_index (global), array_padded, b) of block rows [row0,row1)."""
+        row1 = self.nb if row1 is None else row1
+        rs, nnzb = self.row_sizes(row0, row1)
+        cl = self.stride + self.stride % 2
+        ci = np.zeros(nnzb, np.uint32)
+        arr = np.zeros(nnzb * self.stride * cl)
+        b = np.zeros((row1 - row0) * self.stride)
+        rc = lib().amie_b200_synth_fill(self.handle, row0, row1, _ptr(ci), _ptr(arr), _ptr(b))
+        if rc:
+            raise AmieB200Error(rc, "synth_fill")
+        return rs, ci, arr, b
+
+    def assembly(self, device=None):
+        rs, ci, arr, b = self.rows()
+        return Assembly(CoordinateIndexedSparseMatrix(rs, ci, self.stride, arr), b, device=device)
+
+    def to_device(self, assembly):
+        """Generate structure + values + rhs directly in HBM (no host arrays)."""
+        assembly.check(lib().amie_b200_synth_to_device(assembly.ctx, self.handle))
+
+
+def partition_rows(row_size, nparts):
+    row_size = np.ascontiguousarray(row_size, np.uint32)
+    bounds = np.zeros(nparts + 1, np.uint64)
+    rc = lib().amie_b200_partition_rows(row_size.size, _ptr(row_size), nparts, _ptr(bounds))
+    if rc:
+        raise AmieB200Error(rc, "partition_rows")
+    return bounds
+
+
+def partition_halo(r0, r1, row_size_local, column_index_local):
+    rs = np.ascontiguousarray(row_size_local, np.uint32)
+    ci = np.ascontiguousarray(column_index_local, np.uint32)
+    n = u64()
+    lib().amie_b200_partition_halo(int(r0), int(r1), _ptr(rs), _ptr(ci), None, ctypes.byref(n))
+    halo = np.zeros(n.value, np.uint32)
+    lib().amie_b200_partition_halo(int(r0), int(r1), _ptr(rs), _ptr(ci), _ptr(halo), ctypes.byref(n))
+    return halo

@@ -1,0 +1,80 @@
+// context.h -- the device context behind amie_b200_ctx (one per Assembly).
+#pragma once
+#include "../../include/amie_b200.h"
+#include "common.cuh"
+#include <vector>
+#include <string>
+#include <chrono>
+
+struct DistState ;   // dist.cu
+
+struct amie_b200_ctx
+{
+    int device = 0 ;
+    int num_sms = 148 ;
+    cudaStream_t stream = nullptr ;
+    std::string err ;
+
+    // ---- matrix (device)
+    int S = 0 ;
+    uint64_t nb = 0 ;          // local block rows
+    uint64_t nb_global = 0 ;   // = nb on a single device
+    uint64_t row_base = 0 ;    // global index of local block row 0 (distributed)
+    uint64_t nnzb = 0 ;
+    uint64_t N = 0 ;           // local DOF
+    uint64_t ncols_local = 0 ; // block columns addressable by local col indices (nb + halo)
+    uint32_t * rowptr = nullptr ;
+    uint32_t * col = nullptr ;
+    double * vals = nullptr ;
+    double * dinv = nullptr ;
+    bool have_structure = false, have_values = false, dinv_valid = false ;
+    bool have_rhs = false ;
+
+    // ---- vectors (device); x-like vectors that are SpMV inputs have room for the halo tail
+    uint64_t vec_len = 0 ;     // allocated doubles per vector
+    double * b = nullptr, * x = nullptr, * r = nullptr, * z = nullptr, * p = nullptr, * q = nullptr ;
+    double * xc = nullptr, * rc = nullptr, * xmin = nullptr ;
+    double * w[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr} ;   // BiCGStab work (lazy)
+
+    KrylovState * st = nullptr ;         // device
+    KrylovState * st_host = nullptr ;    // pinned, 4 slots
+    double * partials = nullptr ;        // device, 4*AMIE_MAX_PARTIALS
+    double * partials_host = nullptr ;   // pinned
+    int * flag = nullptr ;               // device scratch
+
+    // ---- options
+    int opt_time_spmv = 0 ;
+    int opt_variant = 0 ;
+    int opt_verbose = 0 ;
+    int opt_batch = 0 ;         // iterations per speculative batch (0 = auto)
+    int opt_graph = -1 ;        // -1 auto, 0 off, 1 on
+
+    // ---- stats
+    amie_b200_stats stats {} ;
+    std::vector<cudaEvent_t> ev_pool ;
+    size_t ev_used = 0 ;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll[2] = {nullptr, nullptr} ;
+
+    DistState * dist = nullptr ;
+
+    void set_error(const std::string & e) { err = e ; }
+} ;
+
+inline double wall_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() ;
+}
+
+// internal entry points shared between translation units
+int ctx_alloc_vectors(amie_b200_ctx * ctx) ;
+int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx) ;
+int ctx_ensure_dinv(amie_b200_ctx * ctx) ;
+int ctx_sync_state(amie_b200_ctx * ctx, int slot) ;       // D2H of KrylovState into st_host[slot] + sync
+int ctx_push_state(amie_b200_ctx * ctx, const KrylovState & s) ;
+void ctx_reset_solve_stats(amie_b200_ctx * ctx) ;
+void ctx_collect_spmv_times(amie_b200_ctx * ctx) ;
+int ctx_max(amie_b200_ctx * ctx, const double * v, uint64_t n, int mode, double * out) ;
+int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t nssor,
+                      uint64_t rowstart, uint64_t colstart, uint64_t * nit_out, double * err_out, double * rho_out) ;
+int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit,
+                        uint64_t * nit_out, double * err_out) ;

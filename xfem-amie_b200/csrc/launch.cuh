@@ -1,0 +1,114 @@
+// launch.cuh -- grid sizing and launch helpers (host side, included by the .cu files).
+#pragma once
+#include "context.h"
+#include "kernels_spmv.cuh"
+#include "kernels_vec.cuh"
+
+// persistent grids: a multiple of the SM count, never more blocks than there is work, and
+// never more than the fused reductions can hold.
+static inline int vec_grid(const amie_b200_ctx * ctx, uint64_t n)
+{
+    uint64_t want = (n+AMIE_VEC_THREADS-1)/AMIE_VEC_THREADS ;
+    uint64_t cap = (uint64_t)ctx->num_sms*8 ;
+    if(cap > AMIE_MAX_PARTIALS) cap = AMIE_MAX_PARTIALS ;
+    uint64_t g = want < cap ? want : cap ;
+    return (int)(g ? g : 1) ;
+}
+
+struct SpmvCall
+{
+    const double * x = nullptr ;
+    const double * b = nullptr ;
+    double * y = nullptr ;
+    const double * w = nullptr ;
+    const double * d = nullptr ;
+    int dot = DOT_NONE ;
+    bool minus_b = false ;
+    double sign = 1. ;
+    uint64_t rowstart = 0 ;     // DOF units, multiple of S
+    uint64_t colstart = 0 ;
+    int finalize = FIN_STORE ;
+    int check_stop = 0 ;
+    bool smoothing = false ;    // stats only
+} ;
+
+static inline int persistent_grid(const amie_b200_ctx * ctx, int per_sm, uint32_t ntiles)
+{
+    if(per_sm < 1) per_sm = 1 ;
+    uint64_t cap = (uint64_t)ctx->num_sms*per_sm ;
+    if(cap > AMIE_MAX_PARTIALS) cap = AMIE_MAX_PARTIALS ;
+    uint64_t g = ntiles < cap ? ntiles : cap ;
+    return (int)(g ? g : 1) ;
+}
+
+// the occupancy query is cached per kernel instantiation (one static per expansion site)
+#define SPMV_LAUNCH(KERNEL, ROWS_PER_TILE) do { \
+        static int per_sm = 0 ; \
+        if(!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KERNEL, 256, 0) ; \
+        uint32_t ntiles = (uint32_t)((args.nrows+(ROWS_PER_TILE)-1)/(ROWS_PER_TILE)) ; \
+        int grid = persistent_grid(ctx, per_sm, ntiles) ; \
+        KERNEL<<<grid, 256, 0, ctx->stream>>>(args) ; } while(0)
+
+template<int DOT, bool MINUS_B>
+static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
+{
+    if(ctx->S == 3)
+        SPMV_LAUNCH((k_spmv_s3<DOT, MINUS_B>), 8) ;
+    else
+    {
+        // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long
+        const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
+        int G = avg > 24. ? 32 : (avg > 10. ? 16 : 8) ;
+        if(ctx->opt_variant == 8 || ctx->opt_variant == 16 || ctx->opt_variant == 32) G = ctx->opt_variant ;
+        if(G == 32)      SPMV_LAUNCH((k_spmv_s2<32, DOT, MINUS_B>), 8) ;
+        else if(G == 16) SPMV_LAUNCH((k_spmv_s2<16, DOT, MINUS_B>), 16) ;
+        else             SPMV_LAUNCH((k_spmv_s2<8, DOT, MINUS_B>), 32) ;
+    }
+}
+
+static inline int launch_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
+{
+    SpmvArgs args ;
+    args.rowptr = ctx->rowptr ; args.col = ctx->col ; args.vals = ctx->vals ;
+    args.x = c.x ; args.b = c.b ; args.y = c.y ; args.w = c.w ; args.d = c.d ;
+    args.row0 = (uint32_t)(c.rowstart/ctx->S) ;
+    args.nrows = (uint32_t)(ctx->nb-args.row0) ;
+    args.colstart_blk = (uint32_t)(c.colstart/ctx->S) ;
+    args.sign = c.sign ;
+    args.st = ctx->st ;
+    args.partials = ctx->partials ;
+    args.finalize = c.finalize ;
+    args.check_stop = c.check_stop ;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr ;
+    if(ctx->opt_time_spmv && ctx->ev_used+2 <= ctx->ev_pool.size())
+    {
+        e0 = ctx->ev_pool[ctx->ev_used++] ;
+        e1 = ctx->ev_pool[ctx->ev_used++] ;
+        cudaEventRecord(e0, ctx->stream) ;
+    }
+    if(c.dot == DOT_NONE && !c.minus_b)      spmv_dispatch<DOT_NONE, false>(ctx, args) ;
+    else if(c.dot == DOT_NONE && c.minus_b)  spmv_dispatch<DOT_NONE, true>(ctx, args) ;
+    else if(c.dot == DOT_YY && c.minus_b)    spmv_dispatch<DOT_YY, true>(ctx, args) ;
+    else if(c.dot == DOT_YX && !c.minus_b)   spmv_dispatch<DOT_YX, false>(ctx, args) ;
+    else if(c.dot == DOT_YW && !c.minus_b)   spmv_dispatch<DOT_YW, false>(ctx, args) ;
+    else if(c.dot == DOT_OMEGA && !c.minus_b) spmv_dispatch<DOT_OMEGA, false>(ctx, args) ;
+    else { ctx->set_error("launch_spmv: unsupported combination") ; return AMIE_B200_ERR_ARG ; }
+    if(e1) cudaEventRecord(e1, ctx->stream) ;
+    ctx->stats.spmv_launches++ ;
+    ctx->stats.kernel_launches++ ;
+    if(c.smoothing) ctx->stats.smoothing_spmv++ ;
+    return AMIE_B200_OK ;
+}
+
+static inline VecArgs vec_args(amie_b200_ctx * ctx, uint64_t begin, int finalize, int check_stop)
+{
+    VecArgs a ;
+    a.x = ctx->x ; a.r = ctx->r ; a.z = ctx->z ; a.p = ctx->p ; a.q = ctx->q ; a.xc = ctx->xc ; a.rc = ctx->rc ;
+    a.d = ctx->dinv ;
+    a.r_ = ctx->w[0] ; a.p_ = ctx->w[1] ; a.v = ctx->w[2] ; a.s = ctx->w[3] ; a.s_ = ctx->w[4] ; a.t = ctx->w[5] ;
+    a.begin = begin ; a.end = ctx->N ;
+    a.st = ctx->st ; a.partials = ctx->partials+AMIE_MAX_PARTIALS*2 ;
+    a.finalize = finalize ; a.check_stop = check_stop ;
+    return a ;
+}

@@ -1,0 +1,213 @@
+// solve_bicg.cu -- BiConjugateGradientStabilized::solve on the device.
+//
+// Restated from solvers/biconjugategradientstabilized.cpp:12-148.  Per iteration (:88-128):
+//     k_bicg_p  -> k_spmv (v = A p^, fused r_.v -> alpha)
+//     k_bicg_s  -> k_spmv (t = A s^, fused (D^-1 t).(D^-1 s), (D^-1 t)^2 -> omega)
+//     k_bicg_xr (x, r update; fused r.r_ -> rho, beta, the while() test, nit)
+// i.e. 2 SpMV + 3 streaming kernels against the reference's 2 SpMV + ~15 vector sweeps.
+// rowstart/colstart are ignored exactly like the reference does.
+#include "launch.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+template<typename F>
+void launch_vec(amie_b200_ctx * ctx, F f)
+{
+    f() ;
+    ctx->stats.kernel_launches++ ;
+}
+
+void queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
+{
+    const int grid = vec_grid(ctx, ctx->N) ;
+    VecArgs a = vec_args(ctx, 0, FIN_STORE, 1) ;
+    if(precond == PRECOND_JACOBI) k_bicg_p<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    else                          k_bicg_p<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    ctx->stats.kernel_launches++ ;
+    SpmvCall c ;
+    c.x = a.p_ ; c.y = a.v ; c.dot = DOT_YW ; c.w = a.r_ ; c.finalize = FIN_BICG_RV ; c.check_stop = 1 ;
+    launch_spmv(ctx, c) ;                                                           // :99-100
+    if(precond == PRECOND_JACOBI) k_bicg_s<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    else                          k_bicg_s<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    ctx->stats.kernel_launches++ ;
+    SpmvCall c2 ;
+    c2.x = a.s_ ; c2.y = a.t ; c2.dot = DOT_OMEGA ; c2.w = a.s ; c2.d = precond == PRECOND_JACOBI ? ctx->dinv : nullptr ;
+    c2.finalize = FIN_BICG_OMEGA ; c2.check_stop = 1 ;
+    launch_spmv(ctx, c2) ;                                                          // :105-115
+    VecArgs a3 = vec_args(ctx, 0, fin_xr, 1) ;
+    k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;                     // :118-120, :92-94
+    ctx->stats.kernel_launches++ ;
+}
+
+}
+
+int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, int maxit, uint64_t * nit_out, double * err_out)
+{
+    if(precond_kind != AMIE_B200_PRECOND_JACOBI && precond_kind != AMIE_B200_PRECOND_NULL)
+    {
+        ctx->set_error("bicgstab: only nullptr (InverseDiagonal) and NullPreconditionner are on the device path") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    if(precond_kind == AMIE_B200_PRECOND_NULL)
+    {
+        // With NullPreconditionner the reference's p_, s_, t__, s__ are never refreshed inside the loop
+        // (precondition() is a no-op on stale copies): a degenerate recurrence nobody calls
+        // (Assembly::cgsolve passes nullptr, solvers/assembly.cpp:1914-1915).  Not mirrored.
+        ctx->set_error("bicgstab: NullPreconditionner is degenerate in the reference and is not supported") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    const int precond = PRECOND_JACOBI ;
+    const int S = ctx->S ;
+    const uint64_t N = ctx->N ;
+    int rc ;
+    ctx_reset_solve_stats(ctx) ;
+    cudaEventRecord(ctx->ev_a, ctx->stream) ;
+    if((rc = ctx_ensure_bicg_vectors(ctx))) return rc ;
+    if(precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx))) return rc ;        // :26-34
+    const size_t vbytes = N*sizeof(double) ;
+    const double vepsilon = epsilon*1e-1 ;                                          // :16
+    uint64_t nit = 0 ;
+    double err_final = 0. ;
+
+    auto finish = [&](int r) -> int
+    {
+        cudaEventRecord(ctx->ev_b, ctx->stream) ;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream) ;
+        if(e == cudaSuccess) e = cudaGetLastError() ;
+        if(e != cudaSuccess) { ctx->set_error(std::string("bicgstab: ")+cudaGetErrorString(e)) ; return AMIE_B200_ERR_CUDA ; }
+        float ms = 0.f ;
+        cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) ;
+        ctx->stats.solve_ms = ms ;
+        ctx->stats.iterations = nit ;
+        ctx_collect_spmv_times(ctx) ;
+        if(nit_out) *nit_out = nit ;
+        if(err_out) *err_out = err_final ;
+        return r ;
+    } ;
+
+    double * r = ctx->r, * r_ = ctx->w[0], * p = ctx->p, * p_ = ctx->w[1], * v = ctx->w[2] ;
+    double * s = ctx->w[3], * s_ = ctx->w[4], * t = ctx->w[5] ;
+    const int grid = vec_grid(ctx, N) ;
+    double * vpart = ctx->partials+AMIE_MAX_PARTIALS*2 ;
+
+    // :36-37  r = -(A x - b)   (all rows, all columns)
+    {
+        SpmvCall c ;
+        c.x = ctx->x ; c.b = ctx->b ; c.y = r ; c.minus_b = true ; c.sign = -1. ;
+        if((rc = launch_spmv(ctx, c))) return rc ;
+    }
+    // :38-40  r_ = P(r) ; rho = r.r_
+    if(precond == PRECOND_JACOBI) k_precond<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(r, ctx->dinv, r_, N) ;
+    else CUDA_TRY(ctx, cudaMemcpyAsync(r_, r, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    k_dot2<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(r, r_, nullptr, 0, N, ctx->st, vpart) ;
+    ctx->stats.kernel_launches += 2 ;
+    if((rc = ctx_sync_state(ctx, 2))) return rc ;
+    double rho = ctx->st_host[2].dot[0] ;
+    if(std::fabs(rho) < vepsilon*vepsilon) return finish(1) ;                       // :43-44
+
+    // :46-48  p = r ; p_ = P(p)
+    CUDA_TRY(ctx, cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    if(precond == PRECOND_JACOBI) k_precond<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(p, ctx->dinv, p_, N) ;
+    else CUDA_TRY(ctx, cudaMemcpyAsync(p_, r, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    ctx->stats.kernel_launches++ ;
+
+    // state for the device-side scalar recurrences
+    KrylovState s0 ;
+    memset(&s0, 0, sizeof(s0)) ;
+    s0.realeps = vepsilon ;
+    s0.rho = rho ;
+    s0.nsq = (double)(int)N ;                                                       // vsize is an int (:50)
+    int64_t lastit = std::min<int64_t>(maxit, (int64_t)(int)(N*4)) ;                // :82
+    if(maxit < 0) lastit = (int64_t)N ;                                             // :83-84
+    s0.n_limit = lastit < 0 ? 0 : (uint64_t)lastit ;
+    if((rc = ctx_push_state(ctx, s0))) return rc ;
+
+    // :51-53  v = A p_ ; alpha = rho / (r_.v)
+    {
+        SpmvCall c ;
+        c.x = p_ ; c.y = v ; c.dot = DOT_YW ; c.w = r_ ; c.finalize = FIN_BICG_RV ;
+        if((rc = launch_spmv(ctx, c))) return rc ;
+    }
+    // :55  s = r - v alpha ; :65-67 s_ = P(s)
+    {
+        VecArgs a = vec_args(ctx, 0, FIN_STORE, 0) ;
+        if(precond == PRECOND_JACOBI) k_bicg_s<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+        else
+        {
+            k_bicg_s<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+            // Vector s_(s) ; precondition is a no-op -> s_ = s once, here
+            CUDA_TRY(ctx, cudaMemcpyAsync(s_, s, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
+        }
+        ctx->stats.kernel_launches++ ;
+    }
+    // :57-63  if |max(s)| < veps : x += p_ alpha ; converged
+    {
+        double smax = 0. ;
+        if((rc = ctx_max(ctx, s, N, 1, &smax))) return rc ;
+        if(std::fabs(smax) < vepsilon)
+        {
+            if((rc = ctx_sync_state(ctx, 2))) return rc ;
+            KrylovState tmp = ctx->st_host[2] ;
+            tmp.omega = 0. ;                 // x += p_ alpha + s_ * 0 ; r is not used afterwards
+            tmp.stop = 0 ;
+            if((rc = ctx_push_state(ctx, tmp))) return rc ;
+            VecArgs a3 = vec_args(ctx, 0, FIN_STORE, 0) ;
+            k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;
+            ctx->stats.kernel_launches++ ;
+            return finish(1) ;
+        }
+    }
+    // :69-74  t = A s_ ; omega
+    {
+        SpmvCall c ;
+        c.x = s_ ; c.y = t ; c.dot = DOT_OMEGA ; c.w = s ; c.d = precond == PRECOND_JACOBI ? ctx->dinv : nullptr ;
+        c.finalize = FIN_BICG_OMEGA ;
+        if((rc = launch_spmv(ctx, c))) return rc ;
+    }
+    // :75-79  x += p_ alpha + omega s_ ; r = s - t omega ; rho_ = rho ; err0 ; then the loop head (:88-94)
+    {
+        VecArgs a3 = vec_args(ctx, 0, FIN_BICG_RHO_INIT, 0) ;
+        k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;
+        ctx->stats.kernel_launches++ ;
+    }
+
+    const double iter_bytes = 2.*((double)ctx->nnzb*(8*S*S+4))+(double)N*8*30 ;
+    int batch = ctx->opt_batch > 0 ? ctx->opt_batch : (int)std::min(32., std::max(1., 300e-6/(iter_bytes/5e12))) ;
+    int slot = 0, pending = 0 ;
+    bool stopped = false ;
+    while(!stopped)
+    {
+        for(int i = 0 ; i < batch ; i++) queue_bicg_iteration(ctx, precond, FIN_BICG_RHO) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_host+slot, ctx->st, sizeof(KrylovState), cudaMemcpyDeviceToHost, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream)) ;
+        pending++ ;
+        if(pending == 2)
+        {
+            const int old = slot^1 ;
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_poll[old])) ;
+            pending-- ;
+            if(ctx->st_host[old].stop) stopped = true ;
+        }
+        slot ^= 1 ;
+    }
+    if((rc = ctx_sync_state(ctx, 2))) return rc ;
+    CUDA_TRY(ctx, cudaGetLastError()) ;
+    const KrylovState fin = ctx->st_host[2] ;
+    nit = fin.nit ;
+
+    // :133-134
+    {
+        SpmvCall c ;
+        c.x = ctx->x ; c.b = ctx->b ; c.y = r ; c.minus_b = true ; c.dot = DOT_YY ; c.finalize = FIN_STORE ;
+        if((rc = launch_spmv(ctx, c))) return rc ;
+        if((rc = ctx_sync_state(ctx, 2))) return rc ;
+        err_final = std::sqrt(ctx->st_host[2].dot[0]) ;
+    }
+    const bool ok = (int64_t)nit < lastit && std::fabs(fin.rho) <= fin.thr ;        // :147
+    if(ctx->opt_verbose)
+        fprintf(stderr, "\n BiCGStab %llu %s after %llu iterations. Error : %g\n", (unsigned long long)N,
+                ok ? "converged" : "did not converge", (unsigned long long)nit, err_final) ;
+    return finish(ok ? 1 : 0) ;
+}
