@@ -98,6 +98,8 @@ int amie_b200_upload_rhs(amie_b200_ctx * ctx, const double * b) ;               
 int amie_b200_upload_x0(amie_b200_ctx * ctx, const double * x0, uint64_t nx0) ;   /* x0 -> device (zero-filled) */
 int amie_b200_download_x(amie_b200_ctx * ctx, double * x_out) ;
 int amie_b200_download_rhs(amie_b200_ctx * ctx, double * b_out) ;
+/* work vectors, for tests: which = 0 x, 1 q (result of amie_b200_spmv_resident), 2 r, 3 p */
+int amie_b200_download_vector(amie_b200_ctx * ctx, int which, double * out) ;
 /* the matrix as held on the device, converted back to the reference layout (tests; any pointer may be NULL) */
 int amie_b200_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out,
                               double * array_padded_out) ;

@@ -21,9 +21,18 @@ for preset, n in cases:
     gen = time.time() - t0
     st = asm.stats()
     out = {"case": f"{preset}-{n}", "ndof": st.ndof, "nnzb": st.nnzb, "gen_s": round(gen, 2), "algo_MB": st.spmv_algorithmic_bytes / 1e6}
-    variants = [0] if st.stride == 3 else [8, 16, 32]
+    variants = [1, 2, 0, 3, 4, 42, 43, 52, 53, 54, 55] if st.stride == 3 else [8, 16, 32]
+    if os.environ.get('PROBE_VARIANTS'):
+        variants = [int(v) for v in os.environ['PROBE_VARIANTS'].split(',')]
+    import numpy as np
+    asm.upload_x0(np.random.default_rng(0).standard_normal(st.ndof))
+    asm.spmv_resident(reps=1, variant=1 if st.stride == 3 else 8)
+    yref = asm.download_vector(1)
     for v in variants:
         ms = asm.spmv_resident(reps=20, variant=v)
+        err = float(np.abs(asm.download_vector(1) - yref).max() / np.abs(yref).max())
+        if err > 1e-13:
+            out[f"ERR_v{v}"] = err
         out[f"spmv_ms_v{v}"] = round(ms, 4)
         out[f"spmv_GBs_v{v}"] = round(st.spmv_algorithmic_bytes / ms / 1e6, 1)
     print(json.dumps(out), flush=True)

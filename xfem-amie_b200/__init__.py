@@ -78,6 +78,7 @@ def lib():
         L.amie_b200_download_x.argtypes = [vp, vp]
         L.amie_b200_download_rhs.argtypes = [vp, vp]
         L.amie_b200_download_matrix.argtypes = [vp, vp, vp, vp]
+        L.amie_b200_download_vector.argtypes = [vp, ci, vp]
         L.amie_b200_pcg_resident.argtypes = [vp, ci, f64, ci, u64, u64, u64, vp, vp, vp]
         L.amie_b200_bicgstab_resident.argtypes = [vp, ci, f64, ci, vp, vp]
         L.amie_b200_spmv_resident.argtypes = [vp, ci, ci, vp]
@@ -193,6 +194,8 @@ class Assembly:
         """Upload structure once per topology, values whenever they changed."""
         A = self.coordinateIndexedMatrix
         L = lib()
+        if A is None:
+            return          # matrix was generated on the device (Synth.to_device)
         key = (A.stride, A.row_size.size, A.column_index.size, A.column_index.ctypes.data)
         if key != self._structure_key:
             self.check(L.amie_b200_set_structure(self.ctx, A.stride, A.row_size.size, _ptr(A.row_size),
@@ -228,6 +231,11 @@ class Assembly:
     def upload_x0(self, x0=None):
         x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
         self.check(lib().amie_b200_upload_x0(self.ctx, _ptr(x0) if x0.size else None, x0.size))
+
+    def download_vector(self, which):
+        v = np.zeros(self.stats().ndof)
+        self.check(lib().amie_b200_download_vector(self.ctx, int(which), _ptr(v)))
+        return v
 
     def download_rhs(self):
         b = np.zeros(self.stats().ndof)

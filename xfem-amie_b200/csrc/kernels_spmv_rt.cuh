@@ -1,0 +1,213 @@
+// kernels_spmv_rt.cuh -- stride-3 block-row SpMV, "row-thread" shared-memory pipeline (sm_100a).
+//
+// Third design of the K-SpMV kernel (history and ncu numbers: profiles/r01_notes.md):
+//   1. plain warp-per-row (kernels_spmv.cuh)        : right traffic, latency-bound (dependent loads)
+//   2. TMA-staged values, warp-per-row compute       : compute warps stall on the x gather and burn
+//      (kernels_spmv_tma.cuh; a variant that also      150-200 instructions per row on reduction
+//       staged x with cp.async was no better)          shuffles, predicates and pointer set-up
+//   3. this one: operands staged in shared memory by asynchronous copies, and a compute mapping
+//      with NO reduction: one THREAD per scalar row.
+//
+//   tile  = 10 consecutive block rows = 30 scalar rows = 30 lanes of ONE compute warp
+//   warp W (producer): cp.async.bulk (1D TMA) of the tile's values + column indices -> full_v[s]
+//   warps 0..W-1     : tile j of this CTA belongs to warp j % W.  G of its own tiles ahead, a warp
+//                      waits full_v of that future tile and issues 8-byte cp.async gathers
+//                      x[3 col .. 3 col + 2] -> xs[stage] for every block (lane <-> block), plus the
+//                      own-row entries of b / x / w / d it will need at the end (aux[stage]).
+//                      cp.async.wait_group<G> = "the gathers of the tile I compute now landed".
+//                      Compute: lane (row rl = lane/3, component r = lane%3) walks its row's blocks:
+//                      3 x (LDS value, LDS x, DFMA) per block; shared-memory reads are
+//                      bank-conflict-free for equal-length rows (row stride 243 doubles = 6 banks).
+//                      y store is one coalesced 240-byte write per tile; fused dot as before.
+#pragma once
+#include "kernels_spmv_tma.cuh"
+
+#define RT_ROWS 10
+
+template<int NST, int CAP>
+struct RtLayout
+{
+    static constexpr int VAL_BYTES = (CAP*72+16+15)/16*16 ;        // every region starts 16-byte aligned (TMA destinations)
+    static constexpr int COL_BYTES = (CAP*4+16+15)/16*16 ;
+    static constexpr int XS_BYTES = (CAP*24+15)/16*16 ;
+    static constexpr int AUX_BYTES = 4*32*8 ;                      // b, x, w, d of the tile's 30 scalar rows
+    static constexpr int META_BYTES = 64 ;                         // 11 row pointers + 3 words
+    static constexpr int STAGE_BYTES = (VAL_BYTES+COL_BYTES+XS_BYTES+AUX_BYTES+META_BYTES+127)/128*128 ;
+    static constexpr int META_OFF = VAL_BYTES+COL_BYTES+XS_BYTES+AUX_BYTES ;
+    static constexpr int TOTAL_BYTES = NST*STAGE_BYTES+2*NST*8+16 ;
+} ;
+
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+__global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
+{
+    if(a.check_stop && a.st->stop) return ;
+    static_assert(NST >= (G+1)*W, "stages: W tiles in compute + G*W tiles being gathered") ;
+    constexpr int R = RT_ROWS ;
+    using L = RtLayout<NST, CAP> ;
+    extern __shared__ __align__(128) unsigned char smem[] ;
+    uint64_t * full_v = reinterpret_cast<uint64_t *>(smem+NST*L::STAGE_BYTES) ;
+    uint64_t * empty = full_v+NST ;
+    const int lane = threadIdx.x & 31 ;
+    const int wid = threadIdx.x >> 5 ;
+    const uint32_t ntiles = (a.nrows+R-1)/R ;
+
+    if(threadIdx.x == 0)
+    {
+        for(int s = 0 ; s < NST ; s++)
+        {
+            mbar_init(full_v+s, 1) ;
+            mbar_init(empty+s, 1) ;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory") ;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory") ;
+    }
+    __syncthreads() ;
+
+    double dsum[2] = {0., 0.} ;
+
+    if(wid == W)
+    {
+        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF>(a, smem, full_v, empty, ntiles, lane) ;
+    }
+    else
+    {
+        const int rl = lane/3 ;                 // block row inside the tile (10 = idle lanes 30, 31)
+        const int r = lane-rl*3 ;               // row component
+
+        // tile number j (CTA-local): x of every block and the own-row aux entries -> shared memory, asynchronously
+        auto issue_gather = [&](uint32_t j)
+        {
+            const uint32_t tile = blockIdx.x+j*gridDim.x ;
+            if(tile < ntiles)
+            {
+                const int s = j%NST ;
+                unsigned char * stage = smem+s*L::STAGE_BYTES ;
+                const uint32_t * meta = reinterpret_cast<const uint32_t *>(stage+L::META_OFF) ;
+                const uint32_t r0 = a.row0+tile*R ;
+                const uint32_t nr = min((uint32_t)R, a.row0+a.nrows-r0) ;
+                double * aux = reinterpret_cast<double *>(stage+L::VAL_BYTES+L::COL_BYTES+L::XS_BYTES) ;
+                if(rl < (int)nr)
+                {
+                    const size_t i = (size_t)(r0+rl)*3+r ;
+                    if(MINUS_B) cp_async_8(aux+lane, a.b+i) ;
+                    if(DOT == DOT_YX) cp_async_8(aux+32+lane, a.x+i) ;
+                    if(DOT == DOT_YW || DOT == DOT_OMEGA) cp_async_8(aux+64+lane, a.w+i) ;
+                    if(DOT == DOT_OMEGA && a.d) cp_async_8(aux+96+lane, a.d+i) ;
+                }
+                mbar_wait(full_v+s, (j/NST) & 1u) ;
+                if(meta[R+3] != 0u)
+                {
+                    const uint32_t * cs = reinterpret_cast<const uint32_t *>(stage+L::VAL_BYTES+meta[R+2]) ;
+                    double * xs = reinterpret_cast<double *>(stage+L::VAL_BYTES+L::COL_BYTES) ;
+                    const uint32_t nblk = meta[nr]-meta[0] ;
+                    #pragma unroll 3
+                    for(uint32_t bk = lane ; bk < nblk ; bk += 32)
+                    {
+                        const double * px = a.x+(size_t)cs[bk]*3 ;
+                        double * d = xs+(size_t)bk*3 ;
+                        cp_async_8(d, px) ;
+                        cp_async_8(d+1, px+1) ;
+                        cp_async_8(d+2, px+2) ;
+                    }
+                }
+            }
+            cp_async_commit() ;
+        } ;
+
+        #pragma unroll
+        for(int g = 0 ; g < G ; g++) issue_gather(wid+g*W) ;
+
+        for(uint32_t j = wid ; blockIdx.x+j*gridDim.x < ntiles ; j += W)
+        {
+            const uint32_t tile = blockIdx.x+j*gridDim.x ;
+            issue_gather(j+G*W) ;
+            cp_async_wait_group<G>() ;
+            __syncwarp() ;
+            const int s = j%NST ;
+            const unsigned char * stage = smem+s*L::STAGE_BYTES ;
+            const uint32_t * meta = reinterpret_cast<const uint32_t *>(stage+L::META_OFF) ;
+            const double * aux = reinterpret_cast<const double *>(stage+L::VAL_BYTES+L::COL_BYTES+L::XS_BYTES) ;
+            const uint32_t r0 = a.row0+tile*R ;
+            const uint32_t nr = min((uint32_t)R, a.row0+a.nrows-r0) ;
+            const uint32_t k_lo = meta[0] ;
+            const bool staged = meta[R+3] != 0u ;
+            if(rl < (int)nr)
+            {
+                uint32_t k0 = meta[rl] ;
+                const uint32_t k1 = meta[rl+1] ;
+                double acc0 = 0., acc1 = 0., acc2 = 0. ;
+                if(staged)
+                {
+                    const uint32_t * cs = reinterpret_cast<const uint32_t *>(stage+L::VAL_BYTES+meta[R+2]) ;
+                    if(a.colstart_blk)
+                    {
+                        uint32_t lo = k0, hi = k1 ;
+                        while(lo < hi)
+                        {
+                            const uint32_t mid = lo+((hi-lo) >> 1) ;
+                            if(cs[mid-k_lo] < a.colstart_blk) lo = mid+1 ; else hi = mid ;
+                        }
+                        k0 = lo ;
+                    }
+                    const double * vs = reinterpret_cast<const double *>(stage+meta[R+1])+(size_t)(k0-k_lo)*9+r ;
+                    const double * xs = reinterpret_cast<const double *>(stage+L::VAL_BYTES+L::COL_BYTES)+(size_t)(k0-k_lo)*3 ;
+                    const uint32_t n = k1-k0 ;
+                    uint32_t t = 0 ;
+                    for( ; t+3 <= n ; t += 3)
+                    {
+                        #pragma unroll
+                        for(int q = 0 ; q < 3 ; q++)
+                        {
+                            acc0 = fma(vs[(t+q)*9], xs[(t+q)*3], acc0) ;
+                            acc1 = fma(vs[(t+q)*9+3], xs[(t+q)*3+1], acc1) ;
+                            acc2 = fma(vs[(t+q)*9+6], xs[(t+q)*3+2], acc2) ;
+                        }
+                    }
+                    for( ; t < n ; t++)
+                    {
+                        acc0 = fma(vs[t*9], xs[t*3], acc0) ;
+                        acc1 = fma(vs[t*9+3], xs[t*3+1], acc1) ;
+                        acc2 = fma(vs[t*9+6], xs[t*3+2], acc2) ;
+                    }
+                }
+                else
+                {
+                    // oversize tile (more than CAP blocks): operands straight from global memory
+                    if(a.colstart_blk) k0 = row_lower_bound(a.col, k0, k1, a.colstart_blk) ;
+                    for(uint32_t k = k0 ; k < k1 ; k++)
+                    {
+                        const double * v = a.vals+(size_t)k*9+r ;
+                        const double * px = a.x+(size_t)__ldg(a.col+k)*3 ;
+                        acc0 = fma(ld_stream(v), __ldg(px), acc0) ;
+                        acc1 = fma(ld_stream(v+3), __ldg(px+1), acc1) ;
+                        acc2 = fma(ld_stream(v+6), __ldg(px+2), acc2) ;
+                    }
+                }
+                const size_t i = (size_t)(r0+rl)*3+r ;
+                double yv = (acc0+acc1)+acc2 ;
+                if(MINUS_B) yv -= aux[lane] ;
+                yv *= a.sign ;
+                a.y[i] = yv ;
+                if(DOT == DOT_YX) dsum[0] = fma(yv, aux[32+lane], dsum[0]) ;
+                if(DOT == DOT_YY) dsum[0] = fma(yv, yv, dsum[0]) ;
+                if(DOT == DOT_YW) dsum[0] = fma(yv, aux[64+lane], dsum[0]) ;
+                if(DOT == DOT_OMEGA)
+                {
+                    const double di = a.d ? aux[96+lane] : 1. ;
+                    const double t2 = yv*di, s2 = aux[64+lane]*di ;
+                    dsum[0] = fma(t2, s2, dsum[0]) ;
+                    dsum[1] = fma(t2, t2, dsum[1]) ;
+                }
+            }
+            __syncwarp() ;
+            if(lane == 0) mbar_arrive(empty+s) ;
+        }
+        cp_async_wait_group<0>() ;
+    }
+    if(DOT != DOT_NONE)
+    {
+        double tot[2] ;
+        if(grid_sum<2, (W+1)*32>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
+            krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
+    }
+}

@@ -2,6 +2,8 @@
 #pragma once
 #include "context.h"
 #include "kernels_spmv.cuh"
+#include "kernels_spmv_tma.cuh"
+#include "kernels_spmv_rt.cuh"
 #include "kernels_vec.cuh"
 
 // persistent grids: a multiple of the SM count, never more blocks than there is work, and
@@ -49,11 +51,64 @@ static inline int persistent_grid(const amie_b200_ctx * ctx, int per_sm, uint32_
         int grid = persistent_grid(ctx, per_sm, ntiles) ; \
         KERNEL<<<grid, 256, 0, ctx->stream>>>(args) ; } while(0)
 
+// TMA-staged stride-3 kernel: R rows per tile, NST stages, CAP blocks of stage capacity
+template<int DOT, bool MINUS_B, int R, int NST, int CAP, bool PF = false>
+static inline void launch_s3_tma(amie_b200_ctx * ctx, const SpmvArgs & args)
+{
+    auto kern = k_spmv_s3_tma<DOT, MINUS_B, R, NST, CAP, PF> ;
+    constexpr int threads = PF ? 320 : 288 ;
+    constexpr int smem = TmaStageLayout<R, NST, CAP>::TOTAL_BYTES ;
+    static int per_sm = 0 ;
+    if(!per_sm)
+    {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
+        if(per_sm < 1) per_sm = 1 ;
+    }
+    const uint32_t ntiles = (args.nrows+R-1)/R ;
+    const int grid = persistent_grid(ctx, per_sm, ntiles) ;
+    kern<<<grid, threads, smem, ctx->stream>>>(args) ;
+}
+
+// row-thread pipeline: W compute warps (one 10-row tile each at a time), NST stages, CAP blocks per stage
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
+{
+    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G> ;
+    constexpr int smem = RtLayout<NST, CAP>::TOTAL_BYTES ;
+    constexpr int threads = (W+1)*32 ;
+    static int per_sm = 0 ;
+    if(!per_sm)
+    {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
+        if(per_sm < 1) per_sm = 1 ;
+    }
+    const uint32_t ntiles = (args.nrows+RT_ROWS-1)/RT_ROWS ;
+    const int grid = persistent_grid(ctx, per_sm, ntiles) ;
+    kern<<<grid, threads, smem, ctx->stream>>>(args) ;
+}
+
+#ifndef AMIE_TMA_R
+#define AMIE_TMA_R 8
+#define AMIE_TMA_NST 3
+#define AMIE_TMA_CAP 240
+#endif
+
 template<int DOT, bool MINUS_B>
 static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
     if(ctx->S == 3)
-        SPMV_LAUNCH((k_spmv_s3<DOT, MINUS_B>), 8) ;
+    {
+        // default: row-thread pipeline (a smaller-stage configuration for short rows was measured
+        // and brought nothing: profiles/r01_notes.md)
+        if(ctx->opt_variant == 1)
+            SPMV_LAUNCH((k_spmv_s3<DOT, MINUS_B>), 8) ;
+        else if(ctx->opt_variant == 2)
+            launch_s3_tma<DOT, MINUS_B, AMIE_TMA_R, AMIE_TMA_NST, AMIE_TMA_CAP>(ctx, args) ;
+        else
+            launch_s3_rt<DOT, MINUS_B, 3, 8, 270, 1>(ctx, args) ;
+    }
     else
     {
         // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long

@@ -64,8 +64,8 @@ int synth_rows_to_device(amie_b200_ctx * ctx, const SynthRecipe & R, uint64_t ro
     CUDA_TRY(ctx, cudaMemcpyAsync(&total, rowptr+nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     cudaFree(tmp) ; cudaFree(sizes) ;
-    CUDA_TRY(ctx, cudaMalloc(&col, std::max<uint64_t>(total, 1)*sizeof(uint32_t))) ;
-    CUDA_TRY(ctx, cudaMalloc(&vals, std::max<uint64_t>(total, 1)*S*S*sizeof(double))) ;
+    CUDA_TRY(ctx, cudaMalloc(&col, std::max<uint64_t>(total, 1)*sizeof(uint32_t)+16)) ;       // +16 B: see api.cu
+    CUDA_TRY(ctx, cudaMalloc(&vals, std::max<uint64_t>(total, 1)*S*S*sizeof(double)+16)) ;
     k_synth_fill<<<grid, 128, 0, ctx->stream>>>(dR, row0, nrows, rowptr, col, vals, b_dev) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     CUDA_TRY(ctx, cudaGetLastError()) ;
