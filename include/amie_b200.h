@@ -42,8 +42,9 @@ typedef struct amie_b200_ctx amie_b200_ctx ;
 
 /* ------------------------------------------------------------------ context */
 
-/* devices: CUDA ordinals; ndev == 1 (single device) in this round.  NULL/0 -> device 0
- * (or env AMIE_B200_DEVICE).  Returns NULL on failure (see amie_b200_global_error). */
+/* devices: CUDA ordinals; ndev == 1: one context drives one device (NULL/0 -> device 0 or env
+ * AMIE_B200_DEVICE).  Several GPUs = one context per device + amie_b200_dist_init (below).
+ * Returns NULL on failure (see amie_b200_global_error). */
 amie_b200_ctx * amie_b200_create(const int * devices, int ndev) ;
 void            amie_b200_destroy(amie_b200_ctx * ctx) ;
 const char *    amie_b200_last_error(const amie_b200_ctx * ctx) ;
@@ -178,6 +179,9 @@ int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_gl
                                  const uint32_t * row_size_local, const uint32_t * column_index_local,
                                  uint64_t nnzb_local) ;
 int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s) ;
+/* halo block columns received / owned block columns sent per SpMV, interior block rows, number of peers */
+int amie_b200_dist_info(const amie_b200_ctx * ctx, uint64_t * nhalo_out, uint64_t * nsend_out,
+                        uint64_t * interior_rows_out, int * npeers_out) ;
 
 #ifdef __cplusplus
 }

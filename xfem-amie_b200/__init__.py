@@ -97,6 +97,7 @@ def lib():
         L.amie_b200_dist_init.argtypes = [vp, ci, ci, vp, vp]
         L.amie_b200_dist_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
         L.amie_b200_dist_synth_to_device.argtypes = [vp, vp]
+        L.amie_b200_dist_info.argtypes = [vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -263,6 +264,29 @@ class Assembly:
         self.check(lib().amie_b200_spmv_resident(self.ctx, int(reps), int(variant), ctypes.byref(ms)))
         return ms.value
 
+    # -- row-partitioned context (one process per GPU)
+    def dist_init(self, rank, world, id128, bounds):
+        self._bounds = np.ascontiguousarray(bounds, np.uint64)
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(id128))
+        self.check(lib().amie_b200_dist_init(self.ctx, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p), _ptr(self._bounds)))
+
+    def dist_set_structure(self, stride, nb_global, row_size_local, column_index_local):
+        rs = np.ascontiguousarray(row_size_local, np.uint32)
+        ci = np.ascontiguousarray(column_index_local, np.uint32)
+        self.check(lib().amie_b200_dist_set_structure(self.ctx, int(stride), int(nb_global), _ptr(rs), _ptr(ci), ci.size))
+
+    def set_values(self, array_padded):
+        arr = np.ascontiguousarray(array_padded, np.float64)
+        self.check(lib().amie_b200_set_values(self.ctx, _ptr(arr)))
+
+    def dist_synth_to_device(self, synth):
+        self.check(lib().amie_b200_dist_synth_to_device(self.ctx, synth.handle))
+
+    def dist_info(self):
+        nh, ns, ni, npeer = u64(), u64(), u64(), ctypes.c_int()
+        self.check(lib().amie_b200_dist_info(self.ctx, ctypes.byref(nh), ctypes.byref(ns), ctypes.byref(ni), ctypes.byref(npeer)))
+        return dict(halo=nh.value, send=ns.value, interior_rows=ni.value, peers=npeer.value)
+
     def spmv(self, x, minus_b=None, rowstart=0, colstart=0):
         """assign(y, A*x [- b], rowstart, colstart)"""
         self.sync_matrix()
@@ -409,6 +433,14 @@ class Synth:
     def to_device(self, assembly):
         """Generate structure + values + rhs directly in HBM (no host arrays)."""
         assembly.check(lib().amie_b200_synth_to_device(assembly.ctx, self.handle))
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    rc = lib().amie_b200_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+    if rc:
+        raise AmieB200Error(rc, "ncclGetUniqueId (is libnccl.so.2 loadable?)")
+    return bytes(buf.raw)
 
 
 def partition_rows(row_size, nparts):

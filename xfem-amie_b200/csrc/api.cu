@@ -72,8 +72,13 @@ int ctx_ensure_dinv(amie_b200_ctx * ctx)
     if(!ctx->have_values) { ctx->set_error("inverse diagonal: no values") ; return AMIE_B200_ERR_STATE ; }
     if(!ctx->dinv) CUDA_TRY(ctx, cudaMalloc(&ctx->dinv, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
     int grid = vec_grid(ctx, ctx->N) ;
-    if(ctx->S == 3) k_inverse_diagonal<3><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else            k_inverse_diagonal<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    if(ctx->dist)
+    {
+        int rc = dist_inverse_diagonal(ctx) ;       // renumbered columns are not sorted: linear scan for the diagonal block
+        if(rc) return rc ;
+    }
+    else if(ctx->S == 3) k_inverse_diagonal<3><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else                 k_inverse_diagonal<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
     CUDA_TRY(ctx, cudaGetLastError()) ;
     ctx->stats.kernel_launches++ ;
     ctx->dinv_valid = true ;
@@ -132,6 +137,7 @@ int ctx_max(amie_b200_ctx * ctx, const double * v, uint64_t n, int mode, double 
         if(y > m || y != y) m = y ;
     }
     *out = m ;
+    if(ctx->dist) return dist_allreduce_max(ctx, out) ;
     return AMIE_B200_OK ;
 }
 
@@ -180,6 +186,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     if(!ctx) return ;
     cudaSetDevice(ctx->device) ;
     cudaStreamSynchronize(ctx->stream) ;
+    dist_destroy(ctx) ;
     free_matrix(ctx) ;
     free_vectors(ctx) ;
     dfree(ctx->st) ; dfree(ctx->partials) ; dfree(ctx->flag) ;
@@ -228,6 +235,15 @@ int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
 int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32_t * row_size,
                             const uint32_t * column_index, uint64_t nnzb)
 {
+    if(ctx && ctx->dist) { ctx->set_error("set_structure on a distributed context: use amie_b200_dist_set_structure") ; return AMIE_B200_ERR_STATE ; }
+    return ctx_set_structure(ctx, stride, nb, row_size, column_index, nnzb, nb) ;
+}
+
+}
+
+int ctx_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32_t * row_size,
+                      const uint32_t * column_index, uint64_t nnzb, uint64_t ncols)
+{
     if(!ctx || !row_size || (!column_index && nnzb)) return AMIE_B200_ERR_ARG ;
     if(stride != 2 && stride != 3)
     {
@@ -255,7 +271,7 @@ int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const 
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->col, column_index, nnzb*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
     // validate: indices in range and strictly ascending per row (binary searches depend on it)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, sizeof(int), ctx->stream)) ;
-    k_rowptr_from_sizes_check<<<vec_grid(ctx, nb), 256, 0, ctx->stream>>>(ctx->col, ctx->rowptr, nb, (uint32_t)nb, ctx->flag) ;
+    k_rowptr_from_sizes_check<<<vec_grid(ctx, nb), 256, 0, ctx->stream>>>(ctx->col, ctx->rowptr, nb, (uint32_t)ncols, ctx->flag) ;
     int bad = 0 ;
     CUDA_TRY(ctx, cudaMemcpyAsync(&bad, ctx->flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
@@ -272,6 +288,8 @@ int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const 
     ctx->stats.structure_ms = (wall_now()-t0)*1e3 ;
     return AMIE_B200_OK ;
 }
+
+extern "C" {
 
 int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
 {

@@ -30,6 +30,9 @@ struct KrylovState
     double nsq ;            // vsize (multiplied twice, as the reference does)
     // generic results of fused reductions (residual norms etc.)
     double dot[4] ;
+    // multi-GPU: per-rank partial sums of the running fused reduction, and their all-reduced values
+    double red_local[2] ;
+    double red_global[2] ;
     // control
     double realeps ;
     unsigned long long nit ;

@@ -1,24 +1,477 @@
 // dist.cu -- row-partitioned execution over the GPUs of one NVSwitch box.
-// Placeholder entry points until the halo exchange lands (this round: single device).
+//
+// One process (and one amie_b200_ctx) per GPU.  Rank r owns the contiguous block rows
+// [bounds[r], bounds[r+1]).  Local column numbering: owned columns first (c - r0), then the halo
+// (the distinct off-range columns the local rows reference, ascending = grouped by owner rank),
+// so every SpMV input vector is  [ owned N_local | halo tail ]  and a peer's contribution lands
+// in one contiguous slice of the tail -- no unpack kernel.
+//
+// Per SpMV:   pack owned entries the peers need -> grouped ncclSend/ncclRecv on a second stream,
+//             overlapped with the SpMV of the interior rows (the longest run of rows that touch no
+//             halo column; for slab partitions of a lexicographic mesh that is everything but one
+//             node plane per side) -> boundary rows after the exchange.
+// Per fused reduction: every rank's last block stores its partial sums; one ncclAllReduce of 2
+//             doubles; a one-thread kernel then runs the same scalar recurrence / loop test
+//             (krylov_scalars.cuh) on every rank, so all ranks take identical decisions and the
+//             speculative batches of iterations stay matched across ranks.
+//
+// NCCL is loaded at run time (dlopen "libnccl.so.2": the copy torch already loaded when the caller
+// is bench.py, else the system one) so that the single-GPU library has no NCCL dependency.
 #include "launch.cuh"
+#include "synth.h"
+#include "dist.h"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <thrust/device_ptr.h>
+#include <thrust/copy.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+#include <thrust/execution_policy.h>
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+struct NcclApi
+{
+    void * handle = nullptr ;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr ;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr ;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr ;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr ;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr ;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr ;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr ;
+    ncclResult_t (*GroupStart)() = nullptr ;
+    ncclResult_t (*GroupEnd)() = nullptr ;
+    const char * (*GetErrorString)(ncclResult_t) = nullptr ;
+} ;
+
+NcclApi g_nccl ;
+
+bool load_nccl(std::string & err)
+{
+    if(g_nccl.handle) return true ;
+    const char * names[] = { "libnccl.so.2", "libnccl.so" } ;
+    for(const char * n : names)
+    {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL) ;
+        if(g_nccl.handle) break ;
+    }
+    if(!g_nccl.handle) { err = std::string("dlopen libnccl.so.2: ")+dlerror() ; return false ; }
+#define NCCL_SYM(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.handle, name)) ; \
+    if(!g_nccl.field) { err = std::string("dlsym ")+name ; g_nccl.handle = nullptr ; return false ; }
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(AllGather, "ncclAllGather")
+    NCCL_SYM(Send, "ncclSend")
+    NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(GroupStart, "ncclGroupStart")
+    NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    return true ;
+}
+
+#define NCCL_TRY(ctx, expr) do { ncclResult_t _r = (expr) ; if(_r != ncclSuccess) { \
+        (ctx)->set_error(std::string(#expr)+": "+g_nccl.GetErrorString(_r)) ; return AMIE_B200_ERR_NCCL ; } } while(0)
+
+struct OffRange
+{
+    uint32_t r0, r1 ;
+    __host__ __device__ bool operator()(uint32_t c) const { return c < r0 || c >= r1 ; }
+} ;
+
+// global block column -> local: owned c - r0 ; halo nb_local + position in the sorted halo list
+__global__ void k_remap_cols(uint32_t * col, uint64_t nnzb, uint32_t r0, uint32_t r1, const uint32_t * halo, uint32_t nhalo, uint32_t nb_local)
+{
+    for(uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; k < nnzb ; k += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint32_t c = col[k] ;
+        if(c >= r0 && c < r1) col[k] = c-r0 ;
+        else
+        {
+            uint32_t lo = 0, hi = nhalo ;
+            while(lo < hi)
+            {
+                const uint32_t mid = lo+((hi-lo) >> 1) ;
+                if(halo[mid] < c) lo = mid+1 ; else hi = mid ;
+            }
+            col[k] = nb_local+lo ;
+        }
+    }
+}
+
+__global__ void k_row_touches_halo(const uint32_t * rowptr, const uint32_t * col, uint32_t nb_local, unsigned char * flag)
+{
+    for(uint64_t r = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; r < nb_local ; r += (uint64_t)gridDim.x*blockDim.x)
+    {
+        unsigned char f = 0 ;
+        for(uint32_t k = rowptr[r] ; k < rowptr[r+1] ; k++)
+            if(col[k] >= nb_local) f = 1 ;
+        flag[r] = f ;
+    }
+}
+
+template<int S>
+__global__ void k_pack(const double * v, const uint32_t * idx, uint64_t n, double * out)
+{
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n*S ; i += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint64_t k = i/S ;
+        out[i] = v[(uint64_t)idx[k]*S+(i-k*S)] ;
+    }
+}
+
+__global__ void k_finalize(KrylovState * st, int kind)
+{
+    if(kind != FIN_STORE && st->stop) return ;      // mirrors the early return of the fused kernels
+    krylov_finalize(st, kind, st->red_global[0], st->red_global[1]) ;
+}
+
+// diagonal of a row whose (remapped) column indices are no longer sorted: linear scan
+template<int S>
+__global__ void k_inverse_diagonal_linear(const uint32_t * rowptr, const uint32_t * col, const double * vals, uint64_t nrows, double * d)
+{
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < nrows*S ; i += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint32_t row = (uint32_t)(i/S) ;
+        const int m = (int)(i-(uint64_t)row*S) ;
+        double v = 0. ;
+        for(uint32_t k = rowptr[row] ; k < rowptr[row+1] ; k++)
+            if(col[k] == row) { v = vals[(size_t)k*S*S+m*S+m] ; break ; }
+        d[i] = fabs(v) > 1e-12 ? 1./v : 0. ;
+    }
+}
+
+}
+
+struct DistPeer
+{
+    int rank ;
+    uint64_t recv_off, recv_cnt ;      // block columns, offset inside the halo tail
+    uint64_t send_off, send_cnt ;      // block columns, offset inside send_idx / sendbuf
+} ;
+
+struct DistState
+{
+    int rank = 0, world = 1 ;
+    ncclComm_t comm = nullptr ;
+    cudaStream_t comm_stream = nullptr ;
+    cudaEvent_t ev_pack = nullptr, ev_comm = nullptr ;
+    std::vector<uint64_t> bounds ;
+    uint64_t nhalo = 0 ;
+    uint64_t nsend = 0 ;
+    std::vector<DistPeer> peers ;
+    uint32_t * send_idx = nullptr ;     // device: local block rows to pack
+    double * sendbuf = nullptr ;        // device
+    uint32_t int_a = 0, int_b = 0 ;     // interior block rows [a, b)
+    double * scratch = nullptr ;        // device, 2 doubles (max reductions)
+} ;
+
+int dist_world(const amie_b200_ctx * ctx) { return ctx->dist ? ctx->dist->world : 1 ; }
+
+void dist_destroy(amie_b200_ctx * ctx)
+{
+    DistState * d = ctx->dist ;
+    if(!d) return ;
+    if(d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm) ;
+    if(d->send_idx) cudaFree(d->send_idx) ;
+    if(d->sendbuf) cudaFree(d->sendbuf) ;
+    if(d->scratch) cudaFree(d->scratch) ;
+    if(d->ev_pack) cudaEventDestroy(d->ev_pack) ;
+    if(d->ev_comm) cudaEventDestroy(d->ev_comm) ;
+    if(d->comm_stream) cudaStreamDestroy(d->comm_stream) ;
+    delete d ;
+    ctx->dist = nullptr ;
+}
+
+// sum st->red_local over the ranks, then run the scalar step `kind` on every rank
+int dist_finalize(amie_b200_ctx * ctx, int kind)
+{
+    DistState * d = ctx->dist ;
+    NCCL_TRY(ctx, g_nccl.AllReduce(ctx->st->red_local, ctx->st->red_global, 2, ncclDouble, ncclSum, d->comm, ctx->stream)) ;
+    k_finalize<<<1, 1, 0, ctx->stream>>>(ctx->st, kind) ;
+    ctx->stats.kernel_launches++ ;
+    return AMIE_B200_OK ;
+}
+
+int dist_allreduce_max(amie_b200_ctx * ctx, double * value)
+{
+    DistState * d = ctx->dist ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d->scratch, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclMax, d->comm, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(value, d->scratch+1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    return AMIE_B200_OK ;
+}
+
+int dist_inverse_diagonal(amie_b200_ctx * ctx)
+{
+    int grid = vec_grid(ctx, ctx->N) ;
+    if(ctx->S == 3) k_inverse_diagonal_linear<3><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    else            k_inverse_diagonal_linear<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    CUDA_TRY(ctx, cudaGetLastError()) ;
+    return AMIE_B200_OK ;
+}
+
+// y = A x on the local rows with the halo exchange of x overlapped with the interior rows
+int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
+{
+    DistState * d = ctx->dist ;
+    if(c.rowstart || c.colstart)
+    {
+        ctx->set_error("distributed SpMV: rowstart/colstart are not supported on a row-partitioned context") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    const int S = ctx->S ;
+    double * xv = const_cast<double *>(c.x) ;
+    const bool dot = c.dot != DOT_NONE ;
+    cudaEvent_t e0 = nullptr, e1 = nullptr ;
+    if(ctx->opt_time_spmv && ctx->ev_used+2 <= ctx->ev_pool.size())
+    {
+        e0 = ctx->ev_pool[ctx->ev_used++] ;
+        e1 = ctx->ev_pool[ctx->ev_used++] ;
+        cudaEventRecord(e0, ctx->stream) ;
+    }
+    if(!d->peers.empty())
+    {
+        if(d->nsend)
+        {
+            if(S == 3) k_pack<3><<<vec_grid(ctx, d->nsend*3), 256, 0, ctx->stream>>>(xv, d->send_idx, d->nsend, d->sendbuf) ;
+            else       k_pack<2><<<vec_grid(ctx, d->nsend*2), 256, 0, ctx->stream>>>(xv, d->send_idx, d->nsend, d->sendbuf) ;
+            ctx->stats.kernel_launches++ ;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(d->ev_pack, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(d->comm_stream, d->ev_pack, 0)) ;
+        NCCL_TRY(ctx, g_nccl.GroupStart()) ;
+        for(const DistPeer & p : d->peers)
+        {
+            if(p.send_cnt) NCCL_TRY(ctx, g_nccl.Send(d->sendbuf+p.send_off*S, p.send_cnt*S, ncclDouble, p.rank, d->comm, d->comm_stream)) ;
+            if(p.recv_cnt) NCCL_TRY(ctx, g_nccl.Recv(xv+ctx->N+p.recv_off*S, p.recv_cnt*S, ncclDouble, p.rank, d->comm, d->comm_stream)) ;
+        }
+        NCCL_TRY(ctx, g_nccl.GroupEnd()) ;
+        CUDA_TRY(ctx, cudaEventRecord(d->ev_comm, d->comm_stream)) ;
+    }
+    int rc ;
+    bool first = true ;
+    auto part = [&](uint32_t a, uint32_t b) -> int
+    {
+        if(b <= a) return AMIE_B200_OK ;
+        int r = launch_spmv_range(ctx, c, a, b-a, dot ? (first ? FIN_DEFER_SET : FIN_DEFER_ADD) : FIN_STORE) ;
+        first = false ;
+        return r ;
+    } ;
+    if((rc = part(d->int_a, d->int_b))) return rc ;                       // interior rows: no halo column
+    if(!d->peers.empty()) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, d->ev_comm, 0)) ;
+    if((rc = part(0, d->int_a))) return rc ;                              // boundary rows
+    if((rc = part(d->int_b, (uint32_t)ctx->nb))) return rc ;
+    if(dot && (rc = dist_finalize(ctx, c.finalize))) return rc ;
+    if(e1) cudaEventRecord(e1, ctx->stream) ;
+    ctx->stats.spmv_launches++ ;
+    if(c.smoothing) ctx->stats.smoothing_spmv++ ;
+    return AMIE_B200_OK ;
+}
+
+// ctx->rowptr / col (GLOBAL block columns) / vals of the local rows are on the device: build the halo,
+// renumber the columns, exchange the send lists, find the interior rows, size the vectors.
+static int dist_finish_structure(amie_b200_ctx * ctx)
+{
+    DistState * d = ctx->dist ;
+    const uint32_t r0 = (uint32_t)d->bounds[d->rank], r1 = (uint32_t)d->bounds[d->rank+1] ;
+    const uint32_t nbl = r1-r0 ;
+    cudaStream_t st = ctx->stream ;
+    auto pol = thrust::cuda::par.on(st) ;
+
+    // ---- halo = sorted distinct off-range columns
+    uint32_t * tmp = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&tmp, std::max<uint64_t>(ctx->nnzb, 1)*sizeof(uint32_t))) ;
+    thrust::device_ptr<uint32_t> colp(ctx->col), tmpp(tmp) ;
+    auto end1 = thrust::copy_if(pol, colp, colp+ctx->nnzb, tmpp, OffRange{r0, r1}) ;
+    thrust::sort(pol, tmpp, end1) ;
+    auto end2 = thrust::unique(pol, tmpp, end1) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    d->nhalo = (uint64_t)(end2-tmpp) ;
+    std::vector<uint32_t> halo(d->nhalo) ;
+    CUDA_TRY(ctx, cudaMemcpy(halo.data(), tmp, d->nhalo*sizeof(uint32_t), cudaMemcpyDeviceToHost)) ;
+    k_remap_cols<<<vec_grid(ctx, ctx->nnzb), 256, 0, st>>>(ctx->col, ctx->nnzb, r0, r1, tmp, (uint32_t)d->nhalo, nbl) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    CUDA_TRY(ctx, cudaGetLastError()) ;
+    cudaFree(tmp) ;
+
+    // ---- who owns which slice of the halo
+    std::vector<long long> need(d->world, 0) ;            // block columns this rank needs from rank q
+    std::vector<uint64_t> need_off(d->world+1, 0) ;
+    for(uint64_t h = 0 ; h < d->nhalo ; h++)
+    {
+        int q = (int)(std::upper_bound(d->bounds.begin(), d->bounds.end(), (uint64_t)halo[h])-d->bounds.begin())-1 ;
+        need[q]++ ;
+    }
+    for(int q = 0 ; q < d->world ; q++) need_off[q+1] = need_off[q]+(uint64_t)need[q] ;
+
+    // ---- all ranks learn the whole need matrix; then the lists travel
+    long long * dneed = nullptr, * dall = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&dneed, d->world*sizeof(long long))) ;
+    CUDA_TRY(ctx, cudaMalloc(&dall, (size_t)d->world*d->world*sizeof(long long))) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dneed, need.data(), d->world*sizeof(long long), cudaMemcpyHostToDevice, st)) ;
+    NCCL_TRY(ctx, g_nccl.AllGather(dneed, dall, d->world, ncclInt64, d->comm, st)) ;
+    std::vector<long long> all((size_t)d->world*d->world) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), dall, all.size()*sizeof(long long), cudaMemcpyDeviceToHost, st)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    cudaFree(dneed) ; cudaFree(dall) ;
+
+    d->peers.clear() ;
+    d->nsend = 0 ;
+    for(int q = 0 ; q < d->world ; q++)
+    {
+        if(q == d->rank) continue ;
+        const uint64_t rc = (uint64_t)all[(size_t)d->rank*d->world+q] ;     // I need from q
+        const uint64_t sc = (uint64_t)all[(size_t)q*d->world+d->rank] ;     // q needs from me
+        if(rc == 0 && sc == 0) continue ;
+        DistPeer p ;
+        p.rank = q ; p.recv_off = need_off[q] ; p.recv_cnt = rc ; p.send_off = d->nsend ; p.send_cnt = sc ;
+        d->nsend += sc ;
+        d->peers.push_back(p) ;
+    }
+    if(d->send_idx) { cudaFree(d->send_idx) ; d->send_idx = nullptr ; }
+    if(d->sendbuf) { cudaFree(d->sendbuf) ; d->sendbuf = nullptr ; }
+    uint32_t * dhalo = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&d->send_idx, std::max<uint64_t>(d->nsend, 1)*sizeof(uint32_t))) ;
+    CUDA_TRY(ctx, cudaMalloc(&d->sendbuf, std::max<uint64_t>(d->nsend, 1)*ctx->S*sizeof(double))) ;
+    CUDA_TRY(ctx, cudaMalloc(&dhalo, std::max<uint64_t>(d->nhalo, 1)*sizeof(uint32_t))) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dhalo, halo.data(), d->nhalo*sizeof(uint32_t), cudaMemcpyHostToDevice, st)) ;
+    NCCL_TRY(ctx, g_nccl.GroupStart()) ;
+    for(const DistPeer & p : d->peers)
+    {
+        if(p.recv_cnt) NCCL_TRY(ctx, g_nccl.Send(dhalo+p.recv_off, p.recv_cnt, ncclUint32, p.rank, d->comm, st)) ;      // "I need these columns of yours"
+        if(p.send_cnt) NCCL_TRY(ctx, g_nccl.Recv(d->send_idx+p.send_off, p.send_cnt, ncclUint32, p.rank, d->comm, st)) ;
+    }
+    NCCL_TRY(ctx, g_nccl.GroupEnd()) ;
+    // global column -> local row of mine
+    std::vector<uint32_t> sidx(d->nsend) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(sidx.data(), d->send_idx, d->nsend*sizeof(uint32_t), cudaMemcpyDeviceToHost, st)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    for(auto & v : sidx)
+    {
+        if(v < r0 || v >= r1) { ctx->set_error("distributed structure: a peer asked for a column this rank does not own") ; return AMIE_B200_ERR_ARG ; }
+        v -= r0 ;
+    }
+    CUDA_TRY(ctx, cudaMemcpy(d->send_idx, sidx.data(), d->nsend*sizeof(uint32_t), cudaMemcpyHostToDevice)) ;
+    cudaFree(dhalo) ;
+
+    // ---- interior rows: the longest run of rows that reference no halo column
+    unsigned char * dflag = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&dflag, std::max<uint32_t>(nbl, 1))) ;
+    k_row_touches_halo<<<vec_grid(ctx, nbl), 256, 0, st>>>(ctx->rowptr, ctx->col, nbl, dflag) ;
+    std::vector<unsigned char> flag(nbl) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(flag.data(), dflag, nbl, cudaMemcpyDeviceToHost, st)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    cudaFree(dflag) ;
+    uint32_t best_a = 0, best_b = 0, run = 0 ;
+    for(uint32_t r = 0 ; r <= nbl ; r++)
+    {
+        if(r < nbl && !flag[r]) { run++ ; continue ; }
+        if(run > best_b-best_a) { best_a = r-run ; best_b = r ; }
+        run = 0 ;
+    }
+    d->int_a = best_a ; d->int_b = best_b ;
+
+    ctx->ncols_local = (uint64_t)nbl+d->nhalo ;
+    return ctx_alloc_vectors(ctx) ;
+}
 
 extern "C" {
 
-int amie_b200_nccl_unique_id(void *) { return AMIE_B200_ERR_UNSUPPORTED ; }
-int amie_b200_dist_init(amie_b200_ctx * ctx, int, int, const void *, const uint64_t *)
+int amie_b200_nccl_unique_id(void * id128_out)
 {
-    if(ctx) ctx->set_error("distributed context: not built yet") ;
-    return AMIE_B200_ERR_UNSUPPORTED ;
+    std::string err ;
+    if(!id128_out || !load_nccl(err)) return AMIE_B200_ERR_NCCL ;
+    ncclUniqueId id ;
+    if(g_nccl.GetUniqueId(&id) != ncclSuccess) return AMIE_B200_ERR_NCCL ;
+    memcpy(id128_out, &id, sizeof(id)) ;
+    return AMIE_B200_OK ;
 }
-int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int, uint64_t, const uint32_t *, const uint32_t *, uint64_t)
+
+int amie_b200_dist_init(amie_b200_ctx * ctx, int rank, int world, const void * id128, const uint64_t * bounds)
 {
-    if(ctx) ctx->set_error("distributed context: not built yet") ;
-    return AMIE_B200_ERR_UNSUPPORTED ;
+    if(!ctx || !id128 || !bounds || world < 1 || rank < 0 || rank >= world) return AMIE_B200_ERR_ARG ;
+    std::string err ;
+    if(!load_nccl(err)) { ctx->set_error(err) ; return AMIE_B200_ERR_NCCL ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    dist_destroy(ctx) ;
+    DistState * d = new DistState ;
+    ctx->dist = d ;
+    d->rank = rank ; d->world = world ;
+    d->bounds.assign(bounds, bounds+world+1) ;
+    ncclUniqueId id ;
+    memcpy(&id, id128, sizeof(id)) ;
+    NCCL_TRY(ctx, g_nccl.CommInitRank(&d->comm, world, id, rank)) ;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking)) ;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&d->ev_pack, cudaEventDisableTiming)) ;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&d->ev_comm, cudaEventDisableTiming)) ;
+    CUDA_TRY(ctx, cudaMalloc(&d->scratch, 2*sizeof(double))) ;
+    return AMIE_B200_OK ;
 }
-int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth *)
+
+int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_global,
+                                 const uint32_t * row_size_local, const uint32_t * column_index_local, uint64_t nnzb_local)
 {
-    if(ctx) ctx->set_error("distributed context: not built yet") ;
-    return AMIE_B200_ERR_UNSUPPORTED ;
+    if(!ctx || !ctx->dist) return AMIE_B200_ERR_STATE ;
+    DistState * d = ctx->dist ;
+    if(d->bounds.back() != nb_global) { ctx->set_error("dist_set_structure: bounds do not cover nb_global") ; return AMIE_B200_ERR_ARG ; }
+    const uint64_t nbl = d->bounds[d->rank+1]-d->bounds[d->rank] ;
+    // upload through the single-device path with GLOBAL columns (range check against nb_global), then renumber
+    int rc = ctx_set_structure(ctx, stride, nbl, row_size_local, column_index_local, nnzb_local, nb_global) ;
+    if(rc) return rc ;
+    ctx->nb_global = nb_global ;
+    ctx->row_base = d->bounds[d->rank] ;
+    return dist_finish_structure(ctx) ;
+}
+
+int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s)
+{
+    if(!ctx || !s || !ctx->dist) return AMIE_B200_ERR_STATE ;
+    DistState * d = ctx->dist ;
+    const SynthRecipe & R = *synth_recipe_of(s) ;
+    const uint64_t nbg = synth_num_nodes(R) ;
+    if(d->bounds.back() != nbg) { ctx->set_error("dist_synth_to_device: bounds do not cover the mesh") ; return AMIE_B200_ERR_ARG ; }
+    const uint64_t r0 = d->bounds[d->rank], r1 = d->bounds[d->rank+1] ;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    if(ctx->rowptr) { cudaFree(ctx->rowptr) ; ctx->rowptr = nullptr ; }
+    if(ctx->col) { cudaFree(ctx->col) ; ctx->col = nullptr ; }
+    if(ctx->vals) { cudaFree(ctx->vals) ; ctx->vals = nullptr ; }
+    if(ctx->dinv) { cudaFree(ctx->dinv) ; ctx->dinv = nullptr ; }
+    ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
+    ctx->S = R.stride ; ctx->nb = r1-r0 ; ctx->nb_global = nbg ; ctx->row_base = r0 ; ctx->N = ctx->nb*R.stride ;
+    ctx->ncols_local = ctx->nb ;
+    // b lives in the vectors: allocate them for the owned part first (re-sized once the halo is known)
+    double * btmp = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&btmp, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
+    uint64_t nnzb = 0 ;
+    int rc = synth_rows_to_device(ctx, R, r0, r1, &ctx->rowptr, &ctx->col, &ctx->vals, btmp, &nnzb) ;
+    if(rc) { cudaFree(btmp) ; return rc ; }
+    ctx->nnzb = nnzb ;
+    ctx->have_structure = ctx->have_values = true ;
+    rc = dist_finish_structure(ctx) ;
+    if(rc) { cudaFree(btmp) ; return rc ; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->b, btmp, ctx->N*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    cudaFree(btmp) ;
+    ctx->have_rhs = true ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_dist_info(const amie_b200_ctx * ctx, uint64_t * nhalo_out, uint64_t * nsend_out, uint64_t * interior_rows_out, int * npeers_out)
+{
+    if(!ctx || !ctx->dist) return AMIE_B200_ERR_STATE ;
+    if(nhalo_out) *nhalo_out = ctx->dist->nhalo ;
+    if(nsend_out) *nsend_out = ctx->dist->nsend ;
+    if(interior_rows_out) *interior_rows_out = ctx->dist->int_b-ctx->dist->int_a ;
+    if(npeers_out) *npeers_out = (int)ctx->dist->peers.size() ;
+    return AMIE_B200_OK ;
 }
 
 }

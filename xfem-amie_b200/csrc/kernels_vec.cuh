@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_smooth(VecArgs a)
     }
     double tot[1] ;
     if(grid_sum<1, AMIE_VEC_THREADS>(sum, a.partials, a.st->ticket+TICKET_MISC, tot) && threadIdx.x == 0)
-        krylov_finalize(a.st, FIN_STORE, tot[0], 0.) ;
+        krylov_finalize(a.st, a.finalize, tot[0], 0.) ;
 }
 
 template<int PRECOND>
@@ -156,8 +156,8 @@ static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_bicg_xr(VecArgs a)
     double tot[2] ;
     if(grid_sum<2, AMIE_VEC_THREADS>(sum, a.partials, a.st->ticket+TICKET_UPDATE, tot) && threadIdx.x == 0)
     {
-        if(a.finalize == FIN_STORE)
-            krylov_finalize(a.st, FIN_STORE, tot[0], tot[1]) ;
+        if(a.finalize == FIN_STORE || a.finalize == FIN_DEFER_SET)
+            krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
         else
         {
             a.st->dot[1] = tot[1] ;
@@ -168,7 +168,7 @@ static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_bicg_xr(VecArgs a)
 
 // generic fused dot products on [begin,end): sums u.v and (optionally) u.w
 static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_dot2(const double * u, const double * v, const double * w,
-                                                          uint64_t begin, uint64_t end, KrylovState * st, double * partials)
+                                                          uint64_t begin, uint64_t end, KrylovState * st, double * partials, int finalize)
 {
     double sum[2] = {0., 0.} ;
     for(uint64_t i = begin+(uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < end ; i += (uint64_t)gridDim.x*blockDim.x)
@@ -179,7 +179,7 @@ static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_dot2(const double *
     }
     double tot[2] ;
     if(grid_sum<2, AMIE_VEC_THREADS>(sum, partials, st->ticket+TICKET_MISC, tot) && threadIdx.x == 0)
-        krylov_finalize(st, FIN_STORE, tot[0], tot[1]) ;
+        krylov_finalize(st, finalize, tot[0], tot[1]) ;
 }
 
 // out = D^-1 in  (InverseDiagonal::precondition, solvers/inversediagonal.cpp:62-67)

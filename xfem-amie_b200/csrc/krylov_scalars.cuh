@@ -18,6 +18,8 @@ enum
     FIN_BICG_OMEGA,          // omega = (t''.s'')/(t''.t'')                          (:115)
     FIN_BICG_RHO,            // rho_ = rho ; while() test ; nit++ ; rho ; beta       (:120, :88-94)
     FIN_BICG_RHO_INIT,       // same after the start-up half step, plus err0 and the threshold (:77-79)
+    FIN_DEFER_SET,           // multi-GPU: red_local = (a, b); the scalar step runs after the all-reduce (dist.cu)
+    FIN_DEFER_ADD,           // multi-GPU: red_local += (a, b)   (second / third row range of one SpMV)
 } ;
 
 #if defined(__CUDACC__)
@@ -39,6 +41,14 @@ __device__ __forceinline__ void krylov_finalize(KrylovState * st, int kind, doub
 {
     switch(kind)
     {
+    case FIN_DEFER_SET :
+        st->red_local[0] = a ;
+        st->red_local[1] = b ;
+        break ;
+    case FIN_DEFER_ADD :
+        st->red_local[0] += a ;
+        st->red_local[1] += b ;
+        break ;
     case FIN_STORE :
         st->dot[0] = a ;
         st->dot[1] = b ;

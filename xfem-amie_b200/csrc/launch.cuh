@@ -1,6 +1,7 @@
 // launch.cuh -- grid sizing and launch helpers (host side, included by the .cu files).
 #pragma once
 #include "context.h"
+#include "dist.h"
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
 #include "kernels_spmv_rt.cuh"
@@ -121,27 +122,20 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
     }
 }
 
-static inline int launch_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
+// block rows [blk_row0, blk_row0+blk_nrows) of the local matrix; `finalize` overrides c.finalize
+static inline int launch_spmv_range(amie_b200_ctx * ctx, const SpmvCall & c, uint32_t blk_row0, uint32_t blk_nrows, int finalize)
 {
     SpmvArgs args ;
     args.rowptr = ctx->rowptr ; args.col = ctx->col ; args.vals = ctx->vals ;
     args.x = c.x ; args.b = c.b ; args.y = c.y ; args.w = c.w ; args.d = c.d ;
-    args.row0 = (uint32_t)(c.rowstart/ctx->S) ;
-    args.nrows = (uint32_t)(ctx->nb-args.row0) ;
+    args.row0 = blk_row0 ;
+    args.nrows = blk_nrows ;
     args.colstart_blk = (uint32_t)(c.colstart/ctx->S) ;
     args.sign = c.sign ;
     args.st = ctx->st ;
     args.partials = ctx->partials ;
-    args.finalize = c.finalize ;
+    args.finalize = finalize ;
     args.check_stop = c.check_stop ;
-
-    cudaEvent_t e0 = nullptr, e1 = nullptr ;
-    if(ctx->opt_time_spmv && ctx->ev_used+2 <= ctx->ev_pool.size())
-    {
-        e0 = ctx->ev_pool[ctx->ev_used++] ;
-        e1 = ctx->ev_pool[ctx->ev_used++] ;
-        cudaEventRecord(e0, ctx->stream) ;
-    }
     if(c.dot == DOT_NONE && !c.minus_b)      spmv_dispatch<DOT_NONE, false>(ctx, args) ;
     else if(c.dot == DOT_NONE && c.minus_b)  spmv_dispatch<DOT_NONE, true>(ctx, args) ;
     else if(c.dot == DOT_YY && c.minus_b)    spmv_dispatch<DOT_YY, true>(ctx, args) ;
@@ -149,12 +143,33 @@ static inline int launch_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
     else if(c.dot == DOT_YW && !c.minus_b)   spmv_dispatch<DOT_YW, false>(ctx, args) ;
     else if(c.dot == DOT_OMEGA && !c.minus_b) spmv_dispatch<DOT_OMEGA, false>(ctx, args) ;
     else { ctx->set_error("launch_spmv: unsupported combination") ; return AMIE_B200_ERR_ARG ; }
+    ctx->stats.kernel_launches++ ;
+    return AMIE_B200_OK ;
+}
+
+static inline int launch_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
+{
+    if(ctx->dist) return dist_spmv(ctx, c) ;
+    cudaEvent_t e0 = nullptr, e1 = nullptr ;
+    if(ctx->opt_time_spmv && ctx->ev_used+2 <= ctx->ev_pool.size())
+    {
+        e0 = ctx->ev_pool[ctx->ev_used++] ;
+        e1 = ctx->ev_pool[ctx->ev_used++] ;
+        cudaEventRecord(e0, ctx->stream) ;
+    }
+    const uint32_t row0 = (uint32_t)(c.rowstart/ctx->S) ;
+    int rc = launch_spmv_range(ctx, c, row0, (uint32_t)(ctx->nb-row0), c.finalize) ;
+    if(rc) return rc ;
     if(e1) cudaEventRecord(e1, ctx->stream) ;
     ctx->stats.spmv_launches++ ;
-    ctx->stats.kernel_launches++ ;
     if(c.smoothing) ctx->stats.smoothing_spmv++ ;
     return AMIE_B200_OK ;
 }
+
+// fused reductions of the vector kernels: on one device the last block runs the scalar step itself;
+// on a row-partitioned context it only stores the rank's partial sums and dist_finalize() follows
+static inline int fin_kind(const amie_b200_ctx * ctx, int kind) { return ctx->dist ? FIN_DEFER_SET : kind ; }
+static inline int after_reduce(amie_b200_ctx * ctx, int kind) { return ctx->dist ? dist_finalize(ctx, kind) : AMIE_B200_OK ; }
 
 static inline VecArgs vec_args(amie_b200_ctx * ctx, uint64_t begin, int finalize, int check_stop)
 {

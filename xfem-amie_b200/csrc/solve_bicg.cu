@@ -36,9 +36,10 @@ void queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
     c2.x = a.s_ ; c2.y = a.t ; c2.dot = DOT_OMEGA ; c2.w = a.s ; c2.d = precond == PRECOND_JACOBI ? ctx->dinv : nullptr ;
     c2.finalize = FIN_BICG_OMEGA ; c2.check_stop = 1 ;
     launch_spmv(ctx, c2) ;                                                          // :105-115
-    VecArgs a3 = vec_args(ctx, 0, fin_xr, 1) ;
+    VecArgs a3 = vec_args(ctx, 0, fin_kind(ctx, fin_xr), 1) ;
     k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;                     // :118-120, :92-94
     ctx->stats.kernel_launches++ ;
+    after_reduce(ctx, fin_xr) ;
 }
 
 }
@@ -101,8 +102,9 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     // :38-40  r_ = P(r) ; rho = r.r_
     if(precond == PRECOND_JACOBI) k_precond<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(r, ctx->dinv, r_, N) ;
     else CUDA_TRY(ctx, cudaMemcpyAsync(r_, r, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
-    k_dot2<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(r, r_, nullptr, 0, N, ctx->st, vpart) ;
+    k_dot2<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(r, r_, nullptr, 0, N, ctx->st, vpart, fin_kind(ctx, FIN_STORE)) ;
     ctx->stats.kernel_launches += 2 ;
+    if((rc = after_reduce(ctx, FIN_STORE))) return rc ;
     if((rc = ctx_sync_state(ctx, 2))) return rc ;
     double rho = ctx->st_host[2].dot[0] ;
     if(std::fabs(rho) < vepsilon*vepsilon) return finish(1) ;                       // :43-44
@@ -118,9 +120,10 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     memset(&s0, 0, sizeof(s0)) ;
     s0.realeps = vepsilon ;
     s0.rho = rho ;
-    s0.nsq = (double)(int)N ;                                                       // vsize is an int (:50)
-    int64_t lastit = std::min<int64_t>(maxit, (int64_t)(int)(N*4)) ;                // :82
-    if(maxit < 0) lastit = (int64_t)N ;                                             // :83-84
+    const uint64_t Nglob = ctx->nb_global*(uint64_t)S ;                             // getForces().size(): the GLOBAL size when row-partitioned
+    s0.nsq = (double)(int)Nglob ;                                                   // vsize is an int (:50)
+    int64_t lastit = std::min<int64_t>(maxit, (int64_t)(int)(Nglob*4)) ;            // :82
+    if(maxit < 0) lastit = (int64_t)Nglob ;                                         // :83-84
     s0.n_limit = lastit < 0 ? 0 : (uint64_t)lastit ;
     if((rc = ctx_push_state(ctx, s0))) return rc ;
 
@@ -153,9 +156,10 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
             tmp.omega = 0. ;                 // x += p_ alpha + s_ * 0 ; r is not used afterwards
             tmp.stop = 0 ;
             if((rc = ctx_push_state(ctx, tmp))) return rc ;
-            VecArgs a3 = vec_args(ctx, 0, FIN_STORE, 0) ;
+            VecArgs a3 = vec_args(ctx, 0, fin_kind(ctx, FIN_STORE), 0) ;
             k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;
             ctx->stats.kernel_launches++ ;
+            if((rc = after_reduce(ctx, FIN_STORE))) return rc ;
             return finish(1) ;
         }
     }
@@ -168,9 +172,10 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     }
     // :75-79  x += p_ alpha + omega s_ ; r = s - t omega ; rho_ = rho ; err0 ; then the loop head (:88-94)
     {
-        VecArgs a3 = vec_args(ctx, 0, FIN_BICG_RHO_INIT, 0) ;
+        VecArgs a3 = vec_args(ctx, 0, fin_kind(ctx, FIN_BICG_RHO_INIT), 0) ;
         k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;
         ctx->stats.kernel_launches++ ;
+        if((rc = after_reduce(ctx, FIN_BICG_RHO_INIT))) return rc ;
     }
 
     const double iter_bytes = 2.*((double)ctx->nnzb*(8*S*S+4))+(double)N*8*30 ;

@@ -23,7 +23,7 @@ struct CgRun
 int launch_dir(const CgRun & R, bool first)
 {
     amie_b200_ctx * ctx = R.ctx ;
-    VecArgs a = vec_args(ctx, first ? 0 : R.rowstart, first ? FIN_CG_RHO0 : FIN_STORE, first ? 0 : 1) ;
+    VecArgs a = vec_args(ctx, first ? 0 : R.rowstart, first ? fin_kind(ctx, FIN_CG_RHO0) : FIN_STORE, first ? 0 : 1) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
     if(first)
     {
@@ -31,6 +31,8 @@ int launch_dir(const CgRun & R, bool first)
         // r is 0 on [0, rowstart) so those entries add nothing to the sum.
         if(R.precond == PRECOND_JACOBI) k_cg_dir<PRECOND_JACOBI, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
         else                            k_cg_dir<PRECOND_NULL, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+        ctx->stats.kernel_launches++ ;
+        return after_reduce(ctx, FIN_CG_RHO0) ;
     }
     else
     {
@@ -44,23 +46,24 @@ int launch_dir(const CgRun & R, bool first)
 int launch_update(const CgRun & R, bool first)
 {
     amie_b200_ctx * ctx = R.ctx ;
-    VecArgs a = vec_args(ctx, R.rowstart, first ? FIN_CG_RHO_FIRST : FIN_CG_RHO, 1) ;
+    const int kind = first ? FIN_CG_RHO_FIRST : FIN_CG_RHO ;
+    VecArgs a = vec_args(ctx, R.rowstart, fin_kind(ctx, kind), 1) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
     if(R.precond == PRECOND_JACOBI) k_cg_update<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     else                            k_cg_update<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     ctx->stats.kernel_launches++ ;
-    return AMIE_B200_OK ;
+    return after_reduce(ctx, kind) ;
 }
 
 int launch_smooth(const CgRun & R)
 {
     amie_b200_ctx * ctx = R.ctx ;
-    VecArgs a = vec_args(ctx, R.rowstart, FIN_STORE, 0) ;
+    VecArgs a = vec_args(ctx, R.rowstart, fin_kind(ctx, FIN_STORE), 0) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
     if(R.precond == PRECOND_JACOBI) k_smooth<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     else                            k_smooth<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     ctx->stats.kernel_launches++ ;
-    return AMIE_B200_OK ;
+    return after_reduce(ctx, FIN_STORE) ;
 }
 
 // r = sign (A x - b) on rows >= rowstart, fused |r|^2 -> *norm
@@ -148,7 +151,9 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     if(R.precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx))) return rc ;
 
     const double realeps = std::max(1e-12, eps) ;                                   // :92
-    const uint64_t Maxit = (maxit != -1) ? (uint64_t)(int64_t)maxit : N/2 ;         // :93
+    // getForces().size() is the GLOBAL system size on a row-partitioned context
+    const uint64_t Nglob = ctx->nb_global*(uint64_t)S ;
+    const uint64_t Maxit = (maxit != -1) ? (uint64_t)(int64_t)maxit : Nglob/2 ;     // :93
     // :95-104 x = x0 was done by the caller (upload) ; :106-111
     if(rowstart) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->x, ctx->b, rowstart*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
     // assign() writes 0 to rows < rowstart on every call; the vectors keep those zeros because no
@@ -202,7 +207,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         s0.realeps = realeps ;
         s0.nit = nit ;
         s0.localnit = 0 ;
-        s0.n_limit = N ;                                                            // localnit < getForces().size()  (:218)
+        s0.n_limit = Nglob ;                                                        // localnit < getForces().size()  (:218)
         if((rc = ctx_push_state(ctx, s0))) return rc ;
 
         launch_dir(R, true) ;                                                       // :183-186, :189
@@ -256,7 +261,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         if(nssor)                                                                   // :274-302
         {
             uint64_t iters = 0 ;
-            while(err > realeps && iters++ < N)
+            while(err > realeps && iters++ < Nglob)
             {
                 double dummy ;
                 if((rc = residual(R, 1., colstart, true, &dummy))) return rc ;      // :279
@@ -280,8 +285,9 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     }
     // :314-317
     {
-        k_dot2<<<vec_grid(ctx, N-rowstart), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->r, ctx->r, nullptr, rowstart, N, ctx->st, ctx->partials+AMIE_MAX_PARTIALS*2) ;
+        k_dot2<<<vec_grid(ctx, N-rowstart), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->r, ctx->r, nullptr, rowstart, N, ctx->st, ctx->partials+AMIE_MAX_PARTIALS*2, fin_kind(ctx, FIN_STORE)) ;
         ctx->stats.kernel_launches++ ;
+        if((rc = after_reduce(ctx, FIN_STORE))) return rc ;
         if((rc = ctx_sync_state(ctx, 2))) return rc ;
         err_final = std::sqrt(ctx->st_host[2].dot[0]) ;
         rho_final = err_final ;
