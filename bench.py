@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("AMIE_BENCH_N", 256)), help="nodes per side of S3-hex-n (256 -> 50.3 M DOF)")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=int(os.environ.get("AMIE_BENCH_N", 256)), help="nodes per side of S3-hex-n (256 -> 50.3 M DOF)")
     ap.add_argument("--preset", default="S3-hex")
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("AMIE_BENCH_CPU_N", 64)), help="size of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _solve_rank(pkg, syn, rank, world, id128, bounds, device, bicg=False, x0=None):
+def _solve_rank(pkg, syn, rank, world, id128, bounds, device, bicg=False, x0=None, id128_b=None):
     s = syn.stride
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     rs, ci, arr, b = syn.rows(r0, r1)
@@ -29,14 +29,16 @@ def _solve_rank(pkg, syn, rank, world, id128, bounds, device, bicg=False, x0=Non
         ok, nit, err, rho = asm.pcg_resident(nssor=32)
     x = asm.download_x()
     info = asm.dist_info()
-    # the device generator must give the same partitioned system
+    asm.close()
+    if id128_b is None:
+        return ok, nit, x, info, None
+    # the device generator must give the same partitioned system (a ncclUniqueId serves ONE communicator)
     asm2 = pkg.Assembly(device=device)
-    asm2.dist_init(rank, world, id128, bounds)
+    asm2.dist_init(rank, world, id128_b, bounds)
     asm2.dist_synth_to_device(syn)
     asm2.upload_x0(None)
     ok2, nit2, _, _ = asm2.pcg_resident(nssor=32)
     x2 = asm2.download_x()
-    asm.close()
     asm2.close()
     return ok, nit, x, info, (ok2, nit2, x2)
 
@@ -46,7 +48,7 @@ def test_dist_world1(pkg, ol, systems, preset, n):
     syn = pkg.Synth(preset, n)
     S = systems(preset, n)
     bounds = np.array([0, syn.nb], np.uint64)
-    ok, nit, x, info, (ok2, nit2, x2) = _solve_rank(pkg, syn, 0, 1, pkg.nccl_unique_id(), bounds, 0)
+    ok, nit, x, info, (ok2, nit2, x2) = _solve_rank(pkg, syn, 0, 1, pkg.nccl_unique_id(), bounds, 0, id128_b=pkg.nccl_unique_id())
     ret, x_ref, oinfo = ol.oracle_cg(S, nssor=32)
     assert ok == bool(ret) and abs(int(nit) - int(oinfo.nit)) <= 2
     assert rel_l2(x, x_ref) <= 1e-8
@@ -79,12 +81,14 @@ def _worker2(rank, world, port, preset, n, out):
     syn = pkg.Synth(preset, n)
     rs, _ = syn.row_sizes()
     bounds = pkg.partition_rows(rs, world)
-    idt = torch.zeros(128, dtype=torch.uint8)
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    ok, nit, x, info, (ok2, nit2, x2) = _solve_rank(pkg, syn, rank, world, idt.numpy().tobytes(), bounds, rank)
-    okb, nitb, xb, _, _ = _solve_rank(pkg, syn, rank, world, idt.numpy().tobytes(), bounds, rank, bicg=True)
+    def fresh_id():
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return idt.numpy().tobytes()
+    ok, nit, x, info, (ok2, nit2, x2) = _solve_rank(pkg, syn, rank, world, fresh_id(), bounds, rank, id128_b=fresh_id())
+    okb, nitb, xb, _, _ = _solve_rank(pkg, syn, rank, world, fresh_id(), bounds, rank, bicg=True)
     out[rank] = (ok, nit, x, info, ok2, nit2, x2, okb, nitb, xb, int(bounds[rank]), int(bounds[rank + 1]))
     dist.barrier()
     dist.destroy_process_group()

@@ -21,6 +21,9 @@ NIT_TOL = 2           # iterations
 SPMV_TOL = 1e-13
 
 CASES = [("S3-hex", 12), ("S3-hex", 20), ("S3-tet", 14), ("S2-tri", 40), ("ASR-hex", 12)]
+# big enough that every CTA of the persistent grids walks its stage ring many times (a stage-reuse race in
+# the fused dot products went unnoticed on the small cases above)
+LARGE = [("S3-hex", 44), ("S3-tet", 44), ("S2-tri", 256)]
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
@@ -83,6 +86,34 @@ def test_pcg_parity(pkg, ol, systems, asm_cache, preset, n):
     # true residual of the returned field
     A = S.to_scipy()
     assert np.linalg.norm(A @ cg.x - S.b) <= 10 * max(np.linalg.norm(A @ x_ref - S.b), 1e-10)
+
+
+@pytest.mark.parametrize("preset,n", LARGE)
+def test_pcg_parity_large_and_reproducible(pkg, ol, systems, preset, n):
+    S = systems(preset, n)
+    asm = assembly_of(pkg, S)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    runs = []
+    for variant in (0, 0, 1):
+        asm.set_option("spmv_variant", variant)
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor = 32
+        ok = cg.solve(None, None, 1e-10, -1)
+        assert ok == bool(ret)
+        assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (variant, cg.nit, info.nit)
+        assert rel_l2(cg.x, x_ref) <= X_TOL
+        runs.append((cg.nit, cg.x.copy()))
+    # deterministic reductions: the same kernel gives the same bits run to run
+    assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    asm.set_option("spmv_variant", 0)
+    reti, xi_ref, _ = ol.oracle_bicgstab(S)
+    assert bi.solve() == bool(reti)
+    assert rel_l2(bi.x, xi_ref) <= X_TOL
+    x1 = bi.x.copy()
+    bi.solve()
+    assert np.array_equal(x1, bi.x)
+    asm.close()
 
 
 @pytest.mark.parametrize("kw", [dict(nssor=0), dict(nssor=128), dict(nssor=32, eps=1e-6), dict(nssor=32, eps=1e-13),

@@ -86,6 +86,10 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
                 const uint32_t r0 = a.row0+tile*R ;
                 const uint32_t nr = min((uint32_t)R, a.row0+a.nrows-r0) ;
                 double * aux = reinterpret_cast<double *>(stage+L::VAL_BYTES+L::COL_BYTES+L::XS_BYTES) ;
+                // full_v[s] of this phase also says the stage is FREE: the producer only refills it after the
+                // warp that computed its previous tile arrived on empty[s].  Nothing may be written into the
+                // stage (aux included) before this wait.
+                mbar_wait(full_v+s, (j/NST) & 1u) ;
                 if(rl < (int)nr)
                 {
                     const size_t i = (size_t)(r0+rl)*3+r ;
@@ -94,7 +98,6 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
                     if(DOT == DOT_YW || DOT == DOT_OMEGA) cp_async_8(aux+64+lane, a.w+i) ;
                     if(DOT == DOT_OMEGA && a.d) cp_async_8(aux+96+lane, a.d+i) ;
                 }
-                mbar_wait(full_v+s, (j/NST) & 1u) ;
                 if(meta[R+3] != 0u)
                 {
                     const uint32_t * cs = reinterpret_cast<const uint32_t *>(stage+L::VAL_BYTES+meta[R+2]) ;
