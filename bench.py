@@ -95,7 +95,8 @@ def cpu_reference_rate(pkg, n_cpu, threads=0):
     rs, ci, arr, b = syn.rows()
     S = ol.Sys(syn.stride, syn.nb, rs, ci, arr, b)
     if ol.ref() is not None:
-        cores = threads or ol.ref_max_threads()
+        # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on
+        cores = threads or len(os.sched_getaffinity(0)) or ol.ref_max_threads()
         ok, x, nit, wall, _ = ol.ref_cg(S, nssor=32, nthreads=cores)
         kind = "reference"
     else:

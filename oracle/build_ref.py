@@ -74,6 +74,26 @@ def main():
     subprocess.check_call([CXX, *FLAGS, "-shared", "-I" + REF, os.path.join(HERE, "ref_harness.cpp"),
                            lib, "-Wl,--no-undefined", "-lm", "-o", so])
     print("[build_ref] built", so, f"({len(objs)} reference objects)")
+
+    # ---- end-to-end pair: the SAME FeatureTree driver linked with the reference solvers / with the drop-in TUs
+    harness = os.path.join(HERE, "e2e_harness.cpp")
+    e2e_ref = os.path.join(OUT, "amie_e2e_ref")
+    subprocess.check_call([CXX, *FLAGS, "-I" + REF, harness, lib, "-lm", "-o", e2e_ref])
+    print("[build_ref] built", e2e_ref)
+    pkg = os.path.join(os.path.dirname(HERE), "xfem-amie_b200")
+    b200 = os.path.join(pkg, "libamie_b200.so")
+    if os.path.exists(b200):
+        shim_objs = []
+        for src in ("amie_b200_shim.cpp", "conjugategradient_b200.cpp", "biconjugategradientstabilized_b200.cpp"):
+            o = os.path.join(OBJ, "shim__" + src[:-4] + ".o")
+            subprocess.check_call([CXX, *FLAGS, "-I" + REF, "-c", os.path.join(pkg, "host", "shim", src), "-o", o])
+            shim_objs.append(o)
+        e2e_b200 = os.path.join(OUT, "amie_e2e_b200")
+        # the shim objects come first: the archive's conjugategradient.o / biconjugategradientstabilized.o are then
+        # never pulled in (every symbol they define is already defined)
+        subprocess.check_call([CXX, *FLAGS, "-I" + REF, harness, *shim_objs, lib, "-L" + pkg, "-lamie_b200",
+                               "-Wl,-rpath,$ORIGIN/../../xfem-amie_b200", "-lm", "-o", e2e_b200])
+        print("[build_ref] built", e2e_b200)
     return 0
 
 

@@ -515,6 +515,15 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
     ctx->opt_time_spmv = 0 ;
     SpmvCall c ;
     c.x = ctx->x ; c.y = ctx->q ;
+    bool insolve = false ;
+    if(variant >= 100)
+    {
+        // the in-solve form: q = A p fused with p.q (result stored, no loop control)
+        variant -= 100 ;
+        ctx->opt_variant = variant ;
+        c.dot = DOT_YX ; c.finalize = FIN_STORE ;
+        insolve = true ;
+    }
     auto one = [&]()
     {
         if(ctx->S == 3 && variant >= 10)
@@ -525,8 +534,21 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
             args.x = c.x ; args.b = nullptr ; args.y = c.y ; args.w = nullptr ; args.d = nullptr ;
             args.row0 = 0 ; args.nrows = (uint32_t)ctx->nb ; args.colstart_blk = 0 ; args.sign = 1. ;
             args.st = ctx->st ; args.partials = ctx->partials ; args.finalize = FIN_STORE ; args.check_stop = 0 ;
+            if(insolve)
+            {
+                args.finalize = FIN_STORE ;
+                switch(variant)
+                {
+                case 60 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
+                case 61 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
+                default : launch_spmv(ctx, c) ;
+                }
+            }
+            else
             switch(variant)
             {
+            case 60 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
+            case 61 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
             case 15 : launch_s3_tma<DOT_NONE, false, 8, 3, 240>(ctx, args) ; break ;
             case 18 : launch_s3_tma<DOT_NONE, false, 8, 2, 240>(ctx, args) ; break ;
             case 52 : launch_s3_rt<DOT_NONE, false, 5, 12, 176, 1>(ctx, args) ; break ;

@@ -37,7 +37,35 @@ struct RtLayout
     static constexpr int TOTAL_BYTES = NST*STAGE_BYTES+2*NST*8+16 ;
 } ;
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+// NB consecutive 3x3 blocks of one scalar row: acc_c += A(r,c) x_c  (vs already points at row component r)
+template<int NB>
+__device__ __forceinline__ void rt_blocks(const double * __restrict__ vs, const double * __restrict__ xs,
+                                          double & acc0, double & acc1, double & acc2)
+{
+    double v0[NB], v1[NB], v2[NB], x0[NB], x1[NB], x2[NB] ;
+    const uint32_t va = smem_u32(vs), xa = smem_u32(xs) ;
+    // volatile asm keeps the 6*NB loads together in front of the DFMAs (the compiler otherwise
+    // interleaves load/use pairs to save registers, which serialises on the LDS latency)
+    #pragma unroll
+    for(int q = 0 ; q < NB ; q++)
+    {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0[q]) : "r"(va+q*72)) ;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1[q]) : "r"(va+q*72+24)) ;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2[q]) : "r"(va+q*72+48)) ;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x0[q]) : "r"(xa+q*24)) ;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x1[q]) : "r"(xa+q*24+8)) ;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x2[q]) : "r"(xa+q*24+16)) ;
+    }
+    #pragma unroll
+    for(int q = 0 ; q < NB ; q++)
+    {
+        acc0 = fma(v0[q], x0[q], acc0) ;
+        acc1 = fma(v1[q], x1[q], acc1) ;
+        acc2 = fma(v2[q], x2[q], acc2) ;
+    }
+}
+
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9>
 __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
 {
     if(a.check_stop && a.st->stop) return ;
@@ -103,14 +131,25 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
                     const uint32_t * cs = reinterpret_cast<const uint32_t *>(stage+L::VAL_BYTES+meta[R+2]) ;
                     double * xs = reinterpret_cast<double *>(stage+L::VAL_BYTES+L::COL_BYTES) ;
                     const uint32_t nblk = meta[nr]-meta[0] ;
-                    #pragma unroll 3
-                    for(uint32_t bk = lane ; bk < nblk ; bk += 32)
+                    // two phases, fully unrolled (a stage holds at most CAP blocks): all column-index reads
+                    // first, then the copies, so the LDS latency is paid once per tile and not once per block
+                    constexpr int GI = (CAP+31)/32 ;
+                    uint32_t cidx[GI] ;
+                    #pragma unroll
+                    for(int g = 0 ; g < GI ; g++)
+                        cidx[g] = (lane+32u*g < nblk) ? cs[lane+32u*g] : 0u ;
+                    #pragma unroll
+                    for(int g = 0 ; g < GI ; g++)
                     {
-                        const double * px = a.x+(size_t)cs[bk]*3 ;
-                        double * d = xs+(size_t)bk*3 ;
-                        cp_async_8(d, px) ;
-                        cp_async_8(d+1, px+1) ;
-                        cp_async_8(d+2, px+2) ;
+                        const uint32_t bk = lane+32u*g ;
+                        if(bk < nblk)
+                        {
+                            const double * px = a.x+(size_t)cidx[g]*3 ;
+                            double * d = xs+(size_t)bk*3 ;
+                            cp_async_8(d, px) ;
+                            cp_async_8(d+1, px+1) ;
+                            cp_async_8(d+2, px+2) ;
+                        }
                     }
                 }
             }
@@ -155,23 +194,13 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
                     const double * vs = reinterpret_cast<const double *>(stage+meta[R+1])+(size_t)(k0-k_lo)*9+r ;
                     const double * xs = reinterpret_cast<const double *>(stage+L::VAL_BYTES+L::COL_BYTES)+(size_t)(k0-k_lo)*3 ;
                     const uint32_t n = k1-k0 ;
+                    // operands of NB blocks are loaded as one batch before the NB*3 DFMAs: with one warp per
+                    // scheduler the LDS latency is only hidden by the warp's own instruction-level parallelism
                     uint32_t t = 0 ;
-                    for( ; t+3 <= n ; t += 3)
-                    {
-                        #pragma unroll
-                        for(int q = 0 ; q < 3 ; q++)
-                        {
-                            acc0 = fma(vs[(t+q)*9], xs[(t+q)*3], acc0) ;
-                            acc1 = fma(vs[(t+q)*9+3], xs[(t+q)*3+1], acc1) ;
-                            acc2 = fma(vs[(t+q)*9+6], xs[(t+q)*3+2], acc2) ;
-                        }
-                    }
-                    for( ; t < n ; t++)
-                    {
-                        acc0 = fma(vs[t*9], xs[t*3], acc0) ;
-                        acc1 = fma(vs[t*9+3], xs[t*3+1], acc1) ;
-                        acc2 = fma(vs[t*9+6], xs[t*3+2], acc2) ;
-                    }
+                    if(NB == 9)
+                        for( ; t+9 <= n ; t += 9) rt_blocks<9>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
+                    for( ; t+3 <= n ; t += 3) rt_blocks<3>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
+                    for( ; t < n ; t++)       rt_blocks<1>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
                 }
                 else
                 {

@@ -72,10 +72,10 @@ static inline void launch_s3_tma(amie_b200_ctx * ctx, const SpmvArgs & args)
 }
 
 // row-thread pipeline: W compute warps (one 10-row tile each at a time), NST stages, CAP blocks per stage
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9>
 static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G> ;
+    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB> ;
     constexpr int smem = RtLayout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+1)*32 ;
     static int per_sm = 0 ;

@@ -1,0 +1,40 @@
+// biconjugategradientstabilized_b200.cpp -- drop-in replacement of
+// solvers/biconjugategradientstabilized.cpp (class of solvers/biconjugategradientstabilized.h:19-24).
+#include "solvers/biconjugategradientstabilized.h"
+#include "amie_b200_shim.h"
+#include <iostream>
+
+using namespace Amie ;
+
+BiConjugateGradientStabilized::BiConjugateGradientStabilized(Assembly * a) :LinearSolver(a) { }
+
+bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * precond, const double epsilon , const int maxit , bool verbose )
+{
+    const int kind = AmieB200Shim::precond_kind(precond) ;
+    if(kind < 0)
+    {
+        std::cerr << "amie_b200: this Preconditionner type is not available on the device" << std::endl ;
+        return false ;
+    }
+    amie_b200_ctx * ctx = AmieB200Shim::context_for(assembly) ;
+    if(!ctx)
+        return false ;
+    const Vector & b = assembly->getForces() ;
+    x.resize(b.size(), 0.) ;
+    uint64_t n = 0 ;
+    double err = 0 ;
+    int ret = amie_b200_bicgstab(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, epsilon, maxit, &x[0], &n, &err) ;
+    if(ret < 0)
+    {
+        std::cerr << "amie_b200: bicgstab: " << amie_b200_last_error(ctx) << std::endl ;
+        return false ;
+    }
+    if(verbose)
+    {
+        if(ret)
+            std::cerr << "\n BiCGStab " << x.size() << " converged after " << n << " iterations. Error : " << err << ", max : "  << x.max() << ", min : "  << x.min() <<std::endl ;
+        else
+            std::cerr << "\n BiCGStab " << x.size() << " did not converge after " << n << " iterations. Error : " << err << ", max : "  << x.max() << ", min : "  << x.min() <<std::endl ;
+    }
+    return ret == 1 ;
+}

@@ -1,0 +1,57 @@
+// conjugategradient_b200.cpp -- drop-in replacement of solvers/conjugategradient.cpp.
+//
+// Same class (solvers/conjugategradient.h:22-43), same constructor and solve() signature; the body
+// of solve() forwards to the C-ABI (include/amie_b200.h).  Link this object INSTEAD of the
+// reference's conjugategradient.o; nothing else of AMIE changes.
+#include "solvers/conjugategradient.h"
+#include "amie_b200_shim.h"
+#include <iostream>
+#include <cstdlib>
+
+namespace Amie {
+
+ConjugateGradient::ConjugateGradient( Assembly* a ) :LinearSolver(a), r(0), z(0), p(0), q(0), xmin(0), cleanup(false), P(nullptr), nit(0)
+{
+    // the work vectors r, z, p, q, xmin of the reference live in HBM here
+}
+
+bool ConjugateGradient::solve(const Vector &x0, Preconditionner * precond, const double eps, const int maxit, bool verbose)
+{
+    const int kind = AmieB200Shim::precond_kind(precond) ;
+    if(kind < 0)
+    {
+        std::cerr << "amie_b200: this Preconditionner type is not available on the device (nullptr and NullPreconditionner are)" << std::endl ;
+        return false ;
+    }
+    amie_b200_ctx * ctx = AmieB200Shim::context_for(assembly) ;
+    if(!ctx)
+        return false ;
+    const Vector & b = assembly->getForces() ;
+    if(x.size() != b.size())
+        x.resize(b.size(), 0.) ;
+    uint64_t n = 0 ;
+    double err = 0, rho = 0 ;
+    int ret = amie_b200_pcg(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, eps, maxit, nssor,
+                            rowstart, colstart, &x[0], &n, &err, &rho) ;
+    nit = n ;
+    if(ret == AMIE_B200_ERR_NAN)
+    {
+        // conjugategradient.cpp:160-165
+        assembly->print() ;
+        std::cout << "NaN error" << std::endl ;
+        exit(0) ;
+    }
+    if(ret < 0)
+    {
+        std::cerr << "amie_b200: pcg: " << amie_b200_last_error(ctx) << std::endl ;
+        return false ;
+    }
+    if(ret)
+        std::cerr << "\n CG " << x.size() << " converged after " << nit << " iterations. Error : " << err << ", last rho = " << rho << ", max : "  << x.max() << ", min : "  << x.min() << std::endl ;
+    else
+        std::cerr << "\n CG " << x.size() << " did not converge after " << nit << " iterations. Error : " << err << ", last rho = " << rho << ", max : "  << x.max() << ", min : "  << x.min() << std::endl ;
+    (void)verbose ;
+    return ret == 1 ;
+}
+
+}
