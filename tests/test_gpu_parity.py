@@ -374,3 +374,17 @@ def test_full_size_properties(pkg, preset, n):
     assert np.linalg.norm(res) <= 1e-5 * max(1.0, np.linalg.norm(rhs))
     assert np.sqrt(abs(rho)) <= 1e-10
     asm.close()
+
+
+def test_cpp_host_mirror(pkg, ol, systems):
+    """xfem-amie_b200/host/amie_b200.hpp (C++ mirror of the solver classes) through its example."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "build", "example_solve")
+    assert os.path.exists(exe), "build() compiles it"
+    p = subprocess.run([exe, "S3-tet", "12"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    S = systems("S3-tet", 12)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    fields = dict(kv.split("=") for kv in p.stdout.split("|")[0].split() if "=" in kv)
+    assert abs(int(fields["nit"]) - int(info.nit)) <= NIT_TOL
+    assert float(fields["checksum"]) == pytest.approx(np.abs(x_ref).sum(), rel=1e-9)

@@ -541,6 +541,16 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
                 {
                 case 60 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
                 case 61 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
+                case 62 : launch_s3_rt<DOT_YX, false, 4, 8, 270, 1, 9>(ctx, args) ; break ;
+                case 63 : launch_s3_rt<DOT_YX, false, 2, 8, 270, 2, 9>(ctx, args) ; break ;
+                case 64 : launch_s3_rt<DOT_YX, false, 2, 8, 270, 3, 9>(ctx, args) ; break ;
+                case 65 : launch_s3_rt<DOT_YX, false, 3, 7, 300, 1, 9>(ctx, args) ; break ;
+                case 66 : launch_s3_rt<DOT_YX, false, 3, 7, 270, 1, 9>(ctx, args) ; break ;
+                case 67 : launch_s3_rt<DOT_YX, false, 3, 6, 270, 1, 9>(ctx, args) ; break ;
+                case 68 : launch_s3_rt<DOT_YX, false, 3, 6, 330, 1, 9>(ctx, args) ; break ;
+                case 69 : launch_s3_rt<DOT_YX, false, 3, 7, 280, 1, 9>(ctx, args) ; break ;
+                case 70 : launch_s3_rt<DOT_YX, false, 3, 8, 272, 1, 9>(ctx, args) ; break ;
+                case 71 : launch_s3_rt<DOT_YX, false, 4, 8, 272, 1, 9>(ctx, args) ; break ;
                 default : launch_spmv(ctx, c) ;
                 }
             }

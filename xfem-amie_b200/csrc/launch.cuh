@@ -108,7 +108,7 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
         else if(ctx->opt_variant == 2)
             launch_s3_tma<DOT, MINUS_B, AMIE_TMA_R, AMIE_TMA_NST, AMIE_TMA_CAP>(ctx, args) ;
         else
-            launch_s3_rt<DOT, MINUS_B, 3, 8, 270, 1>(ctx, args) ;
+            launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;       // 7 stages, not 8: leaves ~30 KB of L1 for the x gather (profiles/r01_notes.md)
     }
     else
     {
