@@ -14,7 +14,7 @@ import numpy as np
 
 def run_distributed(args, pkg, dist, rank, world, local_rank):
     import torch
-    from bench import METRIC, UNIT, ClockSampler, measured_peak, cpu_reference_rate
+    from bench import METRIC, UNIT, ClockSampler, measured_peak, stdout_to_stderr
 
     dev = torch.device("cuda", local_rank)
     syn = pkg.Synth(args.preset, args.n)
@@ -22,14 +22,14 @@ def run_distributed(args, pkg, dist, rank, world, local_rank):
     bounds = pkg.partition_rows(rs, world)
     del rs
 
-    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    id128 = bytes(idt.cpu().numpy().tobytes())
-
-    asm = pkg.Assembly(device=local_rank)
-    asm.dist_init(rank, world, id128, bounds)
+    with stdout_to_stderr():
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        id128 = bytes(idt.cpu().numpy().tobytes())
+        asm = pkg.Assembly(device=local_rank)
+        asm.dist_init(rank, world, id128, bounds)
     t0 = time.time()
     asm.dist_synth_to_device(syn)
     gen_s = time.time() - t0

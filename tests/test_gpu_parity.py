@@ -388,3 +388,25 @@ def test_cpp_host_mirror(pkg, ol, systems):
     fields = dict(kv.split("=") for kv in p.stdout.split("|")[0].split() if "=" in kv)
     assert abs(int(fields["nit"]) - int(info.nit)) <= NIT_TOL
     assert float(fields["checksum"]) == pytest.approx(np.abs(x_ref).sum(), rel=1e-9)
+
+
+@pytest.mark.parametrize("preset,n", [("S2-tri", 40), ("S3-tet", 14)])
+def test_cuda_graph_batches_identical(pkg, ol, systems, asm_cache, preset, n):
+    """Small systems replay a captured CUDA graph of iterations: same kernels, same bits, same nit."""
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    out = {}
+    for graph in (0, 1, 1):
+        asm.set_option("graph", graph)
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor = 32
+        assert cg.solve()
+        bi = pkg.BiConjugateGradientStabilized(asm)
+        assert bi.solve()
+        out.setdefault(graph, []).append((cg.nit, cg.x.copy(), bi.nit, bi.x.copy()))
+    asm.set_option("graph", -1)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    a, b, c = out[0][0], out[1][0], out[1][1]
+    assert a[0] == b[0] == c[0] and abs(int(a[0]) - int(info.nit)) <= NIT_TOL
+    assert np.array_equal(a[1], b[1]) and np.array_equal(b[1], c[1])
+    assert a[2] == b[2] and np.array_equal(a[3], b[3])

@@ -16,6 +16,7 @@ template<typename T> static void dfree(T *& p) { if(p) cudaFree(p) ; p = nullptr
 
 static void free_matrix(amie_b200_ctx * ctx)
 {
+    ctx->alloc_gen++ ;
     dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }
@@ -45,6 +46,7 @@ int ctx_alloc_vectors(amie_b200_ctx * ctx)
     if(len == 0) len = 1 ;
     if(ctx->vec_len == len) return AMIE_B200_OK ;
     free_vectors(ctx) ;
+    ctx->alloc_gen++ ;
     double ** v[] = { &ctx->b, &ctx->x, &ctx->r, &ctx->z, &ctx->p, &ctx->q, &ctx->xc, &ctx->rc, &ctx->xmin } ;
     for(auto pp : v)
     {
@@ -187,6 +189,8 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     cudaSetDevice(ctx->device) ;
     cudaStreamSynchronize(ctx->stream) ;
     dist_destroy(ctx) ;
+    if(ctx->graph_cg.exec) cudaGraphExecDestroy(ctx->graph_cg.exec) ;
+    if(ctx->graph_bicg.exec) cudaGraphExecDestroy(ctx->graph_bicg.exec) ;
     free_matrix(ctx) ;
     free_vectors(ctx) ;
     dfree(ctx->st) ; dfree(ctx->partials) ; dfree(ctx->flag) ;

@@ -57,6 +57,16 @@ struct amie_b200_ctx
 
     DistState * dist = nullptr ;
 
+    // ---- CUDA graphs of iteration batches (small systems: launch-bound inner loops)
+    struct GraphSlot
+    {
+        cudaGraphExec_t exec = nullptr ;
+        int batch = 0, precond = 0, variant = 0 ;
+        uint64_t rowstart = 0, colstart = 0, alloc_gen = 0 ;
+    } ;
+    GraphSlot graph_cg, graph_bicg ;
+    uint64_t alloc_gen = 0 ;           // bumped whenever device arrays are (re)allocated
+
     void set_error(const std::string & e) { err = e ; }
 } ;
 

@@ -6,7 +6,7 @@
 //     k_bicg_xr (x, r update; fused r.r_ -> rho, beta, the while() test, nit)
 // i.e. 2 SpMV + 3 streaming kernels against the reference's 2 SpMV + ~15 vector sweeps.
 // rowstart/colstart are ignored exactly like the reference does.
-#include "launch.cuh"
+#include "batch_loop.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -180,22 +180,11 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
 
     const double iter_bytes = 2.*((double)ctx->nnzb*(8*S*S+4))+(double)N*8*30 ;
     int batch = ctx->opt_batch > 0 ? ctx->opt_batch : (int)std::min(32., std::max(1., 300e-6/(iter_bytes/5e12))) ;
-    int slot = 0, pending = 0 ;
-    bool stopped = false ;
-    while(!stopped)
     {
-        for(int i = 0 ; i < batch ; i++) queue_bicg_iteration(ctx, precond, FIN_BICG_RHO) ;
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_host+slot, ctx->st, sizeof(KrylovState), cudaMemcpyDeviceToHost, ctx->stream)) ;
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream)) ;
-        pending++ ;
-        if(pending == 2)
-        {
-            const int old = slot^1 ;
-            CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_poll[old])) ;
-            pending-- ;
-            if(ctx->st_host[old].stop) stopped = true ;
-        }
-        slot ^= 1 ;
+        const bool graph = want_graph(ctx, iter_bytes) ;
+        const int nb_iter = graph ? (ctx->opt_batch > 0 ? ctx->opt_batch : 16) : batch ;
+        if((rc = run_iteration_batches(ctx, ctx->graph_bicg, graph, nb_iter, precond, 0, 0, 5, 2,
+                                       [&]() { queue_bicg_iteration(ctx, precond, FIN_BICG_RHO) ; }))) return rc ;
     }
     if((rc = ctx_sync_state(ctx, 2))) return rc ;
     CUDA_TRY(ctx, cudaGetLastError()) ;

@@ -7,7 +7,7 @@
 //     k_cg_dir  ->  k_spmv (q = A p, fused p.q)  ->  k_cg_update (x, r Kahan; fused r.D^-1 r)
 // whose scalars (rho, beta, pq, alpha, nit, the while() test) are updated on the device, so the
 // host only queues batches of iterations and polls a pinned copy of the state.
-#include "launch.cuh"
+#include "batch_loop.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -220,24 +220,12 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         }
         launch_update(R, true) ;                                                    // :199-210 (not counted in nit)
 
-        // :218-257, queued speculatively; two polls in flight
-        int slot = 0 ;
-        int pending = 0 ;
-        bool stopped = false ;
-        while(!stopped)
+        // :218-257, queued speculatively (batch_loop.cuh)
         {
-            for(int i = 0 ; i < batch ; i++) queue_iteration(R) ;
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_host+slot, ctx->st, sizeof(KrylovState), cudaMemcpyDeviceToHost, ctx->stream)) ;
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream)) ;
-            pending++ ;
-            if(pending == 2)
-            {
-                const int old = slot^1 ;
-                CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_poll[old])) ;
-                pending-- ;
-                if(ctx->st_host[old].stop) stopped = true ;
-            }
-            slot ^= 1 ;
+            const bool graph = want_graph(ctx, iter_bytes) ;
+            const int nb_iter = graph ? (ctx->opt_batch > 0 ? ctx->opt_batch : 32) : batch ;
+            if((rc = run_iteration_batches(ctx, ctx->graph_cg, graph, nb_iter, R.precond, rowstart, colstart, 3, 1,
+                                           [&]() { queue_iteration(R) ; }))) return rc ;
         }
         if((rc = ctx_sync_state(ctx, 2))) return rc ;
         CUDA_TRY(ctx, cudaGetLastError()) ;

@@ -90,6 +90,7 @@ extern "C" int amie_b200_synth_to_device(amie_b200_ctx * ctx, const amie_b200_sy
     if(ctx->vals) { cudaFree(ctx->vals) ; ctx->vals = nullptr ; }
     if(ctx->dinv) { cudaFree(ctx->dinv) ; ctx->dinv = nullptr ; }
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
+    ctx->alloc_gen++ ;
     ctx->S = R.stride ; ctx->nb = ctx->nb_global = nb ; ctx->row_base = 0 ; ctx->N = nb*R.stride ; ctx->ncols_local = nb ;
     int rc = ctx_alloc_vectors(ctx) ;
     if(rc) return rc ;
