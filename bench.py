@@ -270,6 +270,11 @@ def main():
                "sample": f"one full ConjugateGradient::solve of S3-hex-{r['n']} ({r['ndof']} DOF, {r['nit']} it, {r['wall']:.1f} s); "
                          f"DOF*iter/s scaled by the DOF ratio to this workload ({N} DOF)"}
 
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.preset}-{args.n}/1", {}).get("bytes")
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -283,7 +288,7 @@ def main():
             "pcg_iteration_gbs": iter_bytes * value / 1e9,
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)" if s == 3 else "k_spmv_s2<DOT_YX>",
+                         "traffic": traffic, "kernel": "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)" if s == 3 else "k_spmv_s2<DOT_YX>",
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "peak_source": peak_src},
             "e2e": e2e, "cpu_baseline": cpu}

@@ -37,25 +37,43 @@ struct RtLayout
     static constexpr int TOTAL_BYTES = NST*STAGE_BYTES+2*NST*8+16 ;
 } ;
 
-// NB consecutive 3x3 blocks of one scalar row: acc_c += A(r,c) x_c  (vs already points at row component r)
+// ld.shared.f64 with a compile-time byte offset folded into the instruction (no address arithmetic)
+template<int OFF>
+__device__ __forceinline__ double lds_f64(uint32_t base)
+{
+    double v ;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(base), "n"(OFF)) ;
+    return v ;
+}
+
+// Loads of block Q.. of a batch, unrolled by template recursion so that every offset is an immediate.
+// The volatile asm keeps the 6*NB loads together in front of the DFMAs (the compiler otherwise interleaves
+// load/use pairs to save registers, which serialises on the LDS latency: one warp per scheduler here).
+template<int Q, int NB>
+struct RtLoad
+{
+    static __device__ __forceinline__ void run(uint32_t va, uint32_t xa, double (&v0)[NB], double (&v1)[NB], double (&v2)[NB],
+                                               double (&x0)[NB], double (&x1)[NB], double (&x2)[NB])
+    {
+        v0[Q] = lds_f64<Q*72>(va) ; v1[Q] = lds_f64<Q*72+24>(va) ; v2[Q] = lds_f64<Q*72+48>(va) ;
+        x0[Q] = lds_f64<Q*24>(xa) ; x1[Q] = lds_f64<Q*24+8>(xa) ;  x2[Q] = lds_f64<Q*24+16>(xa) ;
+        RtLoad<Q+1, NB>::run(va, xa, v0, v1, v2, x0, x1, x2) ;
+    }
+} ;
 template<int NB>
-__device__ __forceinline__ void rt_blocks(const double * __restrict__ vs, const double * __restrict__ xs,
-                                          double & acc0, double & acc1, double & acc2)
+struct RtLoad<NB, NB>
+{
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, double (&)[NB], double (&)[NB], double (&)[NB],
+                                               double (&)[NB], double (&)[NB], double (&)[NB]) { }
+} ;
+
+// NB consecutive 3x3 blocks of one scalar row: acc_c += A(r,c) x_c   (va: shared address of A(r,0) of the first
+// block, xa: of x_0 of the first block)
+template<int NB>
+__device__ __forceinline__ void rt_blocks(uint32_t va, uint32_t xa, double & acc0, double & acc1, double & acc2)
 {
     double v0[NB], v1[NB], v2[NB], x0[NB], x1[NB], x2[NB] ;
-    const uint32_t va = smem_u32(vs), xa = smem_u32(xs) ;
-    // volatile asm keeps the 6*NB loads together in front of the DFMAs (the compiler otherwise
-    // interleaves load/use pairs to save registers, which serialises on the LDS latency)
-    #pragma unroll
-    for(int q = 0 ; q < NB ; q++)
-    {
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0[q]) : "r"(va+q*72)) ;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1[q]) : "r"(va+q*72+24)) ;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2[q]) : "r"(va+q*72+48)) ;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x0[q]) : "r"(xa+q*24)) ;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x1[q]) : "r"(xa+q*24+8)) ;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x2[q]) : "r"(xa+q*24+16)) ;
-    }
+    RtLoad<0, NB>::run(va, xa, v0, v1, v2, x0, x1, x2) ;
     #pragma unroll
     for(int q = 0 ; q < NB ; q++)
     {
@@ -191,16 +209,24 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
                         }
                         k0 = lo ;
                     }
-                    const double * vs = reinterpret_cast<const double *>(stage+meta[R+1])+(size_t)(k0-k_lo)*9+r ;
-                    const double * xs = reinterpret_cast<const double *>(stage+L::VAL_BYTES+L::COL_BYTES)+(size_t)(k0-k_lo)*3 ;
+                    const uint32_t va = smem_u32(stage+meta[R+1])+((k0-k_lo)*9u+(uint32_t)r)*8u ;
+                    const uint32_t xa = smem_u32(stage+L::VAL_BYTES+L::COL_BYTES)+(k0-k_lo)*24u ;
                     const uint32_t n = k1-k0 ;
-                    // operands of NB blocks are loaded as one batch before the NB*3 DFMAs: with one warp per
-                    // scheduler the LDS latency is only hidden by the warp's own instruction-level parallelism
-                    uint32_t t = 0 ;
-                    if(NB == 9)
-                        for( ; t+9 <= n ; t += 9) rt_blocks<9>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
-                    for( ; t+3 <= n ; t += 3) rt_blocks<3>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
-                    for( ; t < n ; t++)       rt_blocks<1>(vs+t*9, xs+t*3, acc0, acc1, acc2) ;
+                    if(n == 27u && NB == 9)
+                    {
+                        // the common row of a hexahedral mesh: straight-line code, every offset an immediate
+                        rt_blocks<9>(va, xa, acc0, acc1, acc2) ;
+                        rt_blocks<9>(va+9*72, xa+9*24, acc0, acc1, acc2) ;
+                        rt_blocks<9>(va+18*72, xa+18*24, acc0, acc1, acc2) ;
+                    }
+                    else
+                    {
+                        uint32_t t = 0 ;
+                        if(NB == 9)
+                            for( ; t+9 <= n ; t += 9) rt_blocks<9>(va+t*72, xa+t*24, acc0, acc1, acc2) ;
+                        for( ; t+3 <= n ; t += 3) rt_blocks<3>(va+t*72, xa+t*24, acc0, acc1, acc2) ;
+                        for( ; t < n ; t++)       rt_blocks<1>(va+t*72, xa+t*24, acc0, acc1, acc2) ;
+                    }
                 }
                 else
                 {
