@@ -62,6 +62,10 @@ __device__ __forceinline__ void cp_async_8(void * dst_smem, const void * src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory") ;
 }
+__device__ __forceinline__ void cp_async_16(void * dst_smem, const void * src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory") ;
+}
 __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;" ::: "memory") ;
@@ -75,7 +79,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void * src_gmem, uint32_t 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory") ;
 }
 
-template<int R, int NST, int CAP, int STAGE_BYTES, int VAL_BYTES, int META_OFF, int PFD = 4>
+template<int R, int NST, int CAP, int STAGE_BYTES, int VAL_BYTES, int META_OFF, int PFD = 4, int BB = 72>
 __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char * smem, uint64_t * full, uint64_t * empty,
                                               uint32_t ntiles, int lane)
 {
@@ -115,9 +119,9 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
                     const uint32_t p_hi = __shfl_sync(0xffffffffu, rpp, nrp & 31) ;
                     if(lane == 0 && p_hi > p_lo && p_hi-p_lo <= (uint32_t)CAP)
                     {
-                        const uint64_t va_lo = ((uint64_t)p_lo*72) & ~15ull ;
+                        const uint64_t va_lo = ((uint64_t)p_lo*BB) & ~15ull ;
                         const uint64_t ca_lo = ((uint64_t)p_lo*4) & ~15ull ;
-                        tma_prefetch_l2(reinterpret_cast<const unsigned char *>(a.vals)+va_lo, (uint32_t)((((uint64_t)p_hi*72-va_lo)+15ull) & ~15ull)) ;
+                        tma_prefetch_l2(reinterpret_cast<const unsigned char *>(a.vals)+va_lo, (uint32_t)((((uint64_t)p_hi*BB-va_lo)+15ull) & ~15ull)) ;
                         tma_prefetch_l2(reinterpret_cast<const unsigned char *>(a.col)+ca_lo, (uint32_t)((((uint64_t)p_hi*4-ca_lo)+15ull) & ~15ull)) ;
                     }
                 }
@@ -136,7 +140,7 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
             const bool staged = nblk <= (uint32_t)CAP && nblk > 0 ;
             if(lane == 0)
             {
-                meta[R+1] = (uint32_t)(((uint64_t)k_lo*72) & 15ull) ;
+                meta[R+1] = (uint32_t)(((uint64_t)k_lo*BB) & 15ull) ;
                 meta[R+2] = (uint32_t)(((uint64_t)k_lo*4) & 15ull) ;
                 meta[R+3] = staged ? 1u : 0u ;
             }
@@ -145,7 +149,7 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
             {
                 if(staged)
                 {
-                    const uint64_t vb_lo = (uint64_t)k_lo*72, vb_hi = (uint64_t)k_hi*72 ;
+                    const uint64_t vb_lo = (uint64_t)k_lo*BB, vb_hi = (uint64_t)k_hi*BB ;
                     const uint64_t va_lo = vb_lo & ~15ull ;
                     const uint32_t vbytes = (uint32_t)(((vb_hi-va_lo)+15ull) & ~15ull) ;
                     const uint64_t cb_lo = (uint64_t)k_lo*4, cb_hi = (uint64_t)k_hi*4 ;

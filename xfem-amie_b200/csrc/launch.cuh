@@ -5,6 +5,7 @@
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
 #include "kernels_spmv_rt.cuh"
+#include "kernels_spmv_rt2.cuh"
 #include "kernels_vec.cuh"
 
 // persistent grids: a multiple of the SM count, never more blocks than there is work, and
@@ -90,6 +91,24 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
 }
 
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
+{
+    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G> ;
+    constexpr int smem = Rt2Layout<NST, CAP>::TOTAL_BYTES ;
+    constexpr int threads = (W+1)*32 ;
+    static int per_sm = 0 ;
+    if(!per_sm)
+    {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
+        if(per_sm < 1) per_sm = 1 ;
+    }
+    const uint32_t ntiles = (args.nrows+RT2_ROWS-1)/RT2_ROWS ;
+    const int grid = persistent_grid(ctx, per_sm, ntiles) ;
+    kern<<<grid, threads, smem, ctx->stream>>>(args) ;
+}
+
 #ifndef AMIE_TMA_R
 #define AMIE_TMA_R 8
 #define AMIE_TMA_NST 3
@@ -115,6 +134,13 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
         // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long
         const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
         int G = avg > 24. ? 32 : (avg > 10. ? 16 : 8) ;
+        if(ctx->opt_variant == 3)
+        {
+            // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh): measured SLOWER than the plain kernel
+            // (1.5 vs 4.1 TB/s on S2-tri-4096: 3.6 KB tiles cannot amortise the per-tile costs) -- kept selectable
+            launch_s2_rt<DOT, MINUS_B, 6, 16, 144, 1>(ctx, args) ;
+            return ;
+        }
         if(ctx->opt_variant == 8 || ctx->opt_variant == 16 || ctx->opt_variant == 32) G = ctx->opt_variant ;
         if(G == 32)      SPMV_LAUNCH((k_spmv_s2<32, DOT, MINUS_B>), 8) ;
         else if(G == 16) SPMV_LAUNCH((k_spmv_s2<16, DOT, MINUS_B>), 16) ;
