@@ -21,7 +21,7 @@ for preset, n in cases:
     gen = time.time() - t0
     st = asm.stats()
     out = {"case": f"{preset}-{n}", "ndof": st.ndof, "nnzb": st.nnzb, "gen_s": round(gen, 2), "algo_MB": st.spmv_algorithmic_bytes / 1e6}
-    variants = [0, 100] if st.stride == 3 else [8, 16, 3, 108]
+    variants = [0, 100] if st.stride == 3 else [8, 0, 100]
     if os.environ.get('PROBE_VARIANTS'):
         variants = [int(v) for v in os.environ['PROBE_VARIANTS'].split(',')]
     import numpy as np

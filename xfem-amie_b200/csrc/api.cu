@@ -530,7 +530,23 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
     }
     auto one = [&]()
     {
-        if(ctx->S == 3 && variant >= 10)
+        if(ctx->S == 2 && variant >= 90)
+        {
+            SpmvArgs args ;
+            args.rowptr = ctx->rowptr ; args.col = ctx->col ; args.vals = ctx->vals ;
+            args.x = c.x ; args.b = nullptr ; args.y = c.y ; args.w = nullptr ; args.d = nullptr ;
+            args.row0 = 0 ; args.nrows = (uint32_t)ctx->nb ; args.colstart_blk = 0 ; args.sign = 1. ;
+            args.st = ctx->st ; args.partials = ctx->partials ; args.finalize = FIN_STORE ; args.check_stop = 0 ;
+            switch(variant)
+            {
+            case 90 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 1>(ctx, args) ; break ;
+            case 91 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 2>(ctx, args) ; break ;
+            case 92 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 4>(ctx, args) ; break ;
+            case 93 : launch_s2_rt<DOT_NONE, false, 8, 20, 144, 1, 4>(ctx, args) ; break ;
+            default : launch_spmv(ctx, c) ;
+            }
+        }
+        else if(ctx->S == 3 && variant >= 10)
         {
             // tuning configurations of the TMA pipeline (plain y = A x only)
             SpmvArgs args ;
@@ -561,6 +577,10 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
             else
             switch(variant)
             {
+            case 80 : launch_s3_rt<DOT_NONE, false, 3, 7, 270, 1, 9, 2>(ctx, args) ; break ;
+            case 81 : launch_s3_rt<DOT_NONE, false, 5, 12, 160, 1, 9, 2>(ctx, args) ; break ;
+            case 82 : launch_s3_rt<DOT_NONE, false, 5, 12, 160, 1, 9, 3>(ctx, args) ; break ;
+            case 83 : launch_s3_rt<DOT_NONE, false, 4, 9, 200, 1, 9, 2>(ctx, args) ; break ;
             case 60 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
             case 61 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
             case 15 : launch_s3_tma<DOT_NONE, false, 8, 3, 240>(ctx, args) ; break ;

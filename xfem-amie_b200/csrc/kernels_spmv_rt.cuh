@@ -83,8 +83,8 @@ __device__ __forceinline__ void rt_blocks(uint32_t va, uint32_t xa, double & acc
     }
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9>
-__global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1>
+__global__ void __launch_bounds__((W+NP)*32) k_spmv_s3_rt(SpmvArgs a)
 {
     if(a.check_stop && a.st->stop) return ;
     static_assert(NST >= (G+1)*W, "stages: W tiles in compute + G*W tiles being gathered") ;
@@ -111,9 +111,9 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
 
     double dsum[2] = {0., 0.} ;
 
-    if(wid == W)
+    if(wid >= W)
     {
-        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF>(a, smem, full_v, empty, ntiles, lane) ;
+        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF>(a, smem, full_v, empty, ntiles, lane, wid-W, NP) ;
     }
     else
     {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s3_rt(SpmvArgs a)
     if(DOT != DOT_NONE)
     {
         double tot[2] ;
-        if(grid_sum<2, (W+1)*32>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
+        if(grid_sum<2, (W+NP)*32>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
             krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
     }
 }

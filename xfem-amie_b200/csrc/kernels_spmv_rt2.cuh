@@ -54,8 +54,8 @@ __device__ __forceinline__ void rt2_blocks(uint32_t va, uint32_t xa, double & ac
     }
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
-__global__ void __launch_bounds__((W+1)*32) k_spmv_s2_rt(SpmvArgs a)
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
+__global__ void __launch_bounds__((W+NP)*32) k_spmv_s2_rt(SpmvArgs a)
 {
     if(a.check_stop && a.st->stop) return ;
     static_assert(NST >= (G+1)*W, "stages: W tiles in compute + G*W tiles being gathered") ;
@@ -82,9 +82,9 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s2_rt(SpmvArgs a)
 
     double dsum[2] = {0., 0.} ;
 
-    if(wid == W)
+    if(wid >= W)
     {
-        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF, 4, 32>(a, smem, full_v, empty, ntiles, lane) ;
+        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF, 4, 32>(a, smem, full_v, empty, ntiles, lane, wid-W, NP) ;
     }
     else
     {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__((W+1)*32) k_spmv_s2_rt(SpmvArgs a)
     if(DOT != DOT_NONE)
     {
         double tot[2] ;
-        if(grid_sum<2, (W+1)*32>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
+        if(grid_sum<2, (W+NP)*32>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
             krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
     }
 }

@@ -81,8 +81,10 @@ __device__ __forceinline__ void tma_prefetch_l2(const void * src_gmem, uint32_t 
 
 template<int R, int NST, int CAP, int STAGE_BYTES, int VAL_BYTES, int META_OFF, int PFD = 4, int BB = 72>
 __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char * smem, uint64_t * full, uint64_t * empty,
-                                              uint32_t ntiles, int lane)
+                                              uint32_t ntiles, int lane, uint32_t first = 0, uint32_t step = 1)
 {
+    // `first`/`step`: several producer warps share the CTA's tile sequence (warp p takes tiles p, p+step, ...):
+    // one producer spends ~0.3 us per tile, which caps a CTA at tile_bytes/0.3 us -- too little for short rows
     // PD row-pointer sets in flight; tile it+PFD is pulled into L2 (TMA prefetch, no shared memory
     // needed) while tile it is copied into its stage: the stage copies then see L2 latency, not HBM's.
     constexpr int PD = 8 ;
@@ -95,10 +97,11 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
         const uint32_t nr = min((uint32_t)R, a.row0+a.nrows-r0) ;
         return lane <= (int)nr ? __ldg(a.rowptr+r0+lane) : 0u ;
     } ;
+    const uint32_t tstride = step*gridDim.x ;
     #pragma unroll
-    for(int j = 0 ; j < PD ; j++) rpq[j] = load_rp(blockIdx.x+j*gridDim.x) ;
-    uint32_t it = 0 ;
-    uint32_t tile = blockIdx.x ;
+    for(int j = 0 ; j < PD ; j++) rpq[j] = load_rp(blockIdx.x+(first+j*step)*gridDim.x) ;
+    uint32_t it = first ;
+    uint32_t tile = blockIdx.x+first*gridDim.x ;
     while(tile < ntiles)
     {
         #pragma unroll
@@ -106,10 +109,10 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
         {
             if(tile >= ntiles) break ;
             const uint32_t rp = rpq[j] ;
-            rpq[j] = load_rp(tile+PD*gridDim.x) ;
+            rpq[j] = load_rp(tile+PD*tstride) ;
             if(PFD > 0)
             {
-                const uint32_t tp = tile+PFD*gridDim.x ;
+                const uint32_t tp = tile+PFD*tstride ;
                 if(tp < ntiles)
                 {
                     const uint32_t rpp = rpq[(j+PFD)%PD] ;
@@ -162,8 +165,8 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
                 else
                     mbar_arrive(full+s) ;
             }
-            tile += gridDim.x ;
-            it++ ;
+            tile += tstride ;
+            it += step ;
         }
     }
 }

@@ -73,12 +73,12 @@ static inline void launch_s3_tma(amie_b200_ctx * ctx, const SpmvArgs & args)
 }
 
 // row-thread pipeline: W compute warps (one 10-row tile each at a time), NST stages, CAP blocks per stage
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1>
 static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB> ;
+    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB, NP> ;
     constexpr int smem = RtLayout<NST, CAP>::TOTAL_BYTES ;
-    constexpr int threads = (W+1)*32 ;
+    constexpr int threads = (W+NP)*32 ;
     static int per_sm = 0 ;
     if(!per_sm)
     {
@@ -91,12 +91,12 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
 static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G> ;
+    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP> ;
     constexpr int smem = Rt2Layout<NST, CAP>::TOTAL_BYTES ;
-    constexpr int threads = (W+1)*32 ;
+    constexpr int threads = (W+NP)*32 ;
     static int per_sm = 0 ;
     if(!per_sm)
     {
@@ -127,18 +127,27 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
         else if(ctx->opt_variant == 2)
             launch_s3_tma<DOT, MINUS_B, AMIE_TMA_R, AMIE_TMA_NST, AMIE_TMA_CAP>(ctx, args) ;
         else
-            launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;       // 7 stages, not 8: leaves ~30 KB of L1 for the x gather (profiles/r01_notes.md)
+        {
+            // row-thread TMA pipeline; the stage capacity follows the mean row length so that a tile of 10 rows
+            // fills its stage (27 blocks/row for Q1 hexahedra, 12-15 for linear tetrahedra).  Short rows mean small
+            // tiles, and ONE producer warp (~0.3 us per tile) then caps the CTA: three producers there.
+            const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
+            if(avg > 15.5 || ctx->opt_variant == 3)
+                launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;   // 7 stages, not 8: leaves ~30 KB of L1 for the x gather
+            else
+                launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3>(ctx, args) ;
+        }
     }
     else
     {
         // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long
         const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
         int G = avg > 24. ? 32 : (avg > 10. ? 16 : 8) ;
-        if(ctx->opt_variant == 3)
+        if((ctx->opt_variant == 0 && avg <= 9.) || ctx->opt_variant == 3)
         {
-            // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh): measured SLOWER than the plain kernel
-            // (1.5 vs 4.1 TB/s on S2-tri-4096: 3.6 KB tiles cannot amortise the per-tile costs) -- kept selectable
-            launch_s2_rt<DOT, MINUS_B, 6, 16, 144, 1>(ctx, args) ;
+            // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh).  A 16-row tile is only ~3.6 KB, so the
+            // per-tile producer cost dominates: FOUR producer warps (1 producer: 1.4 TB/s, 4: 4.8 TB/s on S2-tri-4096)
+            launch_s2_rt<DOT, MINUS_B, 8, 20, 144, 1, 4>(ctx, args) ;
             return ;
         }
         if(ctx->opt_variant == 8 || ctx->opt_variant == 16 || ctx->opt_variant == 32) G = ctx->opt_variant ;
