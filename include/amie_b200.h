@@ -88,6 +88,10 @@ int amie_b200_bicgstab(amie_b200_ctx * ctx, const double * b, const double * x0,
 int amie_b200_spmv(amie_b200_ctx * ctx, const double * x, const double * b,
                    uint64_t rowstart, uint64_t colstart, double * y_out) ;
 
+/* r = K u - f and its Euclidean norm: what FeatureTree::solve computes right after cgsolve
+ * (features/features.cpp:4766-4768, there through the serial operator path).  r_out may be NULL.  */
+int amie_b200_residual(amie_b200_ctx * ctx, const double * u, const double * f, double * r_out, double * norm_out) ;
+
 /* CoordinateIndexedSparseMatrix::inverseDiagonal (sparse/sparse_matrix.cpp:216-231)      */
 int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out) ;
 

@@ -50,3 +50,33 @@ def systems(pkg, ol):
 def rel_l2(a, b):
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb else 1.0)
+
+
+def random_spd_blocks(stride, nb, seed):
+    """Symmetric, block-diagonally-dominant random block matrix in the reference layout."""
+    rng = np.random.default_rng(seed)
+    nbrs = [set([i]) for i in range(nb)]
+    for i in range(nb):
+        for j in rng.integers(0, nb, 4):
+            nbrs[i].add(int(j))
+            nbrs[int(j)].add(i)
+    cl = stride + stride % 2
+    blocks = {}
+    for i in range(nb):
+        for j in nbrs[i]:
+            if j > i:
+                B = 0.1 * rng.standard_normal((stride, stride))
+                blocks[(i, j)] = B
+                blocks[(j, i)] = B.T
+    for i in range(nb):
+        D = 0.1 * rng.standard_normal((stride, stride))
+        blocks[(i, i)] = 0.5 * (D + D.T) + np.eye(stride) * (2.0 + 0.1 * stride * len(nbrs[i]))
+    rs = np.array([len(nbrs[i]) for i in range(nb)], np.uint32)
+    ci, arr = [], []
+    for i in range(nb):
+        for j in sorted(nbrs[i]):
+            ci.append(j)
+            blk = np.zeros((stride, cl))              # [c][r] with pad
+            blk[:, :stride] = blocks[(i, j)].T        # element (r,c) at c*cl + r
+            arr.append(blk.ravel())
+    return rs, np.array(ci, np.uint32), np.concatenate(arr), rng.standard_normal(nb * stride)

@@ -92,6 +92,14 @@ def main():
         path = os.path.join(HERE, f"{preset}-{n}.npz")
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path), "bytes; CG nit", out["cg_nit"], "BiCGStab nit", out["bicg_nit"])
+    from conftest import random_spd_blocks
+    for stride in (1, 4, 6):                      # inner_product's other stride cases
+        rs, ci, arr, b = random_spd_blocks(stride, 60, 30 + stride)
+        S = ol.Sys(stride, 60, rs, ci, arr, b)
+        out = reference_outputs(S)
+        path = os.path.join(HERE, f"rand-s{stride}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes; CG nit", out["cg_nit"], "BiCGStab nit", out["bicg_nit"])
     import subprocess
     import tempfile
     exe = os.path.join(ROOT, "oracle", "_ref", "amie_e2e_ref")

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_l2
+from conftest import rel_l2, random_spd_blocks
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,18 @@ def test_spmv_matches_oracle(pkg, ol, systems, asm_cache, preset, n):
     # colstart without rowstart (the final-residual call passes rowstart as colstart, :266)
     y = asm.spmv(v, rowstart=0, colstart=rs)
     assert np.abs(y - ol.oracle_assign(S, v, None, 0, rs)).max() <= SPMV_TOL * scale
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 12), ("S2-tri", 40)])
+def test_residual_after_solve(pkg, ol, systems, asm_cache, preset, n):
+    """r = K u - f, |r| as FeatureTree::solve computes them after cgsolve (features/features.cpp:4766-4768)."""
+    S = systems(preset, n)
+    asm = asm_cache(preset, n)
+    u = np.random.default_rng(4).standard_normal(S.n)
+    r, nrm = asm.residual(u)
+    ro = ol.oracle_spmv_serial(S, u, S.b)
+    assert np.abs(r - ro).max() <= 1e-13 * np.abs(ro).max()
+    assert nrm == pytest.approx(np.linalg.norm(ro), rel=1e-12)
 
 
 @pytest.mark.parametrize("preset,n", CASES)
@@ -251,7 +263,7 @@ def test_edge_cases(pkg, ol, systems, asm_cache):
     assert e.value.code == pkg.ERR_NAN
     an.close()
     # unsupported stride and malformed structure are refused, not mis-computed
-    a1 = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(np.array([1, 1], np.uint32), np.array([0, 1], np.uint32), 1), np.ones(2), device=0)
+    a1 = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(np.array([1, 1], np.uint32), np.array([0, 1], np.uint32), 5), np.ones(10), device=0)
     with pytest.raises(pkg.AmieB200Error) as e:
         a1.sync_matrix()
     assert e.value.code == pkg.ERR_UNSUPPORTED
@@ -410,3 +422,29 @@ def test_cuda_graph_batches_identical(pkg, ol, systems, asm_cache, preset, n):
     assert a[0] == b[0] == c[0] and abs(int(a[0]) - int(info.nit)) <= NIT_TOL
     assert np.array_equal(a[1], b[1]) and np.array_equal(b[1], c[1])
     assert a[2] == b[2] and np.array_equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("stride", [1, 4, 6])
+def test_other_strides(pkg, ol, stride):
+    """Strides 1, 4, 6 of inner_product (sparse/sparse_matrix.h:222-233, :335-676): the generic kernel."""
+    rs, ci, arr, b = random_spd_blocks(stride, 400, 10 + stride)
+    S = ol.Sys(stride, 400, rs, ci, arr, b)
+    asm = assembly_of(pkg, S)
+    v = np.random.default_rng(1).standard_normal(S.n)
+    yo = ol.oracle_assign(S, v, b)
+    assert np.abs(asm.spmv(v, minus_b=b) - yo).max() <= 1e-13 * np.abs(yo).max()
+    cs = stride * 150
+    yo = ol.oracle_assign(S, v, None, cs, cs)
+    assert np.abs(asm.spmv(v, rowstart=cs, colstart=cs) - yo).max() <= 1e-13 * np.abs(yo).max()
+    assert np.array_equal(asm.inverse_diagonal(), ol.oracle_inverse_diagonal(S))
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    assert cg.solve() == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+    ret, xb_ref, _ = ol.oracle_bicgstab(S)
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    assert bi.solve() == bool(ret)
+    assert rel_l2(bi.x, xb_ref) <= X_TOL
+    asm.close()

@@ -67,6 +67,27 @@ def test_oracle_matches_live_reference(ol, systems, preset, n):
     assert np.array_equal(r_x, o_x)
 
 
+@pytest.mark.parametrize("stride", [1, 4, 6])
+def test_oracle_other_strides_match_live_reference(ol, stride):
+    """inner_product's stride 1 / 4 / 6 cases (sparse/sparse_matrix.h:222-233, :335-676), including the
+    stride-4 compensation quirk (row 3 writes compensate2)."""
+    if ol.ref() is None:
+        pytest.skip("oracle/_ref not built here: tests/golden/rand-s*.npz pin these strides instead")
+    from conftest import random_spd_blocks
+    rs, ci, arr, b = random_spd_blocks(stride, 300, 20 + stride)
+    S = ol.Sys(stride, 300, rs, ci, arr, b)
+    v = np.random.default_rng(2).standard_normal(S.n)
+    assert np.array_equal(ol.ref_spmv(S, v, b, mode=1)[0], ol.oracle_assign(S, v, b))
+    assert np.array_equal(ol.ref_spmv(S, v, b, mode=3)[0], ol.oracle_spmv_serial(S, v, b))
+    assert np.array_equal(ol.ref_inverse_diagonal(S), ol.oracle_inverse_diagonal(S))
+    r_ok, r_x, r_nit, _, _ = ol.ref_cg(S, nssor=32, nthreads=1)
+    o_ok, o_x, o_info = ol.oracle_cg(S, nssor=32)
+    assert (r_ok, r_nit) == (o_ok, o_info.nit) and np.array_equal(r_x, o_x)
+    r_ok, r_x, r_nit, _, _ = ol.ref_bicgstab(S, nthreads=1)
+    o_ok, o_x, o_info = ol.oracle_bicgstab(S)
+    assert (r_ok, r_nit) == (o_ok, o_info.nit) and np.array_equal(r_x, o_x)
+
+
 def test_oracle_thread_emulation_close_to_reference(ol, systems):
     """OpenMP reductions reorder sums: the reference's own iteration count moves by +-1-2 with the
     thread count.  The oracle's static-chunk emulation stays inside that band."""

@@ -73,6 +73,7 @@ def lib():
         L.amie_b200_bicgstab.argtypes = [vp, vp, vp, u64, ci, f64, ci, vp, vp, vp]
         L.amie_b200_spmv.argtypes = [vp, vp, vp, u64, u64, vp]
         L.amie_b200_inverse_diagonal.argtypes = [vp, vp]
+        L.amie_b200_residual.argtypes = [vp, vp, vp, vp, vp]
         L.amie_b200_upload_rhs.argtypes = [vp, vp]
         L.amie_b200_upload_x0.argtypes = [vp, vp, u64]
         L.amie_b200_download_x.argtypes = [vp, vp]
@@ -295,6 +296,16 @@ class Assembly:
         b = None if minus_b is None else np.ascontiguousarray(minus_b, np.float64)
         self.check(lib().amie_b200_spmv(self.ctx, _ptr(x), _ptr(b), rowstart, colstart, _ptr(y)))
         return y
+
+    def residual(self, u, f=None):
+        """r = K u - f and |r| (features/features.cpp:4766-4768)."""
+        self.sync_matrix()
+        u = np.ascontiguousarray(u, np.float64)
+        f = self.getForces() if f is None else np.ascontiguousarray(f, np.float64)
+        r = np.zeros_like(u)
+        nrm = f64()
+        self.check(lib().amie_b200_residual(self.ctx, _ptr(u), _ptr(f), _ptr(r), ctypes.byref(nrm)))
+        return r, nrm.value
 
     def inverse_diagonal(self):
         self.sync_matrix()

@@ -3,6 +3,7 @@
 // entry point needs a CUDA device and reports AMIE_B200_ERR_CUDA without one.
 #include "launch.cuh"
 #include <cstring>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
@@ -80,7 +81,10 @@ int ctx_ensure_dinv(amie_b200_ctx * ctx)
         if(rc) return rc ;
     }
     else if(ctx->S == 3) k_inverse_diagonal<3><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else                 k_inverse_diagonal<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else if(ctx->S == 2) k_inverse_diagonal<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else if(ctx->S == 1) k_inverse_diagonal<1><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else if(ctx->S == 4) k_inverse_diagonal<4><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else                 k_inverse_diagonal<6><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
     CUDA_TRY(ctx, cudaGetLastError()) ;
     ctx->stats.kernel_launches++ ;
     ctx->dinv_valid = true ;
@@ -249,9 +253,14 @@ int ctx_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32
                       const uint32_t * column_index, uint64_t nnzb, uint64_t ncols)
 {
     if(!ctx || !row_size || (!column_index && nnzb)) return AMIE_B200_ERR_ARG ;
-    if(stride != 2 && stride != 3)
+    if(stride != 1 && stride != 2 && stride != 3 && stride != 4 && stride != 6)
     {
-        ctx->set_error("set_structure: only stride 2 (2D) and 3 (3D) blocks are on the device path") ;
+        ctx->set_error("set_structure: strides 1, 2, 3, 4 and 6 are on the device path (2 and 3 on the tuned kernels)") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    if(ctx->dist && stride != 2 && stride != 3)
+    {
+        ctx->set_error("set_structure: a row-partitioned context takes stride 2 or 3") ;
         return AMIE_B200_ERR_UNSUPPORTED ;
     }
     if(nnzb >= 0xffffffffull || nb >= 0xffffffffull) { ctx->set_error("set_structure: more than 2^32-1 blocks") ; return AMIE_B200_ERR_UNSUPPORTED ; }
@@ -319,7 +328,8 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
             uint64_t nblk = std::min(chunk_blocks, ctx->nnzb-k) ;
             cudaEventSynchronize(done[which]) ;
             cudaMemcpyAsync(stage[which], array+k*S*cl, nblk*S*cl*sizeof(double), cudaMemcpyHostToDevice, ctx->stream) ;
-            k_repack<3><<<vec_grid(ctx, nblk*9), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k*9, nblk) ;
+            if(S == 3)      k_repack<3><<<vec_grid(ctx, nblk*9), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k*9, nblk) ;
+            else            k_repack<1><<<vec_grid(ctx, nblk), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k, nblk) ;
             cudaEventRecord(done[which], ctx->stream) ;
         }
         cudaError_t e = cudaStreamSynchronize(ctx->stream) ;
@@ -506,6 +516,28 @@ int amie_b200_spmv(amie_b200_ctx * ctx, const double * x, const double * b, uint
     CUDA_TRY(ctx, cudaGetLastError()) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(y_out, ctx->q, ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_residual(amie_b200_ctx * ctx, const double * u, const double * f, double * r_out, double * norm_out)
+{
+    if(!ctx || !u || !f) return AMIE_B200_ERR_ARG ;
+    if(!ctx->have_values) { ctx->set_error("residual before set_values") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->p, u, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->z, f, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    SpmvCall c ;
+    c.x = ctx->p ; c.b = ctx->z ; c.y = ctx->q ; c.minus_b = true ; c.dot = DOT_YY ; c.finalize = FIN_STORE ;
+    int rc = launch_spmv(ctx, c) ;
+    if(rc) return rc ;
+    if((rc = ctx_sync_state(ctx, 2))) return rc ;
+    CUDA_TRY(ctx, cudaGetLastError()) ;
+    if(norm_out) *norm_out = sqrt(ctx->st_host[2].dot[0]) ;
+    if(r_out)
+    {
+        CUDA_TRY(ctx, cudaMemcpyAsync(r_out, ctx->q, ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    }
     return AMIE_B200_OK ;
 }
 

@@ -237,3 +237,54 @@ __global__ void __launch_bounds__(256) k_spmv_s2(SpmvArgs a)
             krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
     }
 }
+
+// ---------------------------------------------------------------- other strides (1, 4, 6): one thread per scalar row
+// The reference's inner_product also has stride 1, 4, 6 and generic cases (sparse/sparse_matrix.h:222-233,
+// :335-676): diffusion problems (1 DOF per node) and space-time elements (4, 6).  They are off the 2D/3D
+// elasticity headline path; this kernel keeps the drop-in usable for them (correct, persistent grid, fused dot,
+// no staging).
+template<int S, int DOT, bool MINUS_B>
+__global__ void __launch_bounds__(256) k_spmv_gen(SpmvArgs a)
+{
+    if(a.check_stop && a.st->stop) return ;
+    double dsum[2] = {0., 0.} ;
+    const uint64_t n = (uint64_t)a.nrows*S ;
+    for(uint64_t t = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; t < n ; t += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint32_t row = a.row0+(uint32_t)(t/S) ;
+        const int r = (int)(t%S) ;
+        uint32_t k0 = __ldg(a.rowptr+row) ;
+        const uint32_t k1 = __ldg(a.rowptr+row+1) ;
+        if(a.colstart_blk) k0 = row_lower_bound(a.col, k0, k1, a.colstart_blk) ;
+        double acc = 0. ;
+        for(uint32_t k = k0 ; k < k1 ; k++)
+        {
+            const double * v = a.vals+(size_t)k*S*S+r ;
+            const double * px = a.x+(size_t)__ldg(a.col+k)*S ;
+            #pragma unroll
+            for(int c = 0 ; c < S ; c++)
+                acc = fma(ld_stream(v+c*S), __ldg(px+c), acc) ;
+        }
+        const size_t i = (size_t)row*S+r ;
+        double yv = acc ;
+        if(MINUS_B) yv -= a.b[i] ;
+        yv *= a.sign ;
+        a.y[i] = yv ;
+        if(DOT == DOT_YX) dsum[0] = fma(yv, a.x[i], dsum[0]) ;
+        if(DOT == DOT_YY) dsum[0] = fma(yv, yv, dsum[0]) ;
+        if(DOT == DOT_YW) dsum[0] = fma(yv, a.w[i], dsum[0]) ;
+        if(DOT == DOT_OMEGA)
+        {
+            const double di = a.d ? a.d[i] : 1. ;
+            const double t2 = yv*di, s2 = a.w[i]*di ;
+            dsum[0] = fma(t2, s2, dsum[0]) ;
+            dsum[1] = fma(t2, t2, dsum[1]) ;
+        }
+    }
+    if(DOT != DOT_NONE)
+    {
+        double tot[2] ;
+        if(grid_sum<2, 256>(dsum, a.partials, a.st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
+            krylov_finalize(a.st, a.finalize, tot[0], tot[1]) ;
+    }
+}

@@ -118,6 +118,15 @@ static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 template<int DOT, bool MINUS_B>
 static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
+    if(ctx->S != 2 && ctx->S != 3)
+    {
+        const uint32_t nt = (uint32_t)(((uint64_t)args.nrows*ctx->S+255)/256) ;
+        const int grid = persistent_grid(ctx, 8, nt) ;
+        if(ctx->S == 1)      k_spmv_gen<1, DOT, MINUS_B><<<grid, 256, 0, ctx->stream>>>(args) ;
+        else if(ctx->S == 4) k_spmv_gen<4, DOT, MINUS_B><<<grid, 256, 0, ctx->stream>>>(args) ;
+        else                 k_spmv_gen<6, DOT, MINUS_B><<<grid, 256, 0, ctx->stream>>>(args) ;
+        return ;
+    }
     if(ctx->S == 3)
     {
         // default: row-thread pipeline (a smaller-stage configuration for short rows was measured
