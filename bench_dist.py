@@ -117,7 +117,7 @@ def run_distributed(args, pkg, dist, rank, world, local_rank):
                 "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.preset}-{args.n}", "ndof": int(N_glob), "stride": int(s), "eps": 1e-10, "nssor": 32,
-                           "maxit": -1, "precond": "InverseDiagonal", "parallelism": f"row-partition x{world} (NCCL halo send/recv + 2-double allreduce)",
+                           "maxit": -1, "precond": "InverseDiagonal", "parallelism": f"row-partition x{world}; halo + 2-double reductions over " + ("NVLink peer memory (device-side flags, no NCCL call per iteration)" if info["transport"] == "peer" else "NCCL send/recv + allreduce"),
                            "step": "one full PCG solve (reference control flow)", "iterations_per_step": its / max(1, args.steps),
                            "halo_block_columns_max": int(halo_max), "l2": "per-rank matrix is far larger than L2; no flush needed",
                            "generate_s": gen_s},

@@ -184,6 +184,9 @@ int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_gl
                                  uint64_t nnzb_local) ;
 int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s) ;
 /* halo block columns received / owned block columns sent per SpMV, interior block rows, number of peers */
+/* 1: halo + reductions go over NVLink peer memory (cudaIpc mappings, device-side flags); 0: NCCL calls.
+ * Env AMIE_B200_TRANSPORT=nccl forces the NCCL path.                                              */
+int amie_b200_dist_transport(const amie_b200_ctx * ctx) ;
 int amie_b200_dist_info(const amie_b200_ctx * ctx, uint64_t * nhalo_out, uint64_t * nsend_out,
                         uint64_t * interior_rows_out, int * npeers_out) ;
 

@@ -112,6 +112,7 @@ def test_dist_world2(pkg, ol, systems, preset, n):
         assert ok == bool(ret) and abs(int(nit) - int(oinfo.nit)) <= 2
         assert ok2 and abs(int(nit2) - int(nit)) <= 0 and np.array_equal(xl, x2)
         assert info["peers"] == 1 and info["halo"] > 0 and info["send"] > 0
+        assert info["transport"] == ("nccl" if os.environ.get("AMIE_B200_TRANSPORT") == "nccl" else "peer")
         x[r0 * S.stride:r1 * S.stride] = xl
         xb[r0 * S.stride:r1 * S.stride] = xbl
         assert okb

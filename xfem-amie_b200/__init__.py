@@ -99,6 +99,7 @@ def lib():
         L.amie_b200_dist_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
         L.amie_b200_dist_synth_to_device.argtypes = [vp, vp]
         L.amie_b200_dist_info.argtypes = [vp, vp, vp, vp, vp]
+        L.amie_b200_dist_transport.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -286,7 +287,8 @@ class Assembly:
     def dist_info(self):
         nh, ns, ni, npeer = u64(), u64(), u64(), ctypes.c_int()
         self.check(lib().amie_b200_dist_info(self.ctx, ctypes.byref(nh), ctypes.byref(ns), ctypes.byref(ni), ctypes.byref(npeer)))
-        return dict(halo=nh.value, send=ns.value, interior_rows=ni.value, peers=npeer.value)
+        return dict(halo=nh.value, send=ns.value, interior_rows=ni.value, peers=npeer.value,
+                    transport="peer" if lib().amie_b200_dist_transport(self.ctx) == 1 else "nccl")
 
     def spmv(self, x, minus_b=None, rowstart=0, colstart=0):
         """assign(y, A*x [- b], rowstart, colstart)"""

@@ -131,6 +131,149 @@ __global__ void k_finalize(KrylovState * st, int kind)
     krylov_finalize(st, kind, st->red_global[0], st->red_global[1]) ;
 }
 
+// ------------------------------------------------------------------ NVLink peer-memory transport
+// Instead of NCCL calls on the critical path, kernels store straight into the neighbours' memory
+// (cudaIpc-mapped) and signal with sequence-numbered flags; consumers spin on their OWN memory.
+//   halo   : k_halo_push writes this rank's boundary entries of the SpMV input vector directly into the halo tail
+//            of the same vector on each neighbour, then raises halo_flag[me] there; k_halo_wait (one warp) spins
+//            until every neighbour's flag reached the current push number; the boundary rows follow in-stream.
+//   reduce : k_finalize_peer writes (partial0, partial1, seq) into mailbox slot [seq&1][me] of EVERY rank, spins
+//            until its own mailbox holds `world` entries of this seq, adds them in rank order (same bits on every
+//            rank) and runs the scalar step.  Two slots suffice because a rank cannot be two executed reductions
+//            ahead of another (each one needs everybody's contribution).
+// Sequence numbers count EXECUTED operations (device-side counters that outlive the per-restart KrylovState):
+// kernels that return early after `stop` do so on every rank alike.
+#define PEER_MAX 8
+#define SYNC_FLAG_OFF 0
+#define SYNC_MBOX_OFF 512
+#define SYNC_BYTES 8192
+
+struct Mbox { double v0, v1 ; unsigned long long seq ; unsigned long long pad ; } ;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long * p)
+{
+    unsigned long long v ;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory") ;
+    return v ;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long * p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory") ;
+}
+
+struct PushArgs
+{
+    const double * v ;
+    const uint32_t * idx ;
+    int npeers ;
+    int S ;
+    uint64_t begin[PEER_MAX], end[PEER_MAX] ;       // block ranges inside idx
+    double * dst[PEER_MAX] ;                         // neighbour's vector + its owned length + my slice of its halo
+    unsigned long long * flag[PEER_MAX] ;            // neighbour's halo_flag[me]
+    KrylovState * st ;
+    unsigned int * ticket ;
+    unsigned long long * counters ;                  // [0] executed reductions, [1] executed halo pushes
+    int check_stop ;
+} ;
+
+__global__ void __launch_bounds__(256) k_halo_push(PushArgs a)
+{
+    if(a.check_stop && a.st->stop) return ;
+    __shared__ bool is_last ;
+    const uint64_t total = a.end[a.npeers-1] ;
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < total*a.S ; i += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint64_t k = i/a.S ;
+        const int c = (int)(i-k*a.S) ;
+        int q = 0 ;
+        #pragma unroll
+        for(int t = 1 ; t < PEER_MAX ; t++) if(t < a.npeers && k >= a.begin[t]) q = t ;
+        a.dst[q][(k-a.begin[q])*a.S+c] = a.v[(uint64_t)a.idx[k]*a.S+c] ;
+    }
+    __threadfence_system() ;
+    __syncthreads() ;
+    if(threadIdx.x == 0)
+    {
+        const unsigned int t = atomicAdd(a.ticket, 1u) ;
+        is_last = (t == gridDim.x-1) ;
+    }
+    __syncthreads() ;
+    if(!is_last) return ;
+    __threadfence_system() ;
+    if(threadIdx.x == 0)
+    {
+        *a.ticket = 0u ;
+        const unsigned long long seq = a.counters[1]+1ull ;
+        a.counters[1] = seq ;
+        for(int q = 0 ; q < a.npeers ; q++) st_release_sys(a.flag[q], seq) ;
+    }
+}
+
+struct WaitArgs
+{
+    int npeers ;
+    const unsigned long long * flag[PEER_MAX] ;      // my halo_flag[neighbour]
+    KrylovState * st ;
+    const unsigned long long * counters ;
+    int check_stop ;
+} ;
+
+__global__ void k_halo_wait(WaitArgs a)
+{
+    if(a.check_stop && a.st->stop) return ;
+    const unsigned long long seq = a.counters[1] ;
+    if((int)threadIdx.x < a.npeers)
+        while(ld_acquire_sys(a.flag[threadIdx.x]) < seq) { }
+    __threadfence_system() ;
+}
+
+struct ReduceArgs
+{
+    int world, rank ;
+    Mbox * mbox[PEER_MAX] ;                          // mailbox of every rank (own included), [2][PEER_MAX]
+    KrylovState * st ;
+    unsigned long long * counters ;
+    int kind ;
+} ;
+
+__global__ void k_finalize_peer(ReduceArgs a)
+{
+    if(a.kind != FIN_STORE && a.kind != FIN_DEFER_SET && a.st->stop) return ;
+    const int lane = threadIdx.x ;
+    const unsigned long long seq = a.counters[0]+1ull ;
+    const int slot = (int)(seq & 1ull) ;
+    if(lane < a.world)
+    {
+        Mbox * m = a.mbox[lane]+slot*PEER_MAX+a.rank ;
+        m->v0 = a.st->red_local[0] ;
+        m->v1 = a.st->red_local[1] ;
+        __threadfence_system() ;
+        st_release_sys(&m->seq, seq) ;
+    }
+    double v0 = 0., v1 = 0. ;
+    if(lane < a.world)
+    {
+        Mbox * m = a.mbox[a.rank]+slot*PEER_MAX+lane ;
+        while(ld_acquire_sys(&m->seq) != seq) { }
+        v0 = *(volatile double *)&m->v0 ;
+        v1 = *(volatile double *)&m->v1 ;
+    }
+    // rank order, the same on every rank
+    double s0 = 0., s1 = 0. ;
+    for(int q = 0 ; q < a.world ; q++)
+    {
+        s0 += __shfl_sync(0xffffffffu, v0, q) ;
+        s1 += __shfl_sync(0xffffffffu, v1, q) ;
+    }
+    if(lane == 0)
+    {
+        a.counters[0] = seq ;
+        a.st->red_global[0] = s0 ;
+        a.st->red_global[1] = s1 ;
+        if(a.kind != FIN_DEFER_SET) krylov_finalize(a.st, a.kind, s0, s1) ;      // FIN_DEFER_SET = barrier only
+    }
+}
+
 // diagonal of a row whose (remapped) column indices are no longer sorted: linear scan
 template<int S>
 __global__ void k_inverse_diagonal_linear(const uint32_t * rowptr, const uint32_t * col, const double * vals, uint64_t nrows, double * d)
@@ -169,6 +312,17 @@ struct DistState
     double * sendbuf = nullptr ;        // device
     uint32_t int_a = 0, int_b = 0 ;     // interior block rows [a, b)
     double * scratch = nullptr ;        // device, 2 doubles (max reductions)
+    std::vector<long long> need_all ;   // need_all[i*world+j] = halo block columns rank i receives from rank j
+
+    // ---- peer-memory transport (NVLink loads/stores through cudaIpc mappings)
+    bool peer_on = false ;
+    unsigned char * sync = nullptr ;                 // this rank's flags + mailboxes
+    std::vector<unsigned char *> sync_of ;           // [world]: every rank's sync buffer as seen from here
+    std::vector<void *> ipc_opened ;                 // mappings to close
+    struct VecMap { const double * base ; uint64_t gen ; std::vector<double *> of_peer ; } ;
+    std::vector<VecMap> vec_maps ;                   // SpMV input vectors already exchanged
+    unsigned int * push_ticket = nullptr ;
+    unsigned long long * counters = nullptr ;        // device: executed reductions / halo pushes (never reset)
 } ;
 
 int dist_world(const amie_b200_ctx * ctx) { return ctx->dist ? ctx->dist->world : 1 ; }
@@ -177,6 +331,10 @@ void dist_destroy(amie_b200_ctx * ctx)
 {
     DistState * d = ctx->dist ;
     if(!d) return ;
+    for(void * m : d->ipc_opened) cudaIpcCloseMemHandle(m) ;
+    if(d->sync) cudaFree(d->sync) ;
+    if(d->push_ticket) cudaFree(d->push_ticket) ;
+    if(d->counters) cudaFree(d->counters) ;
     if(d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm) ;
     if(d->send_idx) cudaFree(d->send_idx) ;
     if(d->sendbuf) cudaFree(d->sendbuf) ;
@@ -189,9 +347,24 @@ void dist_destroy(amie_b200_ctx * ctx)
 }
 
 // sum st->red_local over the ranks, then run the scalar step `kind` on every rank
+static void launch_finalize_peer(amie_b200_ctx * ctx, int kind)
+{
+    DistState * d = ctx->dist ;
+    ReduceArgs ra ;
+    ra.world = d->world ; ra.rank = d->rank ; ra.st = ctx->st ; ra.kind = kind ; ra.counters = d->counters ;
+    for(int r = 0 ; r < d->world ; r++) ra.mbox[r] = reinterpret_cast<Mbox *>(d->sync_of[r]+SYNC_MBOX_OFF) ;
+    k_finalize_peer<<<1, 32, 0, ctx->stream>>>(ra) ;
+    ctx->stats.kernel_launches++ ;
+}
+
 int dist_finalize(amie_b200_ctx * ctx, int kind)
 {
     DistState * d = ctx->dist ;
+    if(d->peer_on)
+    {
+        launch_finalize_peer(ctx, kind) ;
+        return AMIE_B200_OK ;
+    }
     NCCL_TRY(ctx, g_nccl.AllReduce(ctx->st->red_local, ctx->st->red_global, 2, ncclDouble, ncclSum, d->comm, ctx->stream)) ;
     k_finalize<<<1, 1, 0, ctx->stream>>>(ctx->st, kind) ;
     ctx->stats.kernel_launches++ ;
@@ -217,6 +390,86 @@ int dist_inverse_diagonal(amie_b200_ctx * ctx)
     return AMIE_B200_OK ;
 }
 
+// all ranks exchange the cudaIpc handle of one allocation each; out[r] = rank r's pointer as seen from here
+// (nullptr for ranks that are not opened; `only_peers`: open the neighbours' mappings only)
+static int ipc_exchange(amie_b200_ctx * ctx, void * mine, bool only_peers, std::vector<void *> & out)
+{
+    DistState * d = ctx->dist ;
+    cudaIpcMemHandle_t h ;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, mine)) ;
+    unsigned char * dbuf = nullptr ;
+    CUDA_TRY(ctx, cudaMalloc(&dbuf, (size_t)(d->world+1)*sizeof(h))) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dbuf, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream)) ;
+    NCCL_TRY(ctx, g_nccl.AllGather(dbuf, dbuf+sizeof(h), sizeof(h), ncclChar, d->comm, ctx->stream)) ;
+    std::vector<cudaIpcMemHandle_t> all(d->world) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), dbuf+sizeof(h), (size_t)d->world*sizeof(h), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    cudaFree(dbuf) ;
+    out.assign(d->world, nullptr) ;
+    out[d->rank] = mine ;
+    for(int r = 0 ; r < d->world ; r++)
+    {
+        if(r == d->rank) continue ;
+        if(only_peers)
+        {
+            bool is_peer = false ;
+            for(const DistPeer & p : d->peers) if(p.rank == r) is_peer = true ;
+            if(!is_peer) continue ;
+        }
+        void * ptr = nullptr ;
+        CUDA_TRY(ctx, cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess)) ;
+        d->ipc_opened.push_back(ptr) ;
+        out[r] = ptr ;
+    }
+    return AMIE_B200_OK ;
+}
+
+// flags + mailboxes of every rank mapped everywhere; called once the halo lists exist
+static int peer_setup(amie_b200_ctx * ctx)
+{
+    DistState * d = ctx->dist ;
+    d->peer_on = false ;
+    const char * e = getenv("AMIE_B200_TRANSPORT") ;
+    if(e && std::string(e) == "nccl") return AMIE_B200_OK ;
+    if(d->world > PEER_MAX || (int)d->peers.size() > PEER_MAX) return AMIE_B200_OK ;
+    if(!d->sync)
+    {
+        CUDA_TRY(ctx, cudaMalloc(&d->sync, SYNC_BYTES)) ;
+        CUDA_TRY(ctx, cudaMalloc(&d->push_ticket, sizeof(unsigned int))) ;
+        CUDA_TRY(ctx, cudaMemset(d->push_ticket, 0, sizeof(unsigned int))) ;
+        CUDA_TRY(ctx, cudaMalloc(&d->counters, 2*sizeof(unsigned long long))) ;
+        CUDA_TRY(ctx, cudaMemset(d->counters, 0, 2*sizeof(unsigned long long))) ;
+        CUDA_TRY(ctx, cudaMemset(d->sync, 0, SYNC_BYTES)) ;
+        std::vector<void *> out ;
+        int rc = ipc_exchange(ctx, d->sync, false, out) ;
+        if(rc) return rc ;
+        d->sync_of.resize(d->world) ;
+        for(int r = 0 ; r < d->world ; r++) d->sync_of[r] = static_cast<unsigned char *>(out[r]) ;
+    }
+    // every rank's memset must be done before anybody signals: one NCCL all-reduce as a barrier
+    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclSum, d->comm, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    d->peer_on = true ;
+    return AMIE_B200_OK ;
+}
+
+// neighbours' views of one SpMV input vector (exchanged collectively the first time the vector is used)
+static int peer_vector(amie_b200_ctx * ctx, const double * base, const std::vector<double *> ** out)
+{
+    DistState * d = ctx->dist ;
+    for(auto & m : d->vec_maps)
+        if(m.base == base && m.gen == ctx->alloc_gen) { *out = &m.of_peer ; return AMIE_B200_OK ; }
+    std::vector<void *> all ;
+    int rc = ipc_exchange(ctx, const_cast<double *>(base), true, all) ;
+    if(rc) return rc ;
+    DistState::VecMap m ;
+    m.base = base ; m.gen = ctx->alloc_gen ;
+    for(const DistPeer & p : d->peers) m.of_peer.push_back(static_cast<double *>(all[p.rank])) ;
+    d->vec_maps.push_back(m) ;
+    *out = &d->vec_maps.back().of_peer ;
+    return AMIE_B200_OK ;
+}
+
 // y = A x on the local rows with the halo exchange of x overlapped with the interior rows
 int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
 {
@@ -236,7 +489,31 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
         e1 = ctx->ev_pool[ctx->ev_used++] ;
         cudaEventRecord(e0, ctx->stream) ;
     }
-    if(!d->peers.empty())
+    const bool peer = d->peer_on && !d->peers.empty() ;
+    if(peer)
+    {
+        // stores straight into the neighbours' halo tails over NVLink, then a flag; no NCCL call
+        const std::vector<double *> * of_peer = nullptr ;
+        int prc = peer_vector(ctx, xv, &of_peer) ;
+        if(prc) return prc ;
+        PushArgs pa ;
+        pa.v = xv ; pa.idx = d->send_idx ; pa.S = S ; pa.st = ctx->st ; pa.ticket = d->push_ticket ; pa.counters = d->counters ; pa.check_stop = c.check_stop ;
+        pa.npeers = (int)d->peers.size() ;
+        for(int t = 0 ; t < pa.npeers ; t++)
+        {
+            const DistPeer & p = d->peers[t] ;
+            const int q = p.rank ;
+            uint64_t off_q = 0 ;             // where my columns start inside q's halo
+            for(int j = 0 ; j < d->rank ; j++) if(j != q) off_q += (uint64_t)d->need_all[(size_t)q*d->world+j] ;
+            pa.begin[t] = p.send_off ; pa.end[t] = p.send_off+p.send_cnt ;
+            pa.dst[t] = (*of_peer)[t]+(d->bounds[q+1]-d->bounds[q])*S+off_q*S ;
+            pa.flag[t] = reinterpret_cast<unsigned long long *>(d->sync_of[q]+SYNC_FLAG_OFF)+d->rank ;
+        }
+        for(int t = pa.npeers ; t < PEER_MAX ; t++) { pa.begin[t] = pa.end[t] = pa.end[pa.npeers-1] ; pa.dst[t] = nullptr ; pa.flag[t] = nullptr ; }
+        k_halo_push<<<vec_grid(ctx, std::max<uint64_t>(d->nsend*S, 1)), 256, 0, ctx->stream>>>(pa) ;
+        ctx->stats.kernel_launches++ ;
+    }
+    else if(!d->peers.empty())
     {
         if(d->nsend)
         {
@@ -265,10 +542,23 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
         return r ;
     } ;
     if((rc = part(d->int_a, d->int_b))) return rc ;                       // interior rows: no halo column
-    if(!d->peers.empty()) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, d->ev_comm, 0)) ;
+    if(peer)
+    {
+        WaitArgs wa ;
+        wa.npeers = (int)d->peers.size() ; wa.st = ctx->st ; wa.counters = d->counters ; wa.check_stop = c.check_stop ;
+        for(int t = 0 ; t < wa.npeers ; t++)
+            wa.flag[t] = reinterpret_cast<const unsigned long long *>(d->sync+SYNC_FLAG_OFF)+d->peers[t].rank ;
+        for(int t = wa.npeers ; t < PEER_MAX ; t++) wa.flag[t] = nullptr ;
+        k_halo_wait<<<1, 32, 0, ctx->stream>>>(wa) ;
+        ctx->stats.kernel_launches++ ;
+    }
+    else if(!d->peers.empty()) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, d->ev_comm, 0)) ;
     if((rc = part(0, d->int_a))) return rc ;                              // boundary rows
     if((rc = part(d->int_b, (uint32_t)ctx->nb))) return rc ;
     if(dot && (rc = dist_finalize(ctx, c.finalize))) return rc ;
+    // no reduction follows a plain SpMV: a mailbox round keeps a fast neighbour from overwriting this rank's halo
+    // tail with its NEXT push while the boundary rows above still read it
+    if(!dot && peer) launch_finalize_peer(ctx, FIN_DEFER_SET) ;
     if(e1) cudaEventRecord(e1, ctx->stream) ;
     ctx->stats.spmv_launches++ ;
     if(c.smoothing) ctx->stats.smoothing_spmv++ ;
@@ -322,6 +612,7 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
     cudaFree(dneed) ; cudaFree(dall) ;
 
+    d->need_all = all ;
     d->peers.clear() ;
     d->nsend = 0 ;
     for(int q = 0 ; q < d->world ; q++)
@@ -379,7 +670,11 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     d->int_a = best_a ; d->int_b = best_b ;
 
     ctx->ncols_local = (uint64_t)nbl+d->nhalo ;
-    return ctx_alloc_vectors(ctx) ;
+    int arc = ctx_alloc_vectors(ctx) ;
+    if(arc) return arc ;
+    // vectors may have been re-allocated: earlier mappings of them are stale
+    d->vec_maps.clear() ;
+    return peer_setup(ctx) ;
 }
 
 extern "C" {
@@ -462,6 +757,12 @@ int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * 
     cudaFree(btmp) ;
     ctx->have_rhs = true ;
     return AMIE_B200_OK ;
+}
+
+int amie_b200_dist_transport(const amie_b200_ctx * ctx)
+{
+    if(!ctx || !ctx->dist) return AMIE_B200_ERR_STATE ;
+    return ctx->dist->peer_on ? 1 : 0 ;
 }
 
 int amie_b200_dist_info(const amie_b200_ctx * ctx, uint64_t * nhalo_out, uint64_t * nsend_out, uint64_t * interior_rows_out, int * npeers_out)
