@@ -424,31 +424,50 @@ static int ipc_exchange(amie_b200_ctx * ctx, void * mine, bool only_peers, std::
     return AMIE_B200_OK ;
 }
 
-// flags + mailboxes of every rank mapped everywhere; called once the halo lists exist
+// flags + mailboxes of every rank mapped everywhere; called once the halo lists exist.
+// Collective.  If ANY rank cannot map its peers (no P2P path, IPC disabled in the container ...) every rank
+// falls back to the NCCL transport: the decision is agreed with one all-reduce.
+static int peer_setup_local(amie_b200_ctx * ctx)
+{
+    DistState * d = ctx->dist ;
+    if(d->sync) return AMIE_B200_OK ;
+    CUDA_TRY(ctx, cudaMalloc(&d->sync, SYNC_BYTES)) ;
+    CUDA_TRY(ctx, cudaMalloc(&d->push_ticket, sizeof(unsigned int))) ;
+    CUDA_TRY(ctx, cudaMemset(d->push_ticket, 0, sizeof(unsigned int))) ;
+    CUDA_TRY(ctx, cudaMalloc(&d->counters, 2*sizeof(unsigned long long))) ;
+    CUDA_TRY(ctx, cudaMemset(d->counters, 0, 2*sizeof(unsigned long long))) ;
+    CUDA_TRY(ctx, cudaMemset(d->sync, 0, SYNC_BYTES)) ;
+    return AMIE_B200_OK ;
+}
+
 static int peer_setup(amie_b200_ctx * ctx)
 {
     DistState * d = ctx->dist ;
     d->peer_on = false ;
     const char * e = getenv("AMIE_B200_TRANSPORT") ;
-    if(e && std::string(e) == "nccl") return AMIE_B200_OK ;
-    if(d->world > PEER_MAX || (int)d->peers.size() > PEER_MAX) return AMIE_B200_OK ;
-    if(!d->sync)
+    const bool want = !(e && std::string(e) == "nccl") && d->world <= PEER_MAX && (int)d->peers.size() <= PEER_MAX ;
+    double ok = want ? 1. : 0. ;
+    if(want && peer_setup_local(ctx) != AMIE_B200_OK) ok = 0. ;
+    // the handle exchange itself is collective and must run on every rank once any rank wants it
+    CUDA_TRY(ctx, cudaMemcpyAsync(d->scratch, &ok, sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclMin, d->comm, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ok, d->scratch+1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    if(ok < 1.) return AMIE_B200_OK ;                      // NCCL transport on every rank
+    if(d->sync_of.empty())
     {
-        CUDA_TRY(ctx, cudaMalloc(&d->sync, SYNC_BYTES)) ;
-        CUDA_TRY(ctx, cudaMalloc(&d->push_ticket, sizeof(unsigned int))) ;
-        CUDA_TRY(ctx, cudaMemset(d->push_ticket, 0, sizeof(unsigned int))) ;
-        CUDA_TRY(ctx, cudaMalloc(&d->counters, 2*sizeof(unsigned long long))) ;
-        CUDA_TRY(ctx, cudaMemset(d->counters, 0, 2*sizeof(unsigned long long))) ;
-        CUDA_TRY(ctx, cudaMemset(d->sync, 0, SYNC_BYTES)) ;
         std::vector<void *> out ;
-        int rc = ipc_exchange(ctx, d->sync, false, out) ;
-        if(rc) return rc ;
+        double mapped = ipc_exchange(ctx, d->sync, false, out) == AMIE_B200_OK ? 1. : 0. ;
+        cudaGetLastError() ;                               // a failed cudaIpcOpenMemHandle must not poison later calls
+        CUDA_TRY(ctx, cudaMemcpyAsync(d->scratch, &mapped, sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclMin, d->comm, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&mapped, d->scratch+1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+        if(mapped < 1.) { ctx->err.clear() ; return AMIE_B200_OK ; }
         d->sync_of.resize(d->world) ;
         for(int r = 0 ; r < d->world ; r++) d->sync_of[r] = static_cast<unsigned char *>(out[r]) ;
     }
-    // every rank's memset must be done before anybody signals: one NCCL all-reduce as a barrier
-    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclSum, d->comm, ctx->stream)) ;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    // (the all-reduces above also guarantee that every rank's memset finished before anybody signals)
     d->peer_on = true ;
     return AMIE_B200_OK ;
 }
