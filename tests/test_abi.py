@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -48,3 +49,19 @@ def test_stats_struct_layout_matches_header(pkg):
             fields.append((n.strip(), typ))
     assert [f for f, _ in fields] == [f for f, _ in pkg.Stats._fields_]
     assert ctypes.sizeof(pkg.Stats) == 8 * len(fields)
+
+
+def test_nccl_load_order_keeps_torch_importable():
+    """The library dlopens NCCL lazily; in a Python host it must pick the copy torch was built against,
+    or a later `import torch` in the same process dies on an undefined NCCL symbol."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as g\n"
+        "pkg = g.load_package()\n"
+        "assert len(pkg.nccl_unique_id()) == 128\n"
+        "import torch\n"
+        "import torch.distributed\n"
+        "print('ok')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -268,6 +268,7 @@ class Assembly:
 
     # -- row-partitioned context (one process per GPU)
     def dist_init(self, rank, world, id128, bounds):
+        _preload_nccl()
         self._bounds = np.ascontiguousarray(bounds, np.uint64)
         buf = (ctypes.c_char * 128).from_buffer_copy(bytes(id128))
         self.check(lib().amie_b200_dist_init(self.ctx, int(rank), int(world), ctypes.cast(buf, ctypes.c_void_p), _ptr(self._bounds)))
@@ -448,7 +449,32 @@ class Synth:
         assembly.check(lib().amie_b200_synth_to_device(assembly.ctx, self.handle))
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """Python hosts usually carry torch, whose libtorch_cuda.so needs the NCCL wheel it was built with
+    (nvidia/nccl/lib/libnccl.so.2).  ld.so shares libraries by SONAME, so whichever libnccl.so.2 enters the
+    process first serves both torch and this library: load the wheel's copy first (no torch import needed),
+    else leave the choice to the C loader (AMIE_B200_NCCL_LIB, then the system libnccl.so.2)."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("AMIE_B200_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+            return
+
+
 def nccl_unique_id():
+    _preload_nccl()
     buf = ctypes.create_string_buffer(128)
     rc = lib().amie_b200_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p))
     if rc:

@@ -52,9 +52,12 @@ NcclApi g_nccl ;
 bool load_nccl(std::string & err)
 {
     if(g_nccl.handle) return true ;
-    const char * names[] = { "libnccl.so.2", "libnccl.so" } ;
+    // AMIE_B200_NCCL_LIB names the copy to use; a process that also loads another NCCL user (torch) must make
+    // both resolve to the SAME libnccl.so.2 -- ld.so shares objects by SONAME, whichever is loaded first wins.
+    const char * names[] = { getenv("AMIE_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so" } ;
     for(const char * n : names)
     {
+        if(!n || !*n) continue ;
         g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL) ;
         if(g_nccl.handle) break ;
     }
