@@ -11,6 +11,10 @@
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
+// elements.bin (optional 6th argument): the elements FeatureTree::assemble handed to the Assembly, in its order
+//            (features/features.cpp:3360-3403): uint64 n_elem, npe, stride; ids u32[n_elem*npe];
+//            Ke f64[n_elem*npe*npe*s*s] (block (j,k) column-major: [m*s+n] = getCachedElementaryMatrix()[j][k][n][m]);
+//            scales f64[n_elem] (all 1: single layer)
 #include "features/features.h"
 #include "features/sample.h"
 #include "features/sample3d.h"
@@ -21,6 +25,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace Amie ;
 
@@ -46,6 +51,37 @@ static void dump_system(const char * path, Assembly * K)
     fclose(f) ;
 }
 
+template<class MESH>
+static void dump_elements(const char * path, MESH * mesh, size_t s)
+{
+    std::vector<uint32_t> ids ;
+    std::vector<double> ke ;
+    uint64_t n_elem = 0, npe = 0 ;
+    for(auto j = mesh->begin() ; j != mesh->end() ; j++)
+    {
+        if(!(j->getBehaviour() && j->getBehaviour()->type != VOID_BEHAVIOUR)) continue ;
+        std::vector<size_t> id = j->getDofIds() ;
+        auto & cached = j->getCachedElementaryMatrix() ;
+        if(!npe) npe = id.size() ;
+        if(id.size() != npe || cached.size() != npe) { fprintf(stderr, "dump_elements: ragged element\n") ; exit(3) ; }
+        for(size_t a = 0 ; a < npe ; a++) ids.push_back((uint32_t)id[a]) ;
+        for(size_t a = 0 ; a < npe ; a++)
+            for(size_t b = 0 ; b < npe ; b++)
+                for(size_t m = 0 ; m < s ; m++)
+                    for(size_t n = 0 ; n < s ; n++)
+                        ke.push_back(cached[a][b][n][m]) ;
+        n_elem++ ;
+    }
+    FILE * f = fopen(path, "wb") ;
+    uint64_t h[3] = { n_elem, npe, s } ;
+    fwrite(h, 8, 3, f) ;
+    fwrite(ids.data(), 4, ids.size(), f) ;
+    fwrite(ke.data(), 8, ke.size(), f) ;
+    std::vector<double> scales(n_elem, 1.) ;
+    fwrite(scales.data(), 8, n_elem, f) ;
+    fclose(f) ;
+}
+
 int main(int argc, char ** argv)
 {
     if(argc < 4) { fprintf(stderr, "usage: %s 2d|3d <sampling> <out.bin> [dump.bin]\n", argv[0]) ; return 2 ; }
@@ -63,6 +99,7 @@ int main(int argc, char ** argv)
         F.step() ;
         write_vec(argv[3], F.getDisplacements()) ;
         if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
+        if(argc > 5) dump_elements(argv[5], F.get2DMesh(), 2) ;
     }
     else
     {
@@ -88,6 +125,7 @@ int main(int argc, char ** argv)
         F.step() ;
         write_vec(argv[3], F.getDisplacements()) ;
         if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
+        if(argc > 5) dump_elements(argv[5], F.get3DMesh(), 3) ;
     }
     return 0 ;
 }

@@ -9,8 +9,10 @@
 //   Amie::BiConjugateGradientStabilized::solve (solvers/biconjugategradientstabilized.cpp:12-148)
 //   Amie::assign(y, A*x[-b], rowstart, colstart) (sparse/sparse_matrix.cpp:462-547)
 //   CoordinateIndexedSparseMatrix::inverseDiagonal (sparse/sparse_matrix.cpp:216-231)
+//   Amie::Assembly::setBoundaryConditions     (solvers/assembly.cpp:125-383)
 // No reference source is copied here; only its public headers are included.
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <iostream>
@@ -188,6 +190,56 @@ int amie_ref_inverse_diagonal(int stride, uint64_t nb, const uint32_t * row_size
     fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, nullptr) ;
     Vector d = a.coordinateIndexedMatrix->inverseDiagonal() ;
     std::memcpy(d_out, &d[0], d.size()*sizeof(double)) ;
+    return 0 ;
+}
+
+// The unmodified Assembly::setBoundaryConditions on a hand-filled Assembly.  `dim` is set to
+// SPACE_ONE_DIMENSIONAL so that the space-time rowstart block at the end of the function
+// (solvers/assembly.cpp:326-360), which dereferences element2d[0]/element3d[0], is not entered:
+// the elimination itself (:137-324) does not look at `dim`.
+// fix_type: 0 = SET_ALONG_XI, 1 = SET_ALONG_ETA, 2 = SET_ALONG_ZETA, 3 = SET_ALONG_INDEXED_AXIS (all eliminated alike).
+int amie_ref_set_boundary_conditions(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index,
+                                     uint64_t nnzb, double * array_padded, double * forces, double * natural,
+                                     double * add_to_forces,
+                                     uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                                     uint64_t nforce, const uint32_t * force_ids, const double * force_values)
+{
+    CerrCapture quiet ;
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, forces) ;
+    const size_t n = nb*stride ;
+    a.naturalBoundaryConditionForces.resize(n) ;
+    a.naturalBoundaryConditionForces = 0. ;
+    if(natural) std::memcpy(&a.naturalBoundaryConditionForces[0], natural, n*sizeof(double)) ;
+    if(add_to_forces)
+    {
+        a.addToExternalForces.resize(n) ;
+        std::memcpy(&a.addToExternalForces[0], add_to_forces, n*sizeof(double)) ;
+    }
+    else
+        a.addToExternalForces.resize(0) ;
+    a.dim = Amie::SPACE_ONE_DIMENSIONAL ;
+    a.ndof = stride ;
+    const Amie::LagrangeMultiplierType kinds[3] = { Amie::SET_ALONG_XI, Amie::SET_ALONG_ETA, Amie::SET_ALONG_ZETA } ;
+    const Amie::LagrangeMultiplierType fkinds[3] = { Amie::SET_FORCE_XI, Amie::SET_FORCE_ETA, Amie::SET_FORCE_ZETA } ;
+    for(uint64_t i = 0 ; i < nfix ; i++)
+    {
+        Amie::LagrangeMultiplier m(std::valarray<unsigned int>(), Vector(), fix_values[i], (int)fix_ids[i]) ;
+        m.type = kinds[fix_ids[i]%stride%3] ;
+        a.multipliers.push_back(m) ;
+    }
+    for(uint64_t i = 0 ; i < nforce ; i++)
+    {
+        Amie::LagrangeMultiplier m(std::valarray<unsigned int>(), Vector(), force_values[i], (int)force_ids[i]) ;
+        m.type = fkinds[force_ids[i]%stride%3] ;
+        a.multipliers.push_back(m) ;
+    }
+    std::stable_sort(a.multipliers.begin(), a.multipliers.end()) ;      // make_final sorts them (assembly.cpp:428)
+    a.setBoundaryConditions(false) ;
+    std::memcpy(array_padded, &a.coordinateIndexedMatrix->array[0], a.coordinateIndexedMatrix->array.size()*sizeof(double)) ;
+    std::memcpy(forces, &a.externalForces[0], n*sizeof(double)) ;
+    if(natural) std::memcpy(natural, &a.naturalBoundaryConditionForces[0], n*sizeof(double)) ;
+    if(add_to_forces) std::memcpy(add_to_forces, &a.addToExternalForces[0], n*sizeof(double)) ;
     return 0 ;
 }
 

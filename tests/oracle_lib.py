@@ -184,3 +184,76 @@ def ref_inverse_diagonal(S):
 
 def ref_max_threads():
     return ref().amie_ref_max_threads()
+
+
+# ------------------------------------------------------------------ value assembly + Dirichlet elimination
+
+class Elements:
+    """Element connectivity + elementary matrices in the layout of include/amie_b200.h:
+    ids u32[n_elem, npe] (0xFFFFFFFF = unused slot); ke f64[n_elem, npe, npe, s*s] with block (j,k) column-major."""
+
+    def __init__(self, stride, ids, ke, scales=None):
+        self.stride = int(stride)
+        self.ids = np.ascontiguousarray(ids, np.uint32)
+        self.n_elem, self.npe = self.ids.shape
+        self.ke = np.ascontiguousarray(ke, np.float64).reshape(self.n_elem, self.npe, self.npe, self.stride * self.stride)
+        self.scales = np.ones(self.n_elem) if scales is None else np.ascontiguousarray(scales, np.float64)
+
+    def pattern(self, nb):
+        """row_size / column_index of the union of node pairs (plus every diagonal), as Assembly::make_final
+        builds it from a std::set of pairs (solvers/assembly.cpp:455-521)."""
+        ids = self.ids.astype(np.int64)
+        rows, cols = [np.arange(nb)], [np.arange(nb)]
+        for j in range(self.npe):
+            for k in range(self.npe):
+                ok = (ids[:, j] != 0xFFFFFFFF) & (ids[:, k] != 0xFFFFFFFF)
+                rows.append(ids[ok, j])
+                cols.append(ids[ok, k])
+        key = np.unique(np.concatenate(rows) * nb + np.concatenate(cols))
+        r, c = key // nb, key % nb
+        return np.bincount(r, minlength=nb).astype(np.uint32), c.astype(np.uint32)
+
+
+def oracle_assemble(stride, nb, row_size, column_index, el):
+    cl = stride + stride % 2
+    array = np.zeros(column_index.size * stride * cl)
+    rc = oracle().amie_oracle_assemble(int(stride), u64(nb), _vp(row_size), _vp(column_index), u64(column_index.size),
+                                       u64(el.n_elem), int(el.npe), _vp(el.ids), _vp(el.ke), _vp(el.scales), _vp(array))
+    assert rc == 0, "element couples nodes outside the sparsity pattern"
+    return array
+
+
+def _bc_args(S_or_tuple, array, forces, natural, add, fix_ids, fix_values, force_ids, force_values):
+    stride, nb, row_size, column_index = S_or_tuple
+    fix_ids = np.ascontiguousarray(fix_ids, np.uint32)
+    fix_values = np.ascontiguousarray(fix_values, np.float64)
+    force_ids = np.ascontiguousarray(force_ids if force_ids is not None else [], np.uint32)
+    force_values = np.ascontiguousarray(force_values if force_values is not None else [], np.float64)
+    keep = (fix_ids, fix_values, force_ids, force_values)
+    return keep, (int(stride), u64(nb), _vp(row_size), _vp(column_index), u64(column_index.size), _vp(array), _vp(forces),
+                  _vp(natural), _vp(add), u64(fix_ids.size), _vp(fix_ids), _vp(fix_values), u64(force_ids.size),
+                  _vp(force_ids), _vp(force_values))
+
+
+def oracle_set_bcs(stride, nb, row_size, column_index, array, forces, fix_ids, fix_values, force_ids=None,
+                   force_values=None, natural=None, add_to_forces=None):
+    """In place on copies; returns (array, forces, natural, add_to_forces)."""
+    array, forces = array.copy(), forces.copy()
+    natural = None if natural is None else natural.copy()
+    add = None if add_to_forces is None else add_to_forces.copy()
+    keep, args = _bc_args((stride, nb, row_size, column_index), array, forces, natural, add, fix_ids, fix_values,
+                          force_ids, force_values)
+    oracle().amie_oracle_set_boundary_conditions(*args)
+    return array, forces, natural, add
+
+
+def ref_set_bcs(stride, nb, row_size, column_index, array, forces, fix_ids, fix_values, force_ids=None,
+                force_values=None, natural=None, add_to_forces=None):
+    array, forces = array.copy(), forces.copy()
+    natural = None if natural is None else natural.copy()
+    add = None if add_to_forces is None else add_to_forces.copy()
+    keep, args = _bc_args((stride, nb, row_size, column_index), array, forces, natural, add, fix_ids, fix_values,
+                          force_ids, force_values)
+    rc = ref().amie_ref_set_boundary_conditions(*args)
+    assert rc == 0
+    return array, forces, natural, add
