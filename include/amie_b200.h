@@ -117,6 +117,42 @@ int amie_b200_bicgstab_resident(amie_b200_ctx * ctx, int precond_kind, double ep
  * milliseconds per launch (CUDA events on the launch stream) in *ms_out.                  */
 int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double * ms_out) ;
 
+/* ------------------------------------------------------------------ device-side value assembly
+ * The step that PRODUCES the array the solve consumes, for repeated re-solves on one topology (damage steps):
+ * upload the elementary matrices that changed instead of the whole padded array.  Results are bit-identical to
+ * the reference's (element-order Kahan sums replayed per stored entry; see csrc/assemble.cu).
+ *
+ * set_elements -- once per topology, after set_structure: element e couples the nodes (block rows)
+ *   elem_ids[e*npe .. e*npe+npe) ; 0xFFFFFFFF marks an unused slot (elements with fewer nodes).  Element ORDER is the
+ *   order Assembly::element2d / element3d holds them in (it fixes the summation order).  Builds, on the device, the
+ *   list of elementary blocks landing on every stored block.  AMIE_B200_ERR_ARG if an element couples two nodes
+ *   whose block is not in the sparsity pattern.
+ * update_elements -- elementary matrices of elements [first, first+count):
+ *   ke[((e-first)*npe + j)*npe + k)*s*s + m*s + n] = getCachedElementaryMatrix()[j][k][n][m]  (blocks column-major),
+ *   scales (NULL = 1) = Assembly::scales.  Marks the stored blocks those elements touch for re-accumulation.
+ *   Elements never uploaded contribute zero.
+ * assemble -- re-accumulates the marked stored blocks (all of them the first time) in element order with the
+ *   reference's per-entry compensation: Assembly::make_final scatter loops, solvers/assembly.cpp:657-735 (2D),
+ *   :1060-1138 (3D).  Viscous/space-time second matrices are not handled.  Afterwards the ctx holds values.       */
+int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const uint32_t * elem_ids) ;
+int amie_b200_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t count, const double * ke, const double * scales) ;
+int amie_b200_assemble(amie_b200_ctx * ctx) ;
+
+/* Assembly::setBoundaryConditions (solvers/assembly.cpp:125-330) on the resident matrix and force vector
+ * (upload_rhs first; read the result back with download_rhs or solve with the *_resident calls):
+ *   - fix_ids/fix_values: displacement-type multipliers (SET_ALONG_*, FIX_ALONG_*; everything the reference
+ *     eliminates at :170-253): column folded into the forces, row replaced by the identity row, forces[id] = value;
+ *   - force_ids/force_values: SET_FORCE_* multipliers, forces[id] += value (:262-268);
+ *   - add_to_forces (nullable, N): forces += addToExternalForces with the entries of fixed dofs taken as 0 (:177, :323);
+ *   - natural_inout (nullable, N): naturalBoundaryConditionForces, receives the same subtractions as the forces.
+ * Both id lists ascending and unique (Assembly sorts its multipliers by id, :428).  GENERAL and
+ * SET_PROPORTIONAL_DISPLACEMENT multipliers are not handled (AMIE_B200_ERR_ARG is NOT raised for them: the caller
+ * simply must not route such assemblies here).  Stored blocks touched by the elimination are marked, so the next
+ * assemble() restores them from the elements, as the reference's mask does (:539-560).                          */
+int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                                      uint64_t nforce, const uint32_t * force_ids, const double * force_values,
+                                      const double * add_to_forces, double * natural_inout) ;
+
 /* ------------------------------------------------------------------ statistics */
 typedef struct amie_b200_stats
 {
@@ -134,6 +170,10 @@ typedef struct amie_b200_stats
     double   structure_ms, values_ms ; /* last set_structure / set_values (wall)                              */
     uint64_t spmv_algorithmic_bytes ;  /* nnzb*(8 s^2 + 4) + 4 (nb+1) + 16 N                 */
     uint64_t device_bytes ;          /* HBM held by the context                                               */
+    double   elements_ms ;           /* last set_elements (wall: gather-list build)                           */
+    double   assemble_ms ;           /* last assemble (device time, CUDA events)                              */
+    double   bc_ms ;                 /* last set_boundary_conditions kernel (device time)                     */
+    uint64_t element_blocks ;        /* n_elem * npe^2 elementary blocks held on the device                   */
 } amie_b200_stats ;
 int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 

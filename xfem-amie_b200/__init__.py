@@ -43,7 +43,8 @@ class Stats(ctypes.Structure):
                 ("spmv_ms_total", f64), ("spmv_timed", u64), ("solve_ms", f64),
                 ("h2d_ms", f64), ("d2h_ms", f64), ("h2d_bytes", u64), ("d2h_bytes", u64),
                 ("structure_ms", f64), ("values_ms", f64),
-                ("spmv_algorithmic_bytes", u64), ("device_bytes", u64)]
+                ("spmv_algorithmic_bytes", u64), ("device_bytes", u64),
+                ("elements_ms", f64), ("assemble_ms", f64), ("bc_ms", f64), ("element_blocks", u64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -84,6 +85,10 @@ def lib():
         L.amie_b200_bicgstab_resident.argtypes = [vp, ci, f64, ci, vp, vp]
         L.amie_b200_spmv_resident.argtypes = [vp, ci, ci, vp]
         L.amie_b200_get_stats.argtypes = [vp, vp]
+        L.amie_b200_set_elements.argtypes = [vp, u64, ci, vp]
+        L.amie_b200_update_elements.argtypes = [vp, u64, u64, vp, vp]
+        L.amie_b200_assemble.argtypes = [vp]
+        L.amie_b200_set_boundary_conditions.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
         L.amie_b200_set_option.argtypes = [vp, cp, ctypes.c_int64]
         L.amie_b200_synth_create.restype = vp
         L.amie_b200_synth_create.argtypes = [cp, ci, u64]
@@ -208,6 +213,53 @@ class Assembly:
         if self._values_dirty:
             self.check(L.amie_b200_set_values(self.ctx, _ptr(A.array)))
             self._values_dirty = False
+
+    # ---- device-side value assembly + Dirichlet elimination
+    def set_structure_only(self, stride, row_size, column_index):
+        """Topology without host values: the values will be assembled on the device from the elements."""
+        rs = np.ascontiguousarray(row_size, np.uint32)
+        ci = np.ascontiguousarray(column_index, np.uint32)
+        self.coordinateIndexedMatrix = None
+        self.check(lib().amie_b200_set_structure(self.ctx, int(stride), rs.size, _ptr(rs), _ptr(ci), ci.size))
+
+    def set_elements(self, elem_ids):
+        """elem_ids[n_elem, npe] node (block-row) ids in Assembly::element2d/element3d order; 0xFFFFFFFF = unused slot."""
+        ids = np.ascontiguousarray(elem_ids, np.uint32)
+        if ids.ndim != 2:
+            raise ValueError("elem_ids must be [n_elem, npe]")
+        self._npe = ids.shape[1]
+        self.check(lib().amie_b200_set_elements(self.ctx, ids.shape[0], ids.shape[1], _ptr(ids)))
+
+    def update_elements(self, first, ke, scales=None):
+        """Elementary matrices of elements [first, first+len(ke)): ke[e, j, k, m*s+n] = Ke_e[j][k][n][m]."""
+        ke = np.ascontiguousarray(ke, np.float64)
+        count = ke.shape[0]
+        scales = None if scales is None else np.ascontiguousarray(scales, np.float64)
+        if scales is not None and scales.size != count:
+            raise ValueError("one scale per element")
+        self.check(lib().amie_b200_update_elements(self.ctx, int(first), int(count), _ptr(ke) if count else None, _ptr(scales)))
+
+    def assemble(self):
+        """Assembly::make_final's scatter loops on the device (solvers/assembly.cpp:657-735, :1060-1138)."""
+        self.check(lib().amie_b200_assemble(self.ctx))
+
+    def set_boundary_conditions(self, fix_ids, fix_values, force_ids=None, force_values=None, add_to_forces=None,
+                                natural=None):
+        """Assembly::setBoundaryConditions on the resident matrix and forces (solvers/assembly.cpp:125-330).
+        `natural` (naturalBoundaryConditionForces) is updated in place when given."""
+        fi = np.ascontiguousarray(fix_ids, np.uint32)
+        fv = np.ascontiguousarray(fix_values, np.float64)
+        gi = np.ascontiguousarray([] if force_ids is None else force_ids, np.uint32)
+        gv = np.ascontiguousarray([] if force_values is None else force_values, np.float64)
+        if fi.size != fv.size or gi.size != gv.size:
+            raise ValueError("one value per dof id")
+        add = None if add_to_forces is None else np.ascontiguousarray(add_to_forces, np.float64)
+        if natural is not None and (natural.dtype != np.float64 or not natural.flags.c_contiguous):
+            raise ValueError("natural must be a contiguous float64 array (updated in place)")
+        self.check(lib().amie_b200_set_boundary_conditions(self.ctx, fi.size, _ptr(fi) if fi.size else None,
+                                                           _ptr(fv) if fv.size else None, gi.size,
+                                                           _ptr(gi) if gi.size else None, _ptr(gv) if gv.size else None,
+                                                           _ptr(add), _ptr(natural)))
 
     def stats(self):
         s = Stats()

@@ -18,6 +18,7 @@ template<typename T> static void dfree(T *& p) { if(p) cudaFree(p) ; p = nullptr
 static void free_matrix(amie_b200_ctx * ctx)
 {
     ctx->alloc_gen++ ;
+    assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
     dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }

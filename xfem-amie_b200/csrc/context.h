@@ -7,6 +7,7 @@
 #include <chrono>
 
 struct DistState ;   // dist.cu
+struct AssemblyMap ; // assemble.cu
 
 struct amie_b200_ctx
 {
@@ -56,6 +57,7 @@ struct amie_b200_ctx
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll[2] = {nullptr, nullptr} ;
 
     DistState * dist = nullptr ;
+    AssemblyMap * amap = nullptr ;     // element -> stored-block gather lists (device-side value assembly)
 
     // ---- CUDA graphs of iteration batches (small systems: launch-bound inner loops)
     struct GraphSlot
@@ -76,6 +78,7 @@ inline double wall_now()
 }
 
 // internal entry points shared between translation units
+void assembly_map_destroy(amie_b200_ctx * ctx) ;          // assemble.cu
 int ctx_alloc_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_dinv(amie_b200_ctx * ctx) ;
