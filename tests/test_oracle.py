@@ -10,7 +10,9 @@ import os
 import numpy as np
 import pytest
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# solver fixtures only: *-assembly.npz and bc-rand-*.npz belong to the assembly tests
+GOLDEN = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+          if not (p.endswith("-assembly.npz") or os.path.basename(p).startswith("bc-rand-"))]
 
 
 def _sys(ol, g):
