@@ -153,6 +153,33 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
                                       uint64_t nforce, const uint32_t * force_ids, const double * force_values,
                                       const double * add_to_forces, double * natural_inout) ;
 
+/* ------------------------------------------------------------------ field recovery after the solve
+ * What FeatureTree::stepElements / ElementState::getField do with the solution, one element and one virtual call at a
+ * time (elements/integrable_entity.cpp:3607-3667, :964-1104, :1379-1392): gather the element's dofs, total strain from
+ * the shape-function derivatives and the element's cached inverse Jacobian, mechanical strain = total - imposed
+ * strain, real stress = tensor * mechanical strain - imposed stress.  Here: one pass on the device, reading the
+ * RESIDENT solution of the last solve (no download of u).  Results equal ElementState::getField's bit for bit.
+ *
+ * set_element_kinematics -- once per topology, after set_structure.  dim = 2|3 and must equal the stride.
+ *   elem_ids[e*npe + j]: node (block-row) id of slot j, shape functions first, then enrichment functions
+ *   (IntegrableEntity::getDofIds order); 0xFFFFFFFF = unused slot.  A dof beyond the solution vector reads as 0 (:3641-3648).
+ *   dshape[(e*npe + j)*dim + d] = vm.deval(function j, XI|ETA|ZETA, p) at the evaluation point p of the element;
+ *   jinv[(e*dim + a)*dim + b]   = (*ElementState::JinvCache)[a][b].
+ * set_element_behaviour -- whenever behaviours change (damage): a table of n_tensors entries,
+ *   tensors[(t*nc + i)*nc + k] = getBehaviour()->getTensor(p)[i][k], nc = 3 (2D) | 6 (3D);
+ *   imposed_strain / imposed_stress [t*nc + i] (NULL = none: getImposedStrain / getImposedStress);
+ *   tensor_of_elem[e] = table entry of element e (NULL: n_tensors == n_elem, entry e).
+ * element_fields -- u == NULL: use the resident x (the solution of the last *_resident / host-buffer solve);
+ *   otherwise u[n_u] is uploaded first.  Outputs [e*nc + i], any of them may be NULL:
+ *   TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD, REAL_STRESS_FIELD.                                                  */
+int amie_b200_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int npe, int dim, const uint32_t * elem_ids,
+                                     const double * dshape, const double * jinv) ;
+int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, const double * tensors,
+                                    const double * imposed_strain, const double * imposed_stress,
+                                    const uint32_t * tensor_of_elem) ;
+int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u,
+                             double * total_strain_out, double * mechanical_strain_out, double * real_stress_out) ;
+
 /* ------------------------------------------------------------------ statistics */
 typedef struct amie_b200_stats
 {
@@ -174,6 +201,8 @@ typedef struct amie_b200_stats
     double   assemble_ms ;           /* last assemble (device time, CUDA events)                              */
     double   bc_ms ;                 /* last set_boundary_conditions kernel (device time)                     */
     uint64_t element_blocks ;        /* n_elem * npe^2 elementary blocks held on the device                   */
+    double   fields_ms ;             /* last element_fields kernel (device time)                              */
+    uint64_t field_elements ;        /* elements held for field recovery                                      */
 } amie_b200_stats ;
 int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 

@@ -91,7 +91,8 @@ def main():
         e2e_b200 = os.path.join(OUT, "amie_e2e_b200")
         # the shim objects come first: the archive's conjugategradient.o / biconjugategradientstabilized.o are then
         # never pulled in (every symbol they define is already defined)
-        subprocess.check_call([CXX, *FLAGS, "-I" + REF, harness, *shim_objs, lib, "-L" + pkg, "-lamie_b200",
+        subprocess.check_call([CXX, *FLAGS, "-DAMIE_B200_E2E", "-I" + REF, "-I" + os.path.join(pkg, "host", "shim"), harness,
+                               *shim_objs, lib, "-L" + pkg, "-lamie_b200",
                                "-Wl,-rpath,$ORIGIN/../../xfem-amie_b200", "-lm", "-o", e2e_b200])
         print("[build_ref] built", e2e_b200)
     return 0

@@ -7,7 +7,7 @@
 // and both are run on the same problem; the displacement fields they write are compared.
 //
 //   amie_e2e_* 2d <sampling> <out.bin> [dump.bin]   plain-elastic twin of examples/main_tension_benchmark.cpp:119-134
-//   amie_e2e_* 3d <sampling> <out.bin> [dump.bin]   S1 sphere-in-cube of examples/main_3d_benchmark.cpp:184-257 (gridsize 20)
+//   amie_e2e_* 3d|3di <sampling> <out.bin> [dump.bin]   S1 sphere-in-cube of examples/main_3d_benchmark.cpp:184-257 (gridsize 20)
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -15,6 +15,15 @@
 //            (features/features.cpp:3360-3403): uint64 n_elem, npe, stride; ids u32[n_elem*npe];
 //            Ke f64[n_elem*npe*npe*s*s] (block (j,k) column-major: [m*s+n] = getCachedElementaryMatrix()[j][k][n][m]);
 //            scales f64[n_elem] (all 1: single layer)
+// fields.bin (optional 7th argument): what ElementState::getField computes from the
+//            displacement field at each element's centre (local coordinates), together with the operands it used:
+//            uint64 n_elem, npe, dim, nc(=3|6); ids u32[n_elem*npe];
+//            dshape f64[n_elem*npe*dim] (vm.deval(shape function j, XI|ETA|ZETA, p));
+//            jinv f64[n_elem*dim*dim] (row-major, the element's ElementState::JinvCache);
+//            tensor f64[n_elem*nc*nc] (row-major, getBehaviour()->getTensor(p)); imposed strain / stress f64[n_elem*nc] each;
+//            then the reference's own answers: TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD, REAL_STRESS_FIELD f64[n_elem*nc] each,
+//            and ElementState::getDisplacements() f64[n_elem*npe*dim] (what ElementState::step gathered from the solution)
+// mode 3di = 3d with a non-zero imposed strain in the inclusion (exercises the imposed-strain/-stress terms)
 #include "features/features.h"
 #include "features/sample.h"
 #include "features/sample3d.h"
@@ -82,6 +91,102 @@ static void dump_elements(const char * path, MESH * mesh, size_t s)
     fclose(f) ;
 }
 
+struct FieldDump
+{
+    uint64_t n_elem = 0, npe = 0, dim = 0, nc = 0 ;
+    std::vector<uint32_t> ids ;
+    std::vector<double> dshape, jinv, tensor, istrain, istress, total, mech, stress, disp ;
+} ;
+
+// every element's operands and the reference's own answers at the element centre (local coordinates)
+template<class MESH>
+static FieldDump collect_fields(MESH * mesh, size_t dim)
+{
+    FieldDump D ;
+    D.dim = dim ;
+    const size_t nc = D.nc = dim == 2 ? 3 : 6 ;
+    const Point centre = dim == 2 ? Point(1./3., 1./3.) : Point(.25, .25, .25) ;
+    const Variable var[3] = { XI, ETA, ZETA } ;
+    VirtualMachine vm ;
+    for(auto j = mesh->begin() ; j != mesh->end() ; j++)
+    {
+        if(!(j->getBehaviour() && j->getBehaviour()->type != VOID_BEHAVIOUR)) continue ;
+        std::vector<size_t> id = j->getDofIds() ;
+        if(!D.npe) D.npe = id.size() ;
+        const size_t npe = D.npe ;
+        if(id.size() != npe || j->getShapeFunctions().size() != npe || j->getEnrichmentFunctions().size())
+        { fprintf(stderr, "collect_fields: ragged or enriched element\n") ; exit(3) ; }
+        for(size_t a = 0 ; a < npe ; a++) D.ids.push_back((uint32_t)id[a]) ;
+        for(size_t a = 0 ; a < npe ; a++)
+            for(size_t d = 0 ; d < dim ; d++)
+                D.dshape.push_back(vm.deval(j->getShapeFunction(a), var[d], centre)) ;
+        Matrix C = j->getBehaviour()->getTensor(centre, &(*j)) ;
+        if(C.numRows() != nc || C.numCols() != nc) { fprintf(stderr, "collect_fields: tensor is not %zux%zu\n", nc, nc) ; exit(3) ; }
+        for(size_t a = 0 ; a < nc ; a++)
+            for(size_t b = 0 ; b < nc ; b++)
+                D.tensor.push_back(C[a][b]) ;
+        Vector is(0., nc), it(0., nc) ;
+        if(j->getBehaviour()->hasInducedForces())
+        {
+            is = j->getBehaviour()->getImposedStrain(centre, &(*j)) ;
+            it = j->getBehaviour()->getImposedStress(centre, &(*j)) ;
+        }
+        const Vector & ud = j->getState().getDisplacements() ;
+        for(size_t a = 0 ; a < npe*dim ; a++) D.disp.push_back(a < ud.size() ? ud[a] : 0.) ;
+        Vector e(0., nc), em(0., nc), sg(0., nc) ;
+        j->getState().getField(TOTAL_STRAIN_FIELD, centre, e, true, &vm) ;
+        j->getState().getField(MECHANICAL_STRAIN_FIELD, centre, em, true, &vm) ;
+        j->getState().getField(REAL_STRESS_FIELD, centre, sg, true, &vm) ;
+        // the inverse Jacobian getField used: the element's cache (ElementState::JinvCache, filled at the latest by the
+        // calls above; it is NOT recomputed per call -- getInverseJacobianMatrix adds the current displacements to the
+        // node coordinates, elements/integrable_entity.cpp:657-667, so a fresh evaluation would differ)
+        const Matrix & J = *j->getState().JinvCache ;
+        for(size_t a = 0 ; a < dim ; a++)
+            for(size_t b = 0 ; b < dim ; b++)
+                D.jinv.push_back(J[a][b]) ;
+        for(size_t a = 0 ; a < nc ; a++)
+        {
+            D.istrain.push_back(is[a]) ; D.istress.push_back(it[a]) ;
+            D.total.push_back(e[a]) ; D.mech.push_back(em[a]) ; D.stress.push_back(sg[a]) ;
+        }
+        D.n_elem++ ;
+    }
+    return D ;
+}
+
+static void write_fields(const char * path, const FieldDump & D)
+{
+    FILE * f = fopen(path, "wb") ;
+    uint64_t h[4] = { D.n_elem, D.npe, D.dim, D.nc } ;
+    fwrite(h, 8, 4, f) ;
+    fwrite(D.ids.data(), 4, D.ids.size(), f) ;
+    for(const std::vector<double> * v : { &D.dshape, &D.jinv, &D.tensor, &D.istrain, &D.istress, &D.total, &D.mech, &D.stress, &D.disp })
+        fwrite(v->data(), 8, v->size(), f) ;
+    fclose(f) ;
+}
+
+#ifdef AMIE_B200_E2E
+// The drop-in build only: the same fields from the device (amie_b200_element_fields on the context the shim keeps
+// for this Assembly), compared bit for bit with what ElementState::getField just answered in this very process.
+#include "amie_b200_shim.h"
+#include <cstring>
+static void check_fields_on_device(const FieldDump & D, Assembly * K, const Vector & u)
+{
+    amie_b200_ctx * ctx = AmieB200Shim::context_for(K) ;
+    if(!ctx) { fprintf(stderr, "fields-on-device: no context\n") ; exit(4) ; }
+    int rc = amie_b200_set_element_kinematics(ctx, D.n_elem, (int)D.npe, (int)D.dim, D.ids.data(), D.dshape.data(), D.jinv.data()) ;
+    if(!rc) rc = amie_b200_set_element_behaviour(ctx, D.n_elem, D.tensor.data(), D.istrain.data(), D.istress.data(), nullptr) ;
+    std::vector<double> e(D.total.size()), em(D.mech.size()), sg(D.stress.size()) ;
+    if(!rc) rc = amie_b200_element_fields(ctx, &u[0], u.size(), e.data(), em.data(), sg.data()) ;
+    if(rc) { fprintf(stderr, "fields-on-device: %s\n", amie_b200_last_error(ctx)) ; exit(4) ; }
+    size_t bad = 0 ;
+    for(size_t i = 0 ; i < e.size() ; i++)
+        bad += (memcmp(&e[i], &D.total[i], 8) != 0)+(memcmp(&em[i], &D.mech[i], 8) != 0)+(memcmp(&sg[i], &D.stress[i], 8) != 0) ;
+    fprintf(stderr, "fields-on-device: %zu elements, %zu values compared with ElementState::getField, %zu differ\n",
+            (size_t)D.n_elem, 3*e.size(), bad) ;
+}
+#endif
+
 int main(int argc, char ** argv)
 {
     if(argc < 4) { fprintf(stderr, "usage: %s 2d|3d <sampling> <out.bin> [dump.bin]\n", argv[0]) ; return 2 ; }
@@ -100,6 +205,14 @@ int main(int argc, char ** argv)
         write_vec(argv[3], F.getDisplacements()) ;
         if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
         if(argc > 5) dump_elements(argv[5], F.get2DMesh(), 2) ;
+        if(argc > 6)
+        {
+            FieldDump D = collect_fields(F.get2DMesh(), 2) ;
+            write_fields(argv[6], D) ;
+#ifdef AMIE_B200_E2E
+            check_fields_on_device(D, F.getAssembly(false), F.getDisplacements()) ;
+#endif
+        }
     }
     else
     {
@@ -110,6 +223,7 @@ int main(int argc, char ** argv)
         F.setProjectionOnBoundaries(false) ;
         sample.setBehaviour(new Stiffness(Tensor::cauchyGreen(1., 0.2, SPACE_THREE_DIMENSIONAL, PLANE_STRESS, YOUNG_POISSON))) ;
         Vector alpha(0., 6) ;
+        if(mode == "3di") { alpha[0] = 1e-3 ; alpha[1] = 2e-3 ; alpha[2] = -5e-4 ; }
         Inclusion3D * inc = new Inclusion3D(0.0623*scale, sample.getCenter().getX(), sample.getCenter().getY(), sample.getCenter().getZ()) ;
         inc->setBehaviour(new StiffnessWithImposedStrain(Tensor::cauchyGreen(10., .2, SPACE_THREE_DIMENSIONAL, PLANE_STRESS, YOUNG_POISSON), alpha)) ;
         F.addFeature(&sample, inc) ;
@@ -126,6 +240,14 @@ int main(int argc, char ** argv)
         write_vec(argv[3], F.getDisplacements()) ;
         if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
         if(argc > 5) dump_elements(argv[5], F.get3DMesh(), 3) ;
+        if(argc > 6)
+        {
+            FieldDump D = collect_fields(F.get3DMesh(), 3) ;
+            write_fields(argv[6], D) ;
+#ifdef AMIE_B200_E2E
+            check_fields_on_device(D, F.getAssembly(false), F.getDisplacements()) ;
+#endif
+        }
     }
     return 0 ;
 }

@@ -40,8 +40,8 @@ def oracle():
     global _oracle
     if _oracle is None:
         so = os.path.join(ORACLE_DIR, "libamie_oracle.so")
-        src = os.path.join(ORACLE_DIR, "amie_oracle.c")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".c")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "libamie_oracle.so"], stdout=subprocess.DEVNULL)
         _oracle = ctypes.CDLL(so)
         _oracle.amie_oracle_dot.restype = f64
@@ -257,3 +257,23 @@ def ref_set_bcs(stride, nb, row_size, column_index, array, forces, fix_ids, fix_
     rc = ref().amie_ref_set_boundary_conditions(*args)
     assert rc == 0
     return array, forces, natural, add
+
+
+# ------------------------------------------------------------------ field recovery after the solve
+
+def oracle_element_fields(dim, ids, dshape, jinv, u, tensors=None, imposed_strain=None, imposed_stress=None,
+                          tensor_of_elem=None):
+    """(total strain, mechanical strain, real stress), each [n_elem, nc]: ElementState::getField restated
+    (oracle/amie_oracle_fields.c)."""
+    ids = np.ascontiguousarray(ids, np.uint32)
+    ne, npe = ids.shape
+    nc = 3 if dim == 2 else 6
+    c = lambda a, t=np.float64: None if a is None else np.ascontiguousarray(a, t)
+    dshape, jinv, u, tensors = c(dshape), c(jinv), c(u), c(tensors)
+    imposed_strain, imposed_stress, tensor_of_elem = c(imposed_strain), c(imposed_stress), c(tensor_of_elem, np.uint32)
+    tot, mech, sig = np.zeros((ne, nc)), np.zeros((ne, nc)), np.zeros((ne, nc))
+    rc = oracle().amie_oracle_element_fields(int(dim), u64(ne), int(npe), _vp(ids), _vp(dshape), _vp(jinv), _vp(tensors),
+                                             _vp(imposed_strain), _vp(imposed_stress), _vp(tensor_of_elem), _vp(u),
+                                             u64(u.size), _vp(tot), _vp(mech), _vp(sig))
+    assert rc == 0
+    return tot, mech, sig

@@ -44,7 +44,8 @@ class Stats(ctypes.Structure):
                 ("h2d_ms", f64), ("d2h_ms", f64), ("h2d_bytes", u64), ("d2h_bytes", u64),
                 ("structure_ms", f64), ("values_ms", f64),
                 ("spmv_algorithmic_bytes", u64), ("device_bytes", u64),
-                ("elements_ms", f64), ("assemble_ms", f64), ("bc_ms", f64), ("element_blocks", u64)]
+                ("elements_ms", f64), ("assemble_ms", f64), ("bc_ms", f64), ("element_blocks", u64),
+                ("fields_ms", f64), ("field_elements", u64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -89,6 +90,9 @@ def lib():
         L.amie_b200_update_elements.argtypes = [vp, u64, u64, vp, vp]
         L.amie_b200_assemble.argtypes = [vp]
         L.amie_b200_set_boundary_conditions.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
+        L.amie_b200_set_element_kinematics.argtypes = [vp, u64, ci, ci, vp, vp, vp]
+        L.amie_b200_set_element_behaviour.argtypes = [vp, u64, vp, vp, vp, vp]
+        L.amie_b200_element_fields.argtypes = [vp, vp, u64, vp, vp, vp]
         L.amie_b200_set_option.argtypes = [vp, cp, ctypes.c_int64]
         L.amie_b200_synth_create.restype = vp
         L.amie_b200_synth_create.argtypes = [cp, ci, u64]
@@ -260,6 +264,43 @@ class Assembly:
                                                            _ptr(fv) if fv.size else None, gi.size,
                                                            _ptr(gi) if gi.size else None, _ptr(gv) if gv.size else None,
                                                            _ptr(add), _ptr(natural)))
+
+    # ---- field recovery after the solve
+    def set_element_kinematics(self, dim, elem_ids, dshape, jinv):
+        """Once per topology: elem_ids[n_elem, npe] (IntegrableEntity::getDofIds order, 0xFFFFFFFF = unused slot),
+        dshape[n_elem, npe, dim] = vm.deval(function j, XI|ETA|ZETA, p), jinv[n_elem, dim, dim] = ElementState::JinvCache."""
+        ids = np.ascontiguousarray(elem_ids, np.uint32)
+        ds = np.ascontiguousarray(dshape, np.float64)
+        ji = np.ascontiguousarray(jinv, np.float64)
+        if ids.ndim != 2 or ds.shape != ids.shape + (dim,) or ji.shape != (ids.shape[0], dim, dim):
+            raise ValueError("elem_ids [n_elem, npe], dshape [n_elem, npe, dim], jinv [n_elem, dim, dim]")
+        self._field_shape = (ids.shape[0], 3 if dim == 2 else 6)
+        self.check(lib().amie_b200_set_element_kinematics(self.ctx, ids.shape[0], ids.shape[1], int(dim), _ptr(ids), _ptr(ds), _ptr(ji)))
+
+    def set_element_behaviour(self, tensors, imposed_strain=None, imposed_stress=None, tensor_of_elem=None):
+        """A table of behaviours (getTensor / getImposedStrain / getImposedStress at the evaluation point) and the
+        table entry of every element (None: one entry per element, in element order)."""
+        C = np.ascontiguousarray(tensors, np.float64)
+        nc = self._field_shape[1]
+        if C.ndim != 3 or C.shape[1:] != (nc, nc):
+            raise ValueError(f"tensors must be [n_tensors, {nc}, {nc}]")
+        opt = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        es, ss, toe = opt(imposed_strain, np.float64), opt(imposed_stress, np.float64), opt(tensor_of_elem, np.uint32)
+        for a in (es, ss):
+            if a is not None and a.shape != (C.shape[0], nc):
+                raise ValueError(f"imposed strain / stress must be [n_tensors, {nc}]")
+        if toe is not None and toe.shape != (self._field_shape[0],):
+            raise ValueError("tensor_of_elem must be [n_elem]")
+        self.check(lib().amie_b200_set_element_behaviour(self.ctx, C.shape[0], _ptr(C), _ptr(es), _ptr(ss), _ptr(toe)))
+
+    def element_fields(self, u=None):
+        """(TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD, REAL_STRESS_FIELD) per element, from the resident solution
+        of the last solve (u=None) or from a host vector: ElementState::step + getField
+        (elements/integrable_entity.cpp:3607-3667, :964-1104, :1379-1392)."""
+        u = None if u is None else np.ascontiguousarray(u, np.float64)
+        out = [np.zeros(self._field_shape) for _ in range(3)]
+        self.check(lib().amie_b200_element_fields(self.ctx, _ptr(u), 0 if u is None else u.size, *[_ptr(o) for o in out]))
+        return tuple(out)
 
     def stats(self):
         s = Stats()

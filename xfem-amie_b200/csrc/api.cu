@@ -19,6 +19,7 @@ static void free_matrix(amie_b200_ctx * ctx)
 {
     ctx->alloc_gen++ ;
     assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
+    field_map_destroy(ctx) ;             // element data belongs to the topology too
     dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }

@@ -8,6 +8,7 @@
 
 struct DistState ;   // dist.cu
 struct AssemblyMap ; // assemble.cu
+struct FieldMap ;    // fields.cu
 
 struct amie_b200_ctx
 {
@@ -58,6 +59,7 @@ struct amie_b200_ctx
 
     DistState * dist = nullptr ;
     AssemblyMap * amap = nullptr ;     // element -> stored-block gather lists (device-side value assembly)
+    FieldMap * fmap = nullptr ;        // element kinematics + behaviours (field recovery after the solve)
 
     // ---- CUDA graphs of iteration batches (small systems: launch-bound inner loops)
     struct GraphSlot
@@ -79,6 +81,7 @@ inline double wall_now()
 
 // internal entry points shared between translation units
 void assembly_map_destroy(amie_b200_ctx * ctx) ;          // assemble.cu
+void field_map_destroy(amie_b200_ctx * ctx) ;             // fields.cu
 int ctx_alloc_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_dinv(amie_b200_ctx * ctx) ;

@@ -1,0 +1,336 @@
+// fields.cu -- per-element field recovery from the displacement field.
+//
+// What it replaces: the step right after the Krylov solve.  FeatureTree::stepElements hands the solution to every
+// element (ElementState::step, elements/integrable_entity.cpp:3607-3667: a gather of the element's dofs) and the
+// behaviours / post-processors then ask ElementState::getField for
+//   TOTAL_STRAIN_FIELD       :977-1104   (2D :979-1017, 3D :1019-1095)
+//   MECHANICAL_STRAIN_FIELD  :964-975    (total strain - imposed strain)
+//   REAL_STRESS_FIELD        :1379-1392  (tensor * mechanical strain - imposed stress; utilities/matrixops.h:545-558)
+// one element and one virtual call at a time.  Here: one thread per element, the solution read straight from the
+// resident x of the solve (no download of u), all three fields in one pass.
+//
+// Inputs that stay upstream (the reference's polynomial VM and geometry produce them once per topology): the
+// shape-function derivatives at the evaluation point and the element's cached inverse Jacobian
+// (ElementState::JinvCache).  Enrichment functions are just further slots of an element (:1002-1011, :1049-1068).
+//
+// Bit-exactness: every product and sum is an explicit _rn intrinsic in the reference's order (the reference is
+// built without FMA contraction), so the results equal ElementState::getField's bit for bit
+// (tests/test_gpu_recovery.py against tests/golden/AMIE-*-fields.npz, which the unmodified reference produced).
+//
+// Layout in HBM: per-element operands are stored component-major ([component][element]) so that consecutive
+// threads read consecutive addresses; behaviours (tensor + imposed strain/stress) are a table indexed per element
+// -- a handful of entries for an undamaged composite (L1/L2 resident), one per element under damage.  Results are
+// staged through shared memory and written element-major (the layout the caller wants) with coalesced stores.
+// Bound: HBM.  Algorithmic bytes per element (dim d, npe slots, nc = 3|6 components):
+//   4 npe (ids) + 8 npe d (derivatives) + 8 d^2 (Jinv) + 8 npe d (gathered u) + 4 (behaviour index) + 3*8 nc (results)
+//   = 352 B for a linear tetrahedron, 172 B for a linear triangle (+ 8 nc (nc+2) per element with per-element tensors).
+#include "context.h"
+#include "launch.cuh"
+#include <algorithm>
+#include <vector>
+
+#define NO_NODE 0xFFFFFFFFu
+#define FIELD_THREADS 128
+
+struct FieldMap
+{
+    uint64_t n_elem = 0 ;
+    int npe = 0, dim = 0, nc = 0 ;
+    uint32_t * ids = nullptr ;        // [npe][n_elem]
+    double * dshape = nullptr ;       // [npe*dim][n_elem]
+    double * jinv = nullptr ;         // [dim*dim][n_elem]
+    uint64_t n_tensors = 0 ;
+    double * tensors = nullptr ;      // [n_tensors][nc*nc] row-major
+    double * istrain = nullptr ;      // [n_tensors][nc] (zeros when the caller passed NULL)
+    double * istress = nullptr ;
+    uint32_t * tensor_of_elem = nullptr ; // [n_elem] or nullptr (identity)
+    double * out[3] = {nullptr, nullptr, nullptr} ;   // total strain, mechanical strain, real stress: [n_elem][nc]
+    double * u_tmp = nullptr ;        // staging for a host-supplied displacement field
+    uint64_t u_tmp_len = 0 ;
+    bool have_behaviour = false ;
+} ;
+
+template<typename T> static void ffree(T *& p) { if(p) cudaFree(p) ; p = nullptr ; }
+
+void field_map_destroy(amie_b200_ctx * ctx)
+{
+    FieldMap * m = ctx->fmap ;
+    if(!m) return ;
+    ffree(m->ids) ; ffree(m->dshape) ; ffree(m->jinv) ; ffree(m->tensors) ; ffree(m->istrain) ; ffree(m->istress) ;
+    ffree(m->tensor_of_elem) ; ffree(m->u_tmp) ;
+    for(int i = 0 ; i < 3 ; i++) ffree(m->out[i]) ;
+    delete m ;
+    ctx->fmap = nullptr ;
+}
+
+// in[e*K + k] -> out[k*n + e]  (once per topology)
+template<typename T>
+static __global__ void k_to_component_major(const T * __restrict__ in, T * __restrict__ out, uint64_t n, int K)
+{
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    const uint64_t total = n*(uint64_t)K ;
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < total ; i += stride)
+    {
+        const uint64_t e = i/K ;
+        const int k = (int)(i-e*K) ;
+        out[(uint64_t)k*n+e] = in[i] ;
+    }
+}
+
+// One thread per element.  g[c][l] accumulates d(shape_j)/d(local_l) * u_j[c] over the element's slots in slot
+// order, exactly as the reference's x_xi ... z_zeta accumulators do.
+template<int DIM>
+static __global__ void __launch_bounds__(FIELD_THREADS)
+k_element_fields(const uint32_t * __restrict__ ids, const double * __restrict__ dshape, const double * __restrict__ jinv,
+                 const double * __restrict__ tensors, const double * __restrict__ istrain, const double * __restrict__ istress,
+                 const uint32_t * __restrict__ tensor_of_elem, const double * __restrict__ u, uint64_t n_u,
+                 uint64_t n_elem, int npe, double * __restrict__ total_out, double * __restrict__ mech_out,
+                 double * __restrict__ stress_out)
+{
+    constexpr int NC = DIM == 2 ? 3 : 6 ;
+    __shared__ double stage[FIELD_THREADS*NC] ;
+    const uint64_t ntiles = (n_elem+FIELD_THREADS-1)/FIELD_THREADS ;
+    for(uint64_t tile = blockIdx.x ; tile < ntiles ; tile += gridDim.x)
+    {
+        const uint64_t e0 = tile*FIELD_THREADS ;
+        const uint64_t e = e0+threadIdx.x ;
+        const bool live = e < n_elem ;
+        const int cnt = (int)min((uint64_t)FIELD_THREADS, n_elem-e0) ;
+        double t[NC], m[NC], s[NC] ;
+        #pragma unroll
+        for(int i = 0 ; i < NC ; i++) { t[i] = 0. ; m[i] = 0. ; s[i] = 0. ; }
+        if(live)
+        {
+            double g[DIM][DIM] ;
+            #pragma unroll
+            for(int c = 0 ; c < DIM ; c++)
+                #pragma unroll
+                for(int l = 0 ; l < DIM ; l++) g[c][l] = 0. ;
+            for(int j = 0 ; j < npe ; j++)
+            {
+                const uint32_t id = __ldg(ids+(uint64_t)j*n_elem+e) ;
+                if(id == NO_NODE) continue ;
+                double f[DIM] ;
+                #pragma unroll
+                for(int l = 0 ; l < DIM ; l++) f[l] = ld_stream(dshape+(uint64_t)(j*DIM+l)*n_elem+e) ;
+                #pragma unroll
+                for(int c = 0 ; c < DIM ; c++)
+                {
+                    const uint64_t k = (uint64_t)id*DIM+c ;
+                    const double d = k < n_u ? __ldg(u+k) : 0. ;          // ElementState::step, :3641-3648
+                    #pragma unroll
+                    for(int l = 0 ; l < DIM ; l++) g[c][l] = __dadd_rn(g[c][l], __dmul_rn(f[l], d)) ;
+                }
+            }
+            double J[DIM*DIM] ;
+            #pragma unroll
+            for(int k = 0 ; k < DIM*DIM ; k++) J[k] = ld_stream(jinv+(uint64_t)k*n_elem+e) ;
+            // a[0]*J[r][0] + a[1]*J[r][1] (+ a[2]*J[r][2]), left to right
+            auto row = [&](const double * a, int r)
+            {
+                double v = __dadd_rn(__dmul_rn(a[0], J[r*DIM]), __dmul_rn(a[1], J[r*DIM+1])) ;
+                if constexpr(DIM == 3) v = __dadd_rn(v, __dmul_rn(a[2], J[r*DIM+2])) ;
+                return v ;
+            } ;
+            // ... continued with b[0]*J[q][0] + b[1]*J[q][1] (+ b[2]*J[q][2])
+            auto row2 = [&](const double * a, int r, const double * b, int q)
+            {
+                double v = row(a, r) ;
+                v = __dadd_rn(v, __dmul_rn(b[0], J[q*DIM])) ;
+                v = __dadd_rn(v, __dmul_rn(b[1], J[q*DIM+1])) ;
+                if constexpr(DIM == 3) v = __dadd_rn(v, __dmul_rn(b[2], J[q*DIM+2])) ;
+                return v ;
+            } ;
+            if constexpr(DIM == 2)
+            {
+                t[0] = row(g[0], 0) ;                         // :1015
+                t[1] = row(g[1], 1) ;                         // :1016
+                t[2] = row2(g[0], 1, g[1], 0) ;               // :1017
+            }
+            else
+            {
+                t[0] = row(g[0], 0) ;                         // :1072-1074
+                t[1] = row(g[1], 1) ;
+                t[2] = row(g[2], 2) ;
+                t[3] = row2(g[1], 2, g[2], 1) ;               // :1076-1081
+                t[4] = row2(g[0], 2, g[2], 0) ;               // :1083-1088
+                t[5] = row2(g[1], 0, g[0], 1) ;               // :1090-1095
+            }
+            const uint64_t ti = tensor_of_elem ? __ldg(tensor_of_elem+e) : e ;
+            #pragma unroll
+            for(int i = 0 ; i < NC ; i++) m[i] = __dsub_rn(t[i], __ldg(istrain+ti*NC+i)) ;      // :967-968
+            const double * C = tensors+ti*NC*NC ;
+            #pragma unroll
+            for(int i = 0 ; i < NC ; i++)
+            {
+                double acc = 0. ;
+                #pragma unroll
+                for(int k = 0 ; k < NC ; k++) acc = __dadd_rn(acc, __dmul_rn(__ldg(C+i*NC+k), m[k])) ;   // matrixops.h:555
+                s[i] = __dsub_rn(acc, __ldg(istress+ti*NC+i)) ;                              // :1392
+            }
+        }
+        // element-major results through shared memory: one contiguous, coalesced store per field and tile
+        double * outs[3] = { total_out, mech_out, stress_out } ;
+        #pragma unroll
+        for(int w = 0 ; w < 3 ; w++)
+        {
+            __syncthreads() ;
+            #pragma unroll
+            for(int i = 0 ; i < NC ; i++) stage[threadIdx.x*NC+i] = w == 0 ? t[i] : (w == 1 ? m[i] : s[i]) ;
+            __syncthreads() ;
+            double * dst = outs[w]+e0*NC ;
+            for(int i = threadIdx.x ; i < cnt*NC ; i += FIELD_THREADS) dst[i] = stage[i] ;
+        }
+    }
+}
+
+static int field_grid(const amie_b200_ctx * ctx, uint64_t n_elem)
+{
+    const uint64_t tiles = (n_elem+FIELD_THREADS-1)/FIELD_THREADS ;
+    const uint64_t cap = (uint64_t)ctx->num_sms*8 ;
+    return (int)std::max<uint64_t>(1, std::min(tiles, cap)) ;
+}
+
+extern "C" {
+
+int amie_b200_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int npe, int dim, const uint32_t * elem_ids,
+                                     const double * dshape, const double * jinv)
+{
+    if(!ctx || npe < 1 || npe > 64 || (n_elem && (!elem_ids || !dshape || !jinv))) return AMIE_B200_ERR_ARG ;
+    if(ctx->dist) { ctx->set_error("set_element_kinematics: not available on a row-partitioned context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    if(!ctx->have_structure) { ctx->set_error("set_element_kinematics before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    if((dim != 2 && dim != 3) || dim != ctx->S)
+    {
+        // the reference's strain code exists for 2 dofs per node in 2D and 3 in 3D only (elements/integrable_entity.cpp:979, :1019)
+        ctx->set_error("set_element_kinematics: dim must be 2 or 3 and equal the stride of the system") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    field_map_destroy(ctx) ;
+    FieldMap * m = new FieldMap ;
+    ctx->fmap = m ;
+    m->n_elem = n_elem ; m->npe = npe ; m->dim = dim ; m->nc = dim == 2 ? 3 : 6 ;
+    void * tmp = nullptr ;
+    const uint64_t one = 1 ;
+    const uint64_t tmp_bytes = std::max(one, n_elem*(uint64_t)std::max(npe*dim, dim*dim)*sizeof(double)) ;
+#define F_TRY(expr) do { cudaError_t _e = (expr) ; if(_e != cudaSuccess) { if(tmp) cudaFree(tmp) ; field_map_destroy(ctx) ; \
+        ctx->set_error(std::string(#expr)+": "+cudaGetErrorString(_e)) ; return AMIE_B200_ERR_CUDA ; } } while(0)
+    F_TRY(cudaMalloc(&tmp, tmp_bytes)) ;
+    F_TRY(cudaMalloc(&m->ids, std::max(one, n_elem*npe)*sizeof(uint32_t))) ;
+    F_TRY(cudaMalloc(&m->dshape, std::max(one, n_elem*npe*dim)*sizeof(double))) ;
+    F_TRY(cudaMalloc(&m->jinv, std::max(one, n_elem*dim*dim)*sizeof(double))) ;
+    for(int i = 0 ; i < 3 ; i++) F_TRY(cudaMalloc(&m->out[i], std::max(one, n_elem*m->nc)*sizeof(double))) ;
+    if(n_elem)
+    {
+        F_TRY(cudaMemcpyAsync(tmp, elem_ids, n_elem*npe*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
+        k_to_component_major<uint32_t><<<vec_grid(ctx, n_elem*npe), AMIE_VEC_THREADS, 0, ctx->stream>>>((const uint32_t *)tmp, m->ids, n_elem, npe) ;
+        F_TRY(cudaStreamSynchronize(ctx->stream)) ;
+        F_TRY(cudaMemcpyAsync(tmp, dshape, n_elem*npe*dim*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        k_to_component_major<double><<<vec_grid(ctx, n_elem*npe*dim), AMIE_VEC_THREADS, 0, ctx->stream>>>((const double *)tmp, m->dshape, n_elem, npe*dim) ;
+        F_TRY(cudaStreamSynchronize(ctx->stream)) ;
+        F_TRY(cudaMemcpyAsync(tmp, jinv, n_elem*dim*dim*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        k_to_component_major<double><<<vec_grid(ctx, n_elem*dim*dim), AMIE_VEC_THREADS, 0, ctx->stream>>>((const double *)tmp, m->jinv, n_elem, dim*dim) ;
+        F_TRY(cudaGetLastError()) ;
+        F_TRY(cudaStreamSynchronize(ctx->stream)) ;
+    }
+#undef F_TRY
+    cudaFree(tmp) ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, const double * tensors,
+                                    const double * imposed_strain, const double * imposed_stress,
+                                    const uint32_t * tensor_of_elem)
+{
+    if(!ctx || !n_tensors || !tensors) return AMIE_B200_ERR_ARG ;
+    FieldMap * m = ctx->fmap ;
+    if(!m) { ctx->set_error("set_element_behaviour before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    if(!tensor_of_elem && n_tensors != m->n_elem)
+    { ctx->set_error("set_element_behaviour: without tensor_of_elem there must be one behaviour per element") ; return AMIE_B200_ERR_ARG ; }
+    if(tensor_of_elem)
+        for(uint64_t e = 0 ; e < m->n_elem ; e++)
+            if(tensor_of_elem[e] >= n_tensors) { ctx->set_error("set_element_behaviour: tensor_of_elem entry out of range") ; return AMIE_B200_ERR_ARG ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    const uint64_t nc = m->nc ;
+    if(m->n_tensors != n_tensors)
+    {
+        ffree(m->tensors) ; ffree(m->istrain) ; ffree(m->istress) ;
+        m->n_tensors = 0 ; m->have_behaviour = false ;
+        CUDA_TRY(ctx, cudaMalloc(&m->tensors, n_tensors*nc*nc*sizeof(double))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->istrain, n_tensors*nc*sizeof(double))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->istress, n_tensors*nc*sizeof(double))) ;
+        m->n_tensors = n_tensors ;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(m->tensors, tensors, n_tensors*nc*nc*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    // absent imposed terms are zeros: x - 0 == x bit for bit, which is what the reference computes for behaviours
+    // without induced forces (it skips the subtraction, :967) and for the zero vector the base class returns (:1392)
+    if(imposed_strain) CUDA_TRY(ctx, cudaMemcpyAsync(m->istrain, imposed_strain, n_tensors*nc*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    else CUDA_TRY(ctx, cudaMemsetAsync(m->istrain, 0, n_tensors*nc*sizeof(double), ctx->stream)) ;
+    if(imposed_stress) CUDA_TRY(ctx, cudaMemcpyAsync(m->istress, imposed_stress, n_tensors*nc*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    else CUDA_TRY(ctx, cudaMemsetAsync(m->istress, 0, n_tensors*nc*sizeof(double), ctx->stream)) ;
+    if(tensor_of_elem)
+    {
+        if(!m->tensor_of_elem) CUDA_TRY(ctx, cudaMalloc(&m->tensor_of_elem, std::max<uint64_t>(1, m->n_elem)*sizeof(uint32_t))) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(m->tensor_of_elem, tensor_of_elem, m->n_elem*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
+    }
+    else ffree(m->tensor_of_elem) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    m->have_behaviour = true ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u,
+                             double * total_strain_out, double * mechanical_strain_out, double * real_stress_out)
+{
+    if(!ctx || (!u && n_u)) return AMIE_B200_ERR_ARG ;
+    FieldMap * m = ctx->fmap ;
+    if(!m) { ctx->set_error("element_fields before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    if(!m->have_behaviour) { ctx->set_error("element_fields before set_element_behaviour") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    const double * du = ctx->x ;        // the resident solution of the last solve
+    uint64_t len = ctx->N ;
+    uint64_t h2d = 0 ;
+    if(u)
+    {
+        if(m->u_tmp_len < n_u)
+        {
+            ffree(m->u_tmp) ; m->u_tmp_len = 0 ;
+            CUDA_TRY(ctx, cudaMalloc(&m->u_tmp, n_u*sizeof(double))) ;
+            m->u_tmp_len = n_u ;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(m->u_tmp, u, n_u*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        du = m->u_tmp ; len = n_u ; h2d = n_u*sizeof(double) ;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
+    if(m->n_elem)
+    {
+        const int grid = field_grid(ctx, m->n_elem) ;
+        if(m->dim == 2)
+            k_element_fields<2><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress,
+                    m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2]) ;
+        else
+            k_element_fields<3><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress,
+                    m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2]) ;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaGetLastError()) ;
+    const uint64_t bytes = m->n_elem*m->nc*sizeof(double) ;
+    double * host[3] = { total_strain_out, mechanical_strain_out, real_stress_out } ;
+    uint64_t d2h = 0 ;
+    for(int i = 0 ; i < 3 ; i++)
+        if(host[i] && bytes)
+        {
+            CUDA_TRY(ctx, cudaMemcpyAsync(host[i], m->out[i], bytes, cudaMemcpyDeviceToHost, ctx->stream)) ;
+            d2h += bytes ;
+        }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    float ms = 0.f ;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b)) ;
+    ctx->stats.fields_ms = ms ;
+    ctx->stats.field_elements = m->n_elem ;
+    ctx->stats.h2d_bytes = h2d ;
+    ctx->stats.d2h_bytes = d2h ;
+    return AMIE_B200_OK ;
+}
+
+}
