@@ -100,7 +100,8 @@ def fields_row(n=100, reps=5):
         for _ in range(reps):
             asm.check(lib.amie_b200_element_fields(ctx, None, 0, None, None, None))   # results stay on the device
             ms.append(asm.stats().fields_ms)
-        alg = ne * (4 * npe + 8 * npe * dim + 8 * dim * dim + 8 * npe * dim + 4 + 3 * 8 * nc)
+        # the solution is counted once per node (the per-slot gathers hit L2), csrc/fields.cu header
+        alg = ne * (4 * npe + 8 * npe * dim + 8 * dim * dim + 4 + 3 * 8 * nc) + 8 * dim * nb
         if ntab == ne:
             alg += ne * 8 * nc * (nc + 2)
         out[label] = dict(ms=min(ms), algorithmic_bytes=alg, gbs=alg / (min(ms) * 1e-3) / 1e9,
