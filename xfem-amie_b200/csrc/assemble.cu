@@ -158,78 +158,6 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
     }
 }
 
-// Variant 1 (option "assemble_variant" = 1): the same sums, U stored entries per thread.  The plain kernel keeps ONE
-// 8-byte load in flight per thread behind a chain of three dependent loads (list offset -> element-block index ->
-// value): 303 k resident threads x 8 B per ~1 us of latency is the 2.5 TB/s it measures.  Here each thread walks U
-// independent lists in lock step, the loads of every step issued together, so U times the bytes are in flight.
-// Entry u of a thread is U-strided by the thread count, so a warp still reads consecutive entries.  Per entry the
-// additions and their order are unchanged -> same bits.
-template<int SS, int U>
-static __global__ void k_assemble_gather_ilp(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
-                                             const double * __restrict__ ke, const double * __restrict__ scales,
-                                             uint32_t pp, const unsigned char * __restrict__ dirty, int all,
-                                             double * __restrict__ vals, uint64_t nent)
-{
-    const uint64_t nthreads = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t base = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; base < nent ; base += nthreads*U)
-    {
-        uint64_t idx[U] ;
-        uint32_t ent[U], p[U], len[U] ;
-        double a[U], c[U] ;
-        bool on[U] ;
-        uint32_t maxlen = 0 ;
-        #pragma unroll
-        for(int u = 0 ; u < U ; u++)
-        {
-            idx[u] = base+(uint64_t)u*nthreads ;
-            on[u] = idx[u] < nent ;
-            const uint64_t d = on[u] ? idx[u]/SS : 0 ;
-            ent[u] = (uint32_t)(idx[u]-d*SS) ;
-            if(on[u] && !all && !dirty[d]) on[u] = false ;
-            p[u] = 0 ; len[u] = 0 ;
-            if(on[u])
-            {
-                p[u] = __ldg(cptr+d) ;
-                len[u] = __ldg(cptr+d+1)-p[u] ;
-            }
-            a[u] = 0. ; c[u] = 0. ;
-        }
-        #pragma unroll
-        for(int u = 0 ; u < U ; u++) maxlen = max(maxlen, len[u]) ;
-        for(uint32_t k = 0 ; k < maxlen ; k++)
-        {
-            uint32_t src[U] ;
-            double sc[U], v[U] ;
-            #pragma unroll
-            for(int u = 0 ; u < U ; u++) src[u] = k < len[u] ? __ldg(csrc+p[u]+k) : 0u ;
-            #pragma unroll
-            for(int u = 0 ; u < U ; u++)
-            {
-                sc[u] = 0. ; v[u] = 0. ;
-                if(k < len[u])
-                {
-                    sc[u] = __ldg(scales+src[u]/pp) ;
-                    v[u] = ld_stream(ke+(uint64_t)src[u]*SS+ent[u]) ;
-                }
-            }
-            #pragma unroll
-            for(int u = 0 ; u < U ; u++)
-            {
-                if(k < len[u])
-                {
-                    const double y = __dsub_rn(__dmul_rn(sc[u], v[u]), c[u]) ;
-                    const double t = __dadd_rn(a[u], y) ;
-                    c[u] = __dsub_rn(__dsub_rn(t, a[u]), y) ;
-                    a[u] = t ;
-                }
-            }
-        }
-        #pragma unroll
-        for(int u = 0 ; u < U ; u++)
-            if(on[u]) vals[idx[u]] = a[u] ;
-    }
-}
-
 static __global__ void k_clear_dirty(unsigned char * __restrict__ dirty, uint64_t n)
 {
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
@@ -469,10 +397,7 @@ int amie_b200_assemble(amie_b200_ctx * ctx)
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     if(nent)
     {
-#define GATHER(N) do { if(ctx->opt_assemble_variant == 1) \
-            k_assemble_gather_ilp<N, 4><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent) ; \
-        else \
-            k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent) ; } while(0)
+#define GATHER(N) k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent)
         switch(ctx->S)
         {
             case 1: GATHER(1) ; break ;

@@ -50,7 +50,6 @@ struct amie_b200_ctx
     int opt_verbose = 0 ;
     int opt_batch = 0 ;         // iterations per speculative batch (0 = auto)
     int opt_graph = -1 ;        // -1 auto, 0 off, 1 on
-    int opt_assemble_variant = 0 ;  // 0: one stored entry per thread; 1: four in lock step (assemble.cu)
 
     // ---- stats
     amie_b200_stats stats {} ;
