@@ -37,6 +37,11 @@ extern "C" {
 /* precond_kind: what the caller passed as `Preconditionner * precond` */
 #define AMIE_B200_PRECOND_JACOBI 0    /* nullptr -> InverseDiagonal (conjugategradient.cpp:80-84)           */
 #define AMIE_B200_PRECOND_NULL   1    /* NullPreconditionner: precondition() is a no-op (preconditionners.cpp) */
+/* the reference's other diagonal preconditioners (solvers/inversediagonal.cpp; precondition() is t = v .* d):      */
+#define AMIE_B200_PRECOND_DIAGONAL_SQUARED 2  /* InverseDiagonalSquared: d = 1/(A_ii*A_ii)      (:69-82)             */
+#define AMIE_B200_PRECOND_LUMPED 3    /* InverseLumpedDiagonal: d = 1/(row sum), +-1 if tiny    (:19-48)             */
+#define AMIE_B200_PRECOND_DIAGONAL 4  /* any Preconditionner of that form: the caller supplies d with                */
+                                      /* amie_b200_set_preconditioner_diagonal                                       */
 
 typedef struct amie_b200_ctx amie_b200_ctx ;
 
@@ -94,6 +99,12 @@ int amie_b200_residual(amie_b200_ctx * ctx, const double * u, const double * f, 
 
 /* CoordinateIndexedSparseMatrix::inverseDiagonal (sparse/sparse_matrix.cpp:216-231)      */
 int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out) ;
+/* The diagonal of preconditioner `precond_kind` (0, 2, 3: built on the device from the resident values; 4: the one
+ * set below), as the corresponding reference class holds it in its `diagonal` member.                              */
+int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, double * d_out) ;
+/* d[N] for AMIE_B200_PRECOND_DIAGONAL: what a user-written Preconditionner with precondition(v, t) { t = v*d } holds.
+ * Kept until replaced or until the structure changes.                                                              */
+int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d) ;
 
 /* ------------------------------------------------------------------ device-resident variants
  * Same algorithms with b / x0 / x kept in HBM (no host<->device copies in the call): used to

@@ -27,6 +27,7 @@
 #include "solvers/conjugategradient.h"
 #include "solvers/biconjugategradientstabilized.h"
 #include "solvers/inversediagonal.h"
+#include "solvers/preconditionners.h"
 #include "sparse/sparse_matrix.h"
 
 namespace {
@@ -62,6 +63,33 @@ void fill_assembly(Amie::Assembly & a, int stride, uint64_t nb, const uint32_t *
     a.displacements = 0. ;
 }
 
+// a user-written preconditioner, as a caller of LinearSolver::solve(x0, precond, ...) may pass one:
+// precondition() is t = v .* d for a diagonal the user chose
+struct UserDiagonal : public Amie::Preconditionner
+{
+    Vector d ;
+    UserDiagonal(const double * p, size_t n) : d(p, n) { }
+    virtual ~UserDiagonal() { }
+    virtual void precondition(const Vector & v, Vector & t) { for(size_t i = 0 ; i < v.size() ; i++) t[i] = v[i]*d[i] ; }
+} ;
+
+const double * g_user_diag = nullptr ;
+uint64_t g_user_diag_n = 0 ;
+
+// precond_kind: 0 nullptr (the solver builds its InverseDiagonal), 1 NullPreconditionner, 2 InverseDiagonalSquared,
+// 3 InverseLumpedDiagonal, 4 UserDiagonal over the vector given to amie_ref_set_user_diagonal.  Caller deletes.
+Amie::Preconditionner * make_precond(int kind, Amie::Assembly & a)
+{
+    switch(kind)
+    {
+        case 1: return new Amie::NullPreconditionner() ;
+        case 2: return new Amie::InverseDiagonalSquared(a.getMatrix()) ;
+        case 3: return new Amie::InverseLumpedDiagonal(a.getMatrix()) ;
+        case 4: return new UserDiagonal(g_user_diag, g_user_diag_n) ;
+        default: return nullptr ;
+    }
+}
+
 void copy_log(const std::string & s, char * log, uint64_t logcap)
 {
     if(!log || !logcap) return ;
@@ -75,6 +103,24 @@ void copy_log(const std::string & s, char * log, uint64_t logcap)
 
 extern "C" {
 
+// the diagonal amie_ref_cg / amie_ref_bicgstab hand to the solver as a UserDiagonal when precond_kind == 4
+void amie_ref_set_user_diagonal(const double * d, uint64_t n) { g_user_diag = d ; g_user_diag_n = n ; }
+
+// the diagonal the reference's own preconditioner classes build from the matrix: kind 0 InverseDiagonal,
+// 2 InverseDiagonalSquared, 3 InverseLumpedDiagonal (solvers/inversediagonal.cpp:19-42, :50, :69-73)
+int amie_ref_precond_diagonal(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                              const double * array_padded, int kind, double * d_out)
+{
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, nullptr) ;
+    const size_t n = nb*stride ;
+    if(kind == 0) { Amie::InverseDiagonal P(a.getMatrix()) ; std::memcpy(d_out, &P.diagonal[0], n*sizeof(double)) ; }
+    else if(kind == 2) { Amie::InverseDiagonalSquared P(a.getMatrix()) ; std::memcpy(d_out, &(*P.diagonal)[0], n*sizeof(double)) ; }
+    else if(kind == 3) { Amie::InverseLumpedDiagonal P(a.getMatrix()) ; std::memcpy(d_out, &P.diagonal[0], n*sizeof(double)) ; }
+    else return -1 ;
+    return 0 ;
+}
+
 int amie_ref_max_threads()
 {
 #ifdef HAVE_OPENMP
@@ -84,7 +130,7 @@ int amie_ref_max_threads()
 #endif
 }
 
-// returns 1 converged / 0 not converged.  precond_kind: 0 = nullptr (InverseDiagonal), 1 = NullPreconditionner
+// returns 1 converged / 0 not converged.  precond_kind: see make_precond
 int amie_ref_cg(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
                 const double * array_padded, const double * b, const double * x0, uint64_t nx0,
                 int precond_kind, double eps, int maxit, uint64_t nssor, uint64_t rowstart, uint64_t colstart,
@@ -102,10 +148,11 @@ int amie_ref_cg(int stride, uint64_t nb, const uint32_t * row_size, const uint32
     cg.colstart = colstart ;
     Vector vx0(0., nx0) ;
     if(nx0) std::memcpy(&vx0[0], x0, nx0*sizeof(double)) ;
-    Amie::NullPreconditionner np ;
+    Amie::Preconditionner * P = make_precond(precond_kind, a) ;
     double t0 = now() ;
-    bool ok = cg.solve(vx0, precond_kind == 1 ? &np : nullptr, eps, maxit, false) ;
+    bool ok = cg.solve(vx0, P, eps, maxit, false) ;
     double t1 = now() ;
+    delete P ;                       // the solver does not own a preconditioner it was given (cleanup == false)
     std::memcpy(x_out, &cg.x[0], cg.x.size()*sizeof(double)) ;
     if(nit_out) *nit_out = cg.nit ;
     if(wall_s_out) *wall_s_out = t1-t0 ;
@@ -127,10 +174,11 @@ int amie_ref_bicgstab(int stride, uint64_t nb, const uint32_t * row_size, const 
     Amie::BiConjugateGradientStabilized cg(&a) ;
     Vector vx0(0., nx0) ;
     if(nx0) std::memcpy(&vx0[0], x0, nx0*sizeof(double)) ;
-    Amie::NullPreconditionner np ;
+    Amie::Preconditionner * P = make_precond(precond_kind, a) ;
     double t0 = now() ;
-    bool ok = cg.solve(vx0, precond_kind == 1 ? &np : nullptr, eps, maxit, true) ;
+    bool ok = cg.solve(vx0, P, eps, maxit, true) ;
     double t1 = now() ;
+    delete P ;
     std::memcpy(x_out, &cg.x[0], cg.x.size()*sizeof(double)) ;
     if(wall_s_out) *wall_s_out = t1-t0 ;
     std::string s = cap.sink.str() ;

@@ -85,25 +85,44 @@ class Sys:
 
 # ------------------------------------------------------------------ C restatement
 
-def oracle_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None):
+# precond kinds (include/amie_b200.h): 0 nullptr -> InverseDiagonal, 1 NullPreconditionner, 2 InverseDiagonalSquared,
+# 3 InverseLumpedDiagonal, 4 a diagonal supplied by the caller (`diag`)
+def oracle_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None, diag=None):
     b = S.b if b is None else np.ascontiguousarray(b, np.float64)
     x = np.zeros(S.n)
     info = CgInfo()
     x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    if precond == 4:
+        diag = np.ascontiguousarray(diag, np.float64)
+        ret = oracle().amie_oracle_cg_diag(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), _vp(diag),
+                                           f64(eps), int(maxit), u64(nssor), u64(rowstart), u64(colstart), int(nthreads),
+                                           _vp(x), ctypes.byref(info))
+        return ret, x, info
     ret = oracle().amie_oracle_cg(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond),
                                   f64(eps), int(maxit), u64(nssor), u64(rowstart), u64(colstart), int(nthreads),
                                   _vp(x), ctypes.byref(info))
     return ret, x, info
 
 
-def oracle_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None):
+def oracle_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None, diag=None):
     b = S.b if b is None else np.ascontiguousarray(b, np.float64)
     x = np.zeros(S.n)
     info = BicgInfo()
     x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    if precond == 4:
+        diag = np.ascontiguousarray(diag, np.float64)
+        ret = oracle().amie_oracle_bicgstab_diag(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), _vp(diag),
+                                                 f64(eps), int(maxit), int(nthreads), _vp(x), ctypes.byref(info))
+        return ret, x, info
     ret = oracle().amie_oracle_bicgstab(*S.head(), _vp(b), _vp(x0), u64(0 if x0 is None else x0.size), int(precond),
                                         f64(eps), int(maxit), int(nthreads), _vp(x), ctypes.byref(info))
     return ret, x, info
+
+
+def oracle_precond_diagonal(S, kind):
+    d = np.zeros(S.n)
+    oracle().amie_oracle_precond_diagonal(*S.head(), int(kind), _vp(d))
+    return d
 
 
 def oracle_assign(S, v, b=None, rowstart=0, colstart=0):
@@ -136,8 +155,18 @@ def oracle_dot(a, b, nthreads=1):
 
 # ------------------------------------------------------------------ the real reference (oracle/_ref)
 
-def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None):
+def ref_precond_diagonal(S, kind):
+    d = np.zeros(S.n)
+    rc = ref().amie_ref_precond_diagonal(*S.head(), int(kind), _vp(d))
+    assert rc == 0
+    return d
+
+
+def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, colstart=0, nthreads=1, b=None, diag=None):
     R = ref()
+    if precond == 4:
+        diag = np.ascontiguousarray(diag, np.float64)       # stays alive until the call below returns
+        R.amie_ref_set_user_diagonal(_vp(diag), u64(diag.size))
     b = S.b if b is None else np.ascontiguousarray(b, np.float64)
     x = np.zeros(S.n)
     nit = u64()
@@ -150,8 +179,11 @@ def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, col
     return ret, x, nit.value, wall.value, log.value.decode(errors="replace")
 
 
-def ref_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None):
+def ref_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None, diag=None):
     R = ref()
+    if precond == 4:
+        diag = np.ascontiguousarray(diag, np.float64)
+        R.amie_ref_set_user_diagonal(_vp(diag), u64(diag.size))
     b = S.b if b is None else np.ascontiguousarray(b, np.float64)
     x = np.zeros(S.n)
     nit = u64()

@@ -1,0 +1,140 @@
+"""The reference's diagonal preconditioners on the device (solvers/inversediagonal.cpp: InverseDiagonalSquared,
+InverseLumpedDiagonal, and any user-written Preconditionner of the form t = v*d) through the C-ABI: the diagonals
+bit for bit, the solves to the bar of the Jacobi path (iterations within +-2, x within 1e-8 relative L2) on systems
+where the reference itself is that reproducible -- with InverseDiagonalSquared the reference's own answer moves by
+1e-6 .. 1e-2 on the 2D and ASR systems when only its thread count changes, so those pairs are left out."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2, random_spd_blocks
+
+pytestmark = pytest.mark.gpu
+PRECOND = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "precond-*.npz")))
+X_TOL, NIT_TOL = 1e-8, 2
+
+
+def assembly_of(pkg, S):
+    return pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+
+
+def precond_object(pkg, kind, diag):
+    return {2: pkg.InverseDiagonalSquared, 3: pkg.InverseLumpedDiagonal}[kind]() if kind in (2, 3) else pkg.DiagonalPreconditionner(diag)
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 12), ("S3-tet", 14), ("S2-tri", 40), ("ASR-hex", 12)])
+def test_preconditioner_diagonals_bit_exact(pkg, ol, systems, preset, n):
+    S = systems(preset, n)
+    asm = assembly_of(pkg, S)
+    for kind in (pkg.PRECOND_JACOBI, pkg.PRECOND_DIAGONAL_SQUARED, pkg.PRECOND_LUMPED, pkg.PRECOND_JACOBI):
+        assert np.array_equal(asm.preconditioner_diagonal(kind), ol.oracle_precond_diagonal(S, kind)), kind
+    asm.close()
+
+
+@pytest.mark.parametrize("stride", [1, 2, 3, 4, 6])
+def test_preconditioner_diagonals_all_strides(pkg, ol, stride):
+    rs, ci, arr, b = random_spd_blocks(stride, 70, 60 + stride)
+    S = ol.Sys(stride, 70, rs, ci, arr, b)
+    asm = assembly_of(pkg, S)
+    for kind in (2, 3, 0):
+        assert np.array_equal(asm.preconditioner_diagonal(kind), ol.oracle_precond_diagonal(S, kind)), kind
+    asm.close()
+
+
+@pytest.mark.parametrize("path", PRECOND, ids=[os.path.basename(p)[:-4] for p in PRECOND])
+def test_against_reference_precond_golden(pkg, path):
+    """Against what the real preconditioner classes and solvers produced (tests/golden/make_golden_precond.py)."""
+    g = np.load(path)
+    name = os.path.basename(path)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(g["row_size"], g["column_index"], int(g["stride"]), g["array"]),
+                       g["b"], device=0)
+    for kind in (0, 2, 3):
+        assert np.array_equal(asm.preconditioner_diagonal(kind), g[f"diag{kind}"]), kind
+    for kind in (2, 3, 4):
+        if not bool(g[f"cg{kind}_ok"]):
+            continue        # InverseLumpedDiagonal on a stiffness matrix (row sums ~ 0): the reference does not converge
+        if kind == 2 and "S2-tri" in name:
+            continue        # not reproducible in the reference itself (see the module docstring)
+        P = precond_object(pkg, kind, g["user_diagonal"])
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor = 32
+        assert cg.solve(None, P, 1e-10, -1)
+        assert abs(int(cg.nit) - int(g[f"cg{kind}_nit"])) <= NIT_TOL, (kind, cg.nit, int(g[f"cg{kind}_nit"]))
+        assert rel_l2(cg.x, g[f"cg{kind}_x"]) <= X_TOL, kind
+        bi = pkg.BiConjugateGradientStabilized(asm)
+        assert bi.solve(None, P, 1e-10, -1) == bool(g[f"bicg{kind}_ok"])
+        assert rel_l2(bi.x, g[f"bicg{kind}_x"]) <= X_TOL, kind
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n,kinds", [("S3-hex", 12, (2, 4)), ("S3-tet", 14, (2, 4)), ("S2-tri", 40, (4,)),
+                                            ("ASR-hex", 12, (4,))])
+def test_pcg_and_bicgstab_with_diagonal_preconditioners(pkg, ol, systems, preset, n, kinds):
+    S = systems(preset, n)
+    asm = assembly_of(pkg, S)
+    ud = ol.oracle_precond_diagonal(S, 0) * np.random.default_rng(3).uniform(0.5, 1.5, S.n)
+    for kind in kinds:
+        P = precond_object(pkg, kind, ud)
+        ret, x_ref, info = ol.oracle_cg(S, precond=kind, nssor=32, diag=ud)
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor = 32
+        assert cg.solve(None, P, 1e-10, -1) == bool(ret)
+        assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (kind, cg.nit, info.nit)
+        assert rel_l2(cg.x, x_ref) <= X_TOL, kind
+        ret, x_ref, info = ol.oracle_bicgstab(S, precond=kind, diag=ud)
+        bi = pkg.BiConjugateGradientStabilized(asm)
+        assert bi.solve(None, P, 1e-10, -1) == bool(ret)
+        assert rel_l2(bi.x, x_ref) <= X_TOL, kind
+        assert 0.5 * info.nit <= bi.nit <= 1.6 * info.nit + 5, (kind, bi.nit, info.nit)
+    # back to the default: the Jacobi diagonal is rebuilt, not the last one reused
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    assert cg.solve(None, None, 1e-10, -1) == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL and rel_l2(cg.x, x_ref) <= X_TOL
+    asm.close()
+
+
+def test_lumped_diagonal_solves_and_value_updates(pkg, ol):
+    """InverseLumpedDiagonal where it is usable (diagonally dominant blocks), and every device-built diagonal
+    follows a change of the matrix values."""
+    rs, ci, arr, b = random_spd_blocks(3, 120, 21)
+    S = ol.Sys(3, 120, rs, ci, arr, b)
+    asm = assembly_of(pkg, S)
+    for scale in (1.0, 3.0):
+        S2 = ol.Sys(3, 120, rs, ci, arr * scale, b)
+        asm.getMatrix().array[:] = S2.array
+        asm.values_changed()
+        for kind in (3, 2):
+            ret, x_ref, info = ol.oracle_cg(S2, precond=kind, nssor=32)
+            cg = pkg.ConjugateGradient(asm)
+            cg.nssor = 32
+            assert cg.solve(None, precond_object(pkg, kind, None), 1e-10, -1) == bool(ret)
+            assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL and rel_l2(cg.x, x_ref) <= X_TOL, (scale, kind)
+    asm.close()
+
+
+def test_precond_error_paths(pkg, systems):
+    S = systems("S3-hex", 12)
+    asm = assembly_of(pkg, S)
+    asm.sync_matrix()
+    asm.upload_rhs(S.b)
+    asm.upload_x0(None)
+    with pytest.raises(pkg.AmieB200Error) as e:           # a user diagonal was never given
+        asm.pcg_resident(precond=pkg.PRECOND_DIAGONAL)
+    assert e.value.code == pkg.ERR_STATE
+    with pytest.raises(pkg.AmieB200Error) as e:           # no such kind
+        asm.pcg_resident(precond=5)
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    with pytest.raises(pkg.AmieB200Error) as e:           # NullPreconditionner stays refused for BiCGStab
+        asm.bicgstab_resident(precond=pkg.PRECOND_NULL)
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+
+    class Foreign(pkg.Preconditionner):                   # anything that is not a diagonal: no CPU fallback
+        pass
+    with pytest.raises(pkg.AmieB200Error) as e:
+        pkg.ConjugateGradient(asm).solve(None, Foreign(), 1e-10, -1)
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    asm.close()

@@ -10,9 +10,9 @@ import os
 import numpy as np
 import pytest
 
-# solver fixtures only: *-assembly.npz / bc-rand-*.npz / *-fields.npz belong to the assembly and field-recovery tests
+# solver fixtures only: *-assembly.npz / bc-rand-*.npz / *-fields.npz / precond-*.npz belong to the assembly, field-recovery and preconditioner tests
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith("bc-rand-"))]
+          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith(("bc-rand-", "precond-")))]
 
 
 def _sys(ol, g):

@@ -26,7 +26,7 @@ u64 = ctypes.c_uint64
 f64 = ctypes.c_double
 
 ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NAN, ERR_UNSUPPORTED, ERR_NCCL = -1, -2, -3, -4, -5, -6
-PRECOND_JACOBI, PRECOND_NULL = 0, 1
+PRECOND_JACOBI, PRECOND_NULL, PRECOND_DIAGONAL_SQUARED, PRECOND_LUMPED, PRECOND_DIAGONAL = 0, 1, 2, 3, 4
 default_solver_precision = 1e-10          # polynomial/variable.h:14
 
 
@@ -75,6 +75,8 @@ def lib():
         L.amie_b200_bicgstab.argtypes = [vp, vp, vp, u64, ci, f64, ci, vp, vp, vp]
         L.amie_b200_spmv.argtypes = [vp, vp, vp, u64, u64, vp]
         L.amie_b200_inverse_diagonal.argtypes = [vp, vp]
+        L.amie_b200_preconditioner_diagonal.argtypes = [vp, ci, vp]
+        L.amie_b200_set_preconditioner_diagonal.argtypes = [vp, vp]
         L.amie_b200_residual.argtypes = [vp, vp, vp, vp, vp]
         L.amie_b200_upload_rhs.argtypes = [vp, vp]
         L.amie_b200_upload_x0.argtypes = [vp, vp, u64]
@@ -409,6 +411,14 @@ class Assembly:
         self.check(lib().amie_b200_inverse_diagonal(self.ctx, _ptr(d)))
         return d
 
+    def preconditioner_diagonal(self, kind):
+        """The `diagonal` member of the reference's preconditioner class `kind` (PRECOND_JACOBI, _DIAGONAL_SQUARED,
+        _LUMPED), built on the device from the resident values."""
+        self.sync_matrix()
+        d = np.zeros(self.stats().ndof)
+        self.check(lib().amie_b200_preconditioner_diagonal(self.ctx, int(kind), _ptr(d)))
+        return d
+
     def cgsolve(self, maxit=-1, verbose=False):
         """Assembly::cgsolve for an assembled symmetric system (solvers/assembly.cpp:1841-1858)."""
         cg = ConjugateGradient(self)
@@ -421,11 +431,40 @@ class Assembly:
 
 
 class Preconditionner:
+    """solvers/preconditionners.h:19-26.  `kind` is what the C-ABI is told; `diagonal` (kind PRECOND_DIAGONAL) is
+    uploaded before the solve."""
     kind = None
+    diagonal = None
 
 
 class NullPreconditionner(Preconditionner):
     kind = PRECOND_NULL
+
+
+class InverseDiagonalSquared(Preconditionner):
+    """solvers/inversediagonal.h:41-47; built on the device from the assembly's matrix."""
+    kind = PRECOND_DIAGONAL_SQUARED
+
+    def __init__(self, A=None):
+        pass
+
+
+class InverseLumpedDiagonal(Preconditionner):
+    """solvers/inversediagonal.h:32-38; built on the device from the assembly's matrix."""
+    kind = PRECOND_LUMPED
+
+    def __init__(self, A=None):
+        pass
+
+
+class DiagonalPreconditionner(Preconditionner):
+    """A user-written preconditioner whose precondition(v, t) is t = v * diagonal (also what an explicitly
+    constructed InverseDiagonal / InverseDiagonalSquared / InverseLumpedDiagonal object amounts to: the shim
+    uploads the object's own `diagonal`)."""
+    kind = PRECOND_DIAGONAL
+
+    def __init__(self, diagonal):
+        self.diagonal = np.ascontiguousarray(diagonal, np.float64)
 
 
 class LinearSolver:
@@ -436,13 +475,18 @@ class LinearSolver:
         n = 0 if assembly.getForces() is None else assembly.getForces().size
         self.x = np.zeros(n)          # Solver::Solver, solvers/solver.cpp:15
 
-    @staticmethod
-    def _kind(precond):
+    def _kind(self, precond):
         if precond is None:
             return PRECOND_JACOBI
-        if isinstance(precond, NullPreconditionner):
-            return PRECOND_NULL
-        raise AmieB200Error(ERR_UNSUPPORTED, "only nullptr (InverseDiagonal) and NullPreconditionner run on the device")
+        if isinstance(precond, Preconditionner) and precond.kind is not None:
+            if precond.kind == PRECOND_DIAGONAL:
+                d = precond.diagonal
+                if d is None or d.size != self.assembly.getForces().size:
+                    raise ValueError("DiagonalPreconditionner: one entry per degree of freedom")
+                self.assembly.check(lib().amie_b200_set_preconditioner_diagonal(self.assembly.ctx, _ptr(d)))
+            return precond.kind
+        raise AmieB200Error(ERR_UNSUPPORTED, "only diagonal preconditioners (nullptr -> InverseDiagonal, InverseDiagonalSquared, "
+                            "InverseLumpedDiagonal, a user diagonal) and NullPreconditionner run on the device")
 
 
 class ConjugateGradient(LinearSolver):

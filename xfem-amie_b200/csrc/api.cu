@@ -15,12 +15,12 @@ static std::string g_error ;
 
 template<typename T> static void dfree(T *& p) { if(p) cudaFree(p) ; p = nullptr ; }
 
-static void free_matrix(amie_b200_ctx * ctx)
+void ctx_free_matrix(amie_b200_ctx * ctx)
 {
     ctx->alloc_gen++ ;
     assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
     field_map_destroy(ctx) ;             // element data belongs to the topology too
-    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ;
+    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }
 
@@ -71,25 +71,46 @@ int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx)
     return AMIE_B200_OK ;
 }
 
-int ctx_ensure_dinv(amie_b200_ctx * ctx)
+int ctx_ensure_dinv(amie_b200_ctx * ctx, int kind)
 {
-    if(ctx->dinv_valid) return AMIE_B200_OK ;
-    if(!ctx->have_values) { ctx->set_error("inverse diagonal: no values") ; return AMIE_B200_ERR_STATE ; }
+    if(ctx->dinv_valid && ctx->dinv_kind == kind) return AMIE_B200_OK ;
+    if(kind == AMIE_B200_PRECOND_DIAGONAL)
+    {
+        if(!ctx->user_diag) { ctx->set_error("diagonal preconditioner: amie_b200_set_preconditioner_diagonal was not called") ; return AMIE_B200_ERR_STATE ; }
+    }
+    else if(!ctx->have_values) { ctx->set_error("inverse diagonal: no values") ; return AMIE_B200_ERR_STATE ; }
+    if(kind != AMIE_B200_PRECOND_JACOBI && kind != AMIE_B200_PRECOND_DIAGONAL && ctx->dist)
+    {
+        ctx->set_error("InverseDiagonalSquared / InverseLumpedDiagonal: not available on a row-partitioned context (pass the diagonal)") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
     if(!ctx->dinv) CUDA_TRY(ctx, cudaMalloc(&ctx->dinv, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
+    ctx->dinv_valid = false ;
     int grid = vec_grid(ctx, ctx->N) ;
-    if(ctx->dist)
+#define DIAG_BY_STRIDE(KERNEL, ...) do { \
+        if(ctx->S == 3)      KERNEL<3><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__) ; \
+        else if(ctx->S == 2) KERNEL<2><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__) ; \
+        else if(ctx->S == 1) KERNEL<1><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__) ; \
+        else if(ctx->S == 4) KERNEL<4><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__) ; \
+        else                 KERNEL<6><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__) ; } while(0)
+    if(kind == AMIE_B200_PRECOND_DIAGONAL)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dinv, ctx->user_diag, ctx->N*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    else if(kind == AMIE_B200_PRECOND_DIAGONAL_SQUARED)
+        DIAG_BY_STRIDE(k_inverse_diagonal_squared, ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    else if(kind == AMIE_B200_PRECOND_LUMPED)
+        DIAG_BY_STRIDE(k_inverse_lumped_diagonal, ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    else if(kind != AMIE_B200_PRECOND_JACOBI) { ctx->set_error("unknown diagonal preconditioner kind") ; return AMIE_B200_ERR_ARG ; }
+    else if(ctx->dist)
     {
         int rc = dist_inverse_diagonal(ctx) ;       // renumbered columns are not sorted: linear scan for the diagonal block
         if(rc) return rc ;
     }
-    else if(ctx->S == 3) k_inverse_diagonal<3><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else if(ctx->S == 2) k_inverse_diagonal<2><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else if(ctx->S == 1) k_inverse_diagonal<1><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else if(ctx->S == 4) k_inverse_diagonal<4><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
-    else                 k_inverse_diagonal<6><<<grid, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+    else DIAG_BY_STRIDE(k_inverse_diagonal, ctx->rowptr, ctx->col, ctx->vals, 0u, ctx->nb, ctx->dinv) ;
+#undef DIAG_BY_STRIDE
     CUDA_TRY(ctx, cudaGetLastError()) ;
     ctx->stats.kernel_launches++ ;
     ctx->dinv_valid = true ;
+    ctx->dinv_kind = kind ;
     return AMIE_B200_OK ;
 }
 
@@ -197,7 +218,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     dist_destroy(ctx) ;
     if(ctx->graph_cg.exec) cudaGraphExecDestroy(ctx->graph_cg.exec) ;
     if(ctx->graph_bicg.exec) cudaGraphExecDestroy(ctx->graph_bicg.exec) ;
-    free_matrix(ctx) ;
+    ctx_free_matrix(ctx) ;
     free_vectors(ctx) ;
     dfree(ctx->st) ; dfree(ctx->partials) ; dfree(ctx->flag) ;
     if(ctx->st_host) cudaFreeHost(ctx->st_host) ;
@@ -269,7 +290,7 @@ int ctx_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32
     double t0 = wall_now() ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
-    free_matrix(ctx) ;
+    ctx_free_matrix(ctx) ;
     // accumulated_row_size (sparse/sparse_matrix.cpp:59-66), with the total appended
     std::vector<uint32_t> rp(nb+1) ;
     uint64_t acc = 0 ;
@@ -292,7 +313,7 @@ int ctx_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     if(bad)
     {
-        free_matrix(ctx) ;
+        ctx_free_matrix(ctx) ;
         ctx->set_error(bad == 1 ? "set_structure: column index out of range" : "set_structure: column indices not strictly ascending in a row") ;
         return AMIE_B200_ERR_ARG ;
     }
@@ -651,6 +672,29 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
     float ms = 0.f ;
     cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) ;
     if(ms_out) *ms_out = ms/reps ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d)
+{
+    if(!ctx || !d) return AMIE_B200_ERR_ARG ;
+    if(!ctx->have_structure) { ctx->set_error("set_preconditioner_diagonal before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    if(!ctx->user_diag) CUDA_TRY(ctx, cudaMalloc(&ctx->user_diag, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->user_diag, d, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    if(ctx->dinv_kind == AMIE_B200_PRECOND_DIAGONAL) ctx->dinv_valid = false ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, double * d_out)
+{
+    if(!ctx || !d_out || precond_kind == AMIE_B200_PRECOND_NULL) return AMIE_B200_ERR_ARG ;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    int rc = ctx_ensure_dinv(ctx, precond_kind) ;
+    if(rc) return rc ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_out, ctx->dinv, ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     return AMIE_B200_OK ;
 }
 

@@ -30,6 +30,8 @@ struct amie_b200_ctx
     double * vals = nullptr ;
     double * dinv = nullptr ;
     bool have_structure = false, have_values = false, dinv_valid = false ;
+    int dinv_kind = AMIE_B200_PRECOND_JACOBI ;   // which diagonal preconditioner `dinv` holds while dinv_valid
+    double * user_diag = nullptr ;               // AMIE_B200_PRECOND_DIAGONAL: the caller's diagonal (N doubles)
     bool have_rhs = false ;
 
     // ---- vectors (device); x-like vectors that are SpMV inputs have room for the halo tail
@@ -82,9 +84,10 @@ inline double wall_now()
 // internal entry points shared between translation units
 void assembly_map_destroy(amie_b200_ctx * ctx) ;          // assemble.cu
 void field_map_destroy(amie_b200_ctx * ctx) ;             // fields.cu
+void ctx_free_matrix(amie_b200_ctx * ctx) ;               // api.cu: matrix arrays + everything tied to the topology
 int ctx_alloc_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx) ;
-int ctx_ensure_dinv(amie_b200_ctx * ctx) ;
+int ctx_ensure_dinv(amie_b200_ctx * ctx, int kind = AMIE_B200_PRECOND_JACOBI) ;   // dinv = the diagonal of preconditioner `kind`
 int ctx_sync_state(amie_b200_ctx * ctx, int slot) ;       // D2H of KrylovState into st_host[slot] + sync
 int ctx_push_state(amie_b200_ctx * ctx, const KrylovState & s) ;
 void ctx_reset_solve_stats(amie_b200_ctx * ctx) ;

@@ -757,11 +757,7 @@ int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * 
     const uint64_t r0 = d->bounds[d->rank], r1 = d->bounds[d->rank+1] ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
-    if(ctx->rowptr) { cudaFree(ctx->rowptr) ; ctx->rowptr = nullptr ; }
-    if(ctx->col) { cudaFree(ctx->col) ; ctx->col = nullptr ; }
-    if(ctx->vals) { cudaFree(ctx->vals) ; ctx->vals = nullptr ; }
-    if(ctx->dinv) { cudaFree(ctx->dinv) ; ctx->dinv = nullptr ; }
-    ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
+    ctx_free_matrix(ctx) ;
     ctx->S = R.stride ; ctx->nb = r1-r0 ; ctx->nb_global = nbg ; ctx->row_base = r0 ; ctx->N = ctx->nb*R.stride ;
     ctx->ncols_local = ctx->nb ;
     // b lives in the vectors: allocate them for the owned part first (re-sized once the halo is known)

@@ -46,9 +46,9 @@ void queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
 
 int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, int maxit, uint64_t * nit_out, double * err_out)
 {
-    if(precond_kind != AMIE_B200_PRECOND_JACOBI && precond_kind != AMIE_B200_PRECOND_NULL)
+    if(precond_kind < AMIE_B200_PRECOND_JACOBI || precond_kind > AMIE_B200_PRECOND_DIAGONAL)
     {
-        ctx->set_error("bicgstab: only nullptr (InverseDiagonal) and NullPreconditionner are on the device path") ;
+        ctx->set_error("bicgstab: preconditioner kind not on the device path (diagonal preconditioners are)") ;
         return AMIE_B200_ERR_UNSUPPORTED ;
     }
     if(precond_kind == AMIE_B200_PRECOND_NULL)
@@ -66,7 +66,7 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     ctx_reset_solve_stats(ctx) ;
     cudaEventRecord(ctx->ev_a, ctx->stream) ;
     if((rc = ctx_ensure_bicg_vectors(ctx))) return rc ;
-    if(precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx))) return rc ;        // :26-34
+    if(precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx, precond_kind))) return rc ;        // :26-34
     const size_t vbytes = N*sizeof(double) ;
     const double vepsilon = epsilon*1e-1 ;                                          // :16
     uint64_t nit = 0 ;

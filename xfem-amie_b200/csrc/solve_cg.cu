@@ -99,9 +99,9 @@ void queue_iteration(const CgRun & R)
 int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t nssor,
                       uint64_t rowstart, uint64_t colstart, uint64_t * nit_out, double * err_out, double * rho_out)
 {
-    if(precond_kind != AMIE_B200_PRECOND_JACOBI && precond_kind != AMIE_B200_PRECOND_NULL)
+    if(precond_kind < AMIE_B200_PRECOND_JACOBI || precond_kind > AMIE_B200_PRECOND_DIAGONAL)
     {
-        ctx->set_error("pcg: only nullptr (InverseDiagonal) and NullPreconditionner are on the device path") ;
+        ctx->set_error("pcg: preconditioner kind not on the device path (diagonal preconditioners and NullPreconditionner are)") ;
         return AMIE_B200_ERR_UNSUPPORTED ;
     }
     const int S = ctx->S ;
@@ -148,7 +148,8 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         return finish(1) ;
     }
     // :80-90
-    if(R.precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx))) return rc ;
+    // every diagonal preconditioner (t = v .* d) runs the Jacobi kernels on its own d
+    if(R.precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx, precond_kind))) return rc ;
 
     const double realeps = std::max(1e-12, eps) ;                                   // :92
     // getForces().size() is the GLOBAL system size on a row-partitioned context

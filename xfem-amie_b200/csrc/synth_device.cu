@@ -85,12 +85,7 @@ extern "C" int amie_b200_synth_to_device(amie_b200_ctx * ctx, const amie_b200_sy
     if(nb >= 0xffffffffull) { ctx->set_error("synth_to_device: too many nodes") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     // a rough upper bound of the stored blocks must fit uint32 offsets
     if(nb*27 >= 0xffffffffull && R.dim == 3 && R.ntemplates == 1) { ctx->set_error("synth_to_device: more than 2^32-1 blocks") ; return AMIE_B200_ERR_UNSUPPORTED ; }
-    if(ctx->rowptr) { cudaFree(ctx->rowptr) ; ctx->rowptr = nullptr ; }
-    if(ctx->col) { cudaFree(ctx->col) ; ctx->col = nullptr ; }
-    if(ctx->vals) { cudaFree(ctx->vals) ; ctx->vals = nullptr ; }
-    if(ctx->dinv) { cudaFree(ctx->dinv) ; ctx->dinv = nullptr ; }
-    ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
-    ctx->alloc_gen++ ;
+    ctx_free_matrix(ctx) ;
     ctx->S = R.stride ; ctx->nb = ctx->nb_global = nb ; ctx->row_base = 0 ; ctx->N = nb*R.stride ; ctx->ncols_local = nb ;
     int rc = ctx_alloc_vectors(ctx) ;
     if(rc) return rc ;

@@ -34,8 +34,25 @@ struct CoordinateIndexedSparseMatrix
     }
 } ;
 
-struct Preconditionner { virtual ~Preconditionner() { } virtual int kind() const = 0 ; } ;
+// solvers/preconditionners.h:19-32, solvers/inversediagonal.h:23-47.  kind() is what the C-ABI is told; diagonal()
+// (kind AMIE_B200_PRECOND_DIAGONAL) is uploaded before the solve.
+struct Preconditionner
+{
+    virtual ~Preconditionner() { }
+    virtual int kind() const = 0 ;
+    virtual const Vector * diagonal() const { return nullptr ; }
+} ;
 struct NullPreconditionner : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_NULL ; } } ;
+struct InverseDiagonalSquared : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_DIAGONAL_SQUARED ; } } ;
+struct InverseLumpedDiagonal : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_LUMPED ; } } ;
+// a user-written preconditioner whose precondition(v, t) is t = v * d
+struct DiagonalPreconditionner : public Preconditionner
+{
+    Vector d ;
+    explicit DiagonalPreconditionner(const Vector & diag) : d(diag) { }
+    int kind() const override { return AMIE_B200_PRECOND_DIAGONAL ; }
+    const Vector * diagonal() const override { return &d ; }
+} ;
 
 class Assembly
 {
@@ -75,6 +92,17 @@ public:
         if(rc < 0) throw std::runtime_error(std::string("amie_b200: ")+amie_b200_last_error(ctx)) ;
         return rc ;
     }
+    // what the caller passed as Preconditionner* -> precond_kind (uploading a user diagonal first)
+    int precondKind(Preconditionner * p)
+    {
+        if(!p) return AMIE_B200_PRECOND_JACOBI ;
+        if(const Vector * d = p->diagonal())
+        {
+            if(d->size() != getForces().size()) throw std::runtime_error("amie_b200: DiagonalPreconditionner needs one entry per degree of freedom") ;
+            check(amie_b200_set_preconditioner_diagonal(device(), &(*d)[0])) ;
+        }
+        return p->kind() ;
+    }
     bool cgsolve(int maxit = -1, bool verbose = true) ;      // solvers/assembly.cpp:1829
 private:
     amie_b200_ctx * ctx = nullptr ;
@@ -107,7 +135,7 @@ struct ConjugateGradient : public LinearSolver
         if(x.size() != b.size()) x.resize(b.size(), 0.) ;
         uint64_t n = 0 ;
         int ret = assembly->check(amie_b200_pcg(c, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(),
-                                                precond ? precond->kind() : AMIE_B200_PRECOND_JACOBI, eps, maxit, nssor,
+                                                assembly->precondKind(precond), eps, maxit, nssor,
                                                 rowstart, colstart, &x[0], &n, &last_error, &last_rho)) ;
         nit = n ;
         (void)verbose ;
@@ -128,7 +156,7 @@ struct BiConjugateGradientStabilized : public LinearSolver
         x.resize(b.size(), 0.) ;
         uint64_t n = 0 ;
         int ret = assembly->check(amie_b200_bicgstab(c, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(),
-                                                     precond ? precond->kind() : AMIE_B200_PRECOND_JACOBI, eps, maxit, &x[0], &n, &last_error)) ;
+                                                     assembly->precondKind(precond), eps, maxit, &x[0], &n, &last_error)) ;
         nit = n ;
         (void)verbose ;
         return ret == 1 ;

@@ -1,6 +1,7 @@
 // amie_b200_shim.cpp -- per-Assembly device contexts for the drop-in translation units.
 #include "amie_b200_shim.h"
 #include "solvers/preconditionners.h"
+#include "solvers/inversediagonal.h"
 #include <map>
 #include <iostream>
 #include <cstdlib>
@@ -74,11 +75,31 @@ void release(Amie::Assembly * a)
     registry.erase(it) ;
 }
 
-int precond_kind(Amie::Preconditionner * p)
+int precond_kind(Amie::Preconditionner * p, const Vector ** diagonal_out)
 {
+    *diagonal_out = nullptr ;
     if(!p) return AMIE_B200_PRECOND_JACOBI ;
     if(dynamic_cast<Amie::NullPreconditionner *>(p)) return AMIE_B200_PRECOND_NULL ;
+    if(Amie::InverseDiagonal * d = dynamic_cast<Amie::InverseDiagonal *>(p)) { *diagonal_out = &d->diagonal ; return AMIE_B200_PRECOND_DIAGONAL ; }
+    if(Amie::InverseLumpedDiagonal * d = dynamic_cast<Amie::InverseLumpedDiagonal *>(p)) { *diagonal_out = &d->diagonal ; return AMIE_B200_PRECOND_DIAGONAL ; }
+    if(Amie::InverseDiagonalSquared * d = dynamic_cast<Amie::InverseDiagonalSquared *>(p)) { *diagonal_out = d->diagonal ; return AMIE_B200_PRECOND_DIAGONAL ; }
     return -1 ;
+}
+
+bool upload_diagonal(amie_b200_ctx * ctx, const Vector * diagonal, size_t ndof)
+{
+    if(!diagonal) return true ;
+    if(diagonal->size() != ndof)
+    {
+        std::cerr << "amie_b200: the preconditioner's diagonal has " << diagonal->size() << " entries for " << ndof << " degrees of freedom" << std::endl ;
+        return false ;
+    }
+    if(amie_b200_set_preconditioner_diagonal(ctx, &(*diagonal)[0]))
+    {
+        std::cerr << "amie_b200: set_preconditioner_diagonal: " << amie_b200_last_error(ctx) << std::endl ;
+        return false ;
+    }
+    return true ;
 }
 
 }

@@ -15,6 +15,12 @@ namespace AmieB200Shim
 // context of this assembly with the current matrix uploaded; nullptr + message on cerr if no device
 amie_b200_ctx * context_for(Amie::Assembly * a) ;
 void release(Amie::Assembly * a) ;
-// what the caller passed as Preconditionner*: AMIE_B200_PRECOND_* or -1 (not available on the device)
-int precond_kind(Amie::Preconditionner * p) ;
+// what the caller passed as Preconditionner*: AMIE_B200_PRECOND_* or -1 (not available on the device).
+// For the reference's diagonal classes (InverseDiagonal, InverseDiagonalSquared, InverseLumpedDiagonal:
+// precondition() is t = v .* diagonal, solvers/inversediagonal.cpp:44-82) *diagonal_out points at the OBJECT's own
+// vector -- it may have been built from another matrix than the one being solved -- and the kind is
+// AMIE_B200_PRECOND_DIAGONAL; pass it to upload_diagonal() once the context exists.
+int precond_kind(Amie::Preconditionner * p, const Vector ** diagonal_out) ;
+// false + message on cerr if the vector does not have one entry per degree of freedom or the upload fails
+bool upload_diagonal(amie_b200_ctx * ctx, const Vector * diagonal, size_t ndof) ;
 }

@@ -10,16 +10,19 @@ BiConjugateGradientStabilized::BiConjugateGradientStabilized(Assembly * a) :Line
 
 bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * precond, const double epsilon , const int maxit , bool verbose )
 {
-    const int kind = AmieB200Shim::precond_kind(precond) ;
+    const Vector * diagonal = nullptr ;
+    const int kind = AmieB200Shim::precond_kind(precond, &diagonal) ;
     if(kind < 0)
     {
-        std::cerr << "amie_b200: this Preconditionner type is not available on the device" << std::endl ;
+        std::cerr << "amie_b200: this Preconditionner type is not available on the device (nullptr, NullPreconditionner and the diagonal classes of solvers/inversediagonal.h are)" << std::endl ;
         return false ;
     }
     amie_b200_ctx * ctx = AmieB200Shim::context_for(assembly) ;
     if(!ctx)
         return false ;
     const Vector & b = assembly->getForces() ;
+    if(!AmieB200Shim::upload_diagonal(ctx, diagonal, b.size()))
+        return false ;
     x.resize(b.size(), 0.) ;
     uint64_t n = 0 ;
     double err = 0 ;
