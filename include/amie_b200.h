@@ -128,6 +128,24 @@ int amie_b200_bicgstab_resident(amie_b200_ctx * ctx, int precond_kind, double ep
  * milliseconds per launch (CUDA events on the launch stream) in *ms_out.                  */
 int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double * ms_out) ;
 
+/* ------------------------------------------------------------------ Assembly::cgsolve with the history in HBM
+ * cgsolve_resident = the solver part of Assembly::cgsolve (solvers/assembly.cpp:1841-1868) without host vectors:
+ *   x0 = Assembly::extrapolate(factor) (:1772-1814) from the two last solutions kept on the device
+ *        (fewer than two: the resident x as it is -- "displacements"; size changed: history cleared, x0 = 0);
+ *   ConjugateGradient::solve(x0, precond, eps, -1) with nssor / rowstart / colstart;
+ *   displacementHistory update (:1859-1868).
+ * The forces must be resident (upload_rhs / set_boundary_conditions); the solution stays in x (download_x,
+ * element_fields).  Returns 1/0 like the solver, or <0.  The reference passes factor = 1.
+ * extrapolate / push_history expose the two halves (tests; hosts that run their own solver sequence):
+ * extrapolate writes x0 into the resident x (and x0_out if not NULL), *case_out = 0 no history (x untouched),
+ * 1 extrapolated, 2 size mismatch (history cleared, x zeroed).                                                   */
+int amie_b200_cgsolve_resident(amie_b200_ctx * ctx, int precond_kind, double eps, uint64_t nssor,
+                               uint64_t rowstart, uint64_t colstart, double factor,
+                               uint64_t * nit_out, double * err_out, double * rho_out) ;
+int amie_b200_extrapolate(amie_b200_ctx * ctx, double factor, double * x0_out, int * case_out) ;
+int amie_b200_push_history(amie_b200_ctx * ctx) ;
+int amie_b200_reset_history(amie_b200_ctx * ctx) ;
+
 /* ------------------------------------------------------------------ device-side value assembly
  * The step that PRODUCES the array the solve consumes, for repeated re-solves on one topology (damage steps):
  * upload the elementary matrices that changed instead of the whole padded array.  Results are bit-identical to

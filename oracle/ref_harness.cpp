@@ -121,6 +121,26 @@ int amie_ref_precond_diagonal(int stride, uint64_t nb, const uint32_t * row_size
     return 0 ;
 }
 
+// Assembly::extrapolate(factor) (solvers/assembly.cpp:1772-1814) on a hand-filled displacementHistory {prev, back}
+// (nhist = 2) or {back} alone (nhist = 1), with `displacements` = disp (ndisp entries).  Returns the size of the
+// vector the reference returned (copied to out, which holds max(n, ndisp) doubles); back_out receives the newest
+// history vector afterwards (the reference scrubs NaNs in it) when the history survived.
+uint64_t amie_ref_extrapolate(const double * prev, const double * back, uint64_t n, int nhist, const double * disp, uint64_t ndisp,
+                              double factor, double * out, double * back_out, uint64_t * hist_size_out)
+{
+    Amie::Assembly a ;
+    if(nhist == 2) a.displacementHistory.push_back(Vector(prev, n)) ;
+    if(nhist >= 1) a.displacementHistory.push_back(Vector(back, n)) ;
+    a.displacements.resize(ndisp) ;
+    if(ndisp) std::memcpy(&a.displacements[0], disp, ndisp*sizeof(double)) ;
+    Vector r = a.extrapolate(factor) ;
+    if(r.size()) std::memcpy(out, &r[0], r.size()*sizeof(double)) ;
+    if(hist_size_out) *hist_size_out = a.displacementHistory.size() ;
+    if(back_out && a.displacementHistory.size() && a.displacementHistory.back().size() == n && n)
+        std::memcpy(back_out, &a.displacementHistory.back()[0], n*sizeof(double)) ;
+    return r.size() ;
+}
+
 int amie_ref_max_threads()
 {
 #ifdef HAVE_OPENMP

@@ -309,3 +309,30 @@ def oracle_element_fields(dim, ids, dshape, jinv, u, tensors=None, imposed_strai
                                              u64(u.size), _vp(tot), _vp(mech), _vp(sig))
     assert rc == 0
     return tot, mech, sig
+
+
+# ------------------------------------------------------------------ Assembly::extrapolate
+
+def oracle_extrapolate(prev, back, factor=1.0):
+    """(x0, back after the NaN scrub): Assembly::extrapolate for a two-vector history (oracle/amie_oracle.c)."""
+    prev = np.ascontiguousarray(prev, np.float64)
+    back = np.array(back, np.float64)
+    out = np.zeros_like(back)
+    oracle().amie_oracle_extrapolate(_vp(prev), _vp(back), u64(back.size), f64(factor), _vp(out))
+    return out, back
+
+
+def ref_extrapolate(prev, back, disp, factor=1.0, nhist=2):
+    """The real Assembly::extrapolate on a hand-filled history: (returned vector, newest history vector afterwards,
+    history size afterwards)."""
+    R = ref()
+    R.amie_ref_extrapolate.restype = u64
+    prev = np.ascontiguousarray(prev, np.float64)
+    back = np.ascontiguousarray(back, np.float64)
+    disp = np.ascontiguousarray(disp, np.float64)
+    out = np.zeros(max(back.size, disp.size, 1))
+    back_out = back.copy()
+    hs = u64()
+    n = R.amie_ref_extrapolate(_vp(prev), _vp(back), u64(back.size), int(nhist), _vp(disp), u64(disp.size), f64(factor),
+                               _vp(out), _vp(back_out), ctypes.byref(hs))
+    return out[:n].copy(), back_out, hs.value

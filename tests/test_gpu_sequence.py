@@ -1,0 +1,107 @@
+"""Assembly::cgsolve's solver part with the displacement history in HBM (SURVEY.md section 8(f) row 3,
+csrc/cgsolve.cu): extrapolation bit for bit against the oracle (pinned against the real Assembly::extrapolate,
+tests/test_oracle_sequence.py), and a sequence of load steps against the same sequence driven through the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+
+
+def device_assembly(pkg, S):
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+    asm.sync_matrix()
+    asm.upload_rhs(S.b)
+    asm.upload_x0(None)
+    return asm
+
+
+def test_extrapolate_and_history_bits(pkg, ol, systems):
+    S = systems("S2-tri", 24)
+    asm = device_assembly(pkg, S)
+    rng = np.random.default_rng(2)
+    a, b, c = rng.standard_normal(S.n), rng.standard_normal(S.n), rng.standard_normal(S.n)
+    b[3] = np.nan
+    # no history: x0 is the resident x ("displacements"), untouched
+    asm.upload_x0(a)
+    x0, case = asm.extrapolate()
+    assert case == 0 and same_bits(x0, a)
+    # first push: history = [x*0, x]  ->  x0 = x + (x - x*0)*factor
+    asm.push_history()
+    for factor in (1.0, 0.37):
+        x0, case = asm.extrapolate(factor)
+        want, _ = ol.oracle_extrapolate(a * 0., a, factor)
+        assert case == 1 and same_bits(x0, want), factor
+        asm.upload_x0(a)
+    # second push shifts: history = [a, b]; the NaN in b is scrubbed (in the history too)
+    asm.upload_x0(b)
+    asm.push_history()
+    x0, case = asm.extrapolate(1.0)
+    want, b_scrubbed = ol.oracle_extrapolate(a, b, 1.0)
+    assert case == 1 and same_bits(x0, want) and not np.isnan(x0).any()
+    asm.upload_x0(c)
+    asm.push_history()                     # history = [b scrubbed, c]
+    x0, case = asm.extrapolate(-1.5)
+    want, _ = ol.oracle_extrapolate(b_scrubbed, c, -1.5)
+    assert case == 1 and same_bits(x0, want)
+    asm.reset_history()
+    asm.upload_x0(c)
+    x0, case = asm.extrapolate()
+    assert case == 0 and same_bits(x0, c)
+    asm.close()
+
+
+def test_history_cleared_when_the_system_size_changes(pkg, ol, systems):
+    S, T = systems("S2-tri", 24), systems("S2-tri", 20)
+    asm = device_assembly(pkg, S)
+    asm.upload_x0(np.ones(S.n))
+    asm.push_history()
+    asm.push_history()
+    # a new topology with another number of dofs on the same context (Assembly re-meshed)
+    asm.coordinateIndexedMatrix = pkg.CoordinateIndexedSparseMatrix(T.row_size, T.column_index, T.stride, T.array)
+    asm.externalForces = T.b
+    asm.sync_matrix()
+    asm.upload_x0(np.full(T.n, 7.0))
+    x0, case = asm.extrapolate()
+    assert case == 2 and not x0.any()      # Vector(0): the solver starts from zeros (solvers/assembly.cpp:1781-1785)
+    x0, case = asm.extrapolate()
+    assert case == 0                       # and the history is gone
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 12), ("S2-tri", 40)])
+def test_load_steps_on_the_device_follow_the_reference_sequence(pkg, ol, systems, preset, n):
+    """Five load steps (forces scaled and perturbed, as in a loading ramp): device-resident cgsolve vs the same
+    sequence through the oracle -- x0 = extrapolate(history), CG, history update."""
+    S = systems(preset, n)
+    asm = device_assembly(pkg, S)
+    asm.nssor = 32
+    rng = np.random.default_rng(1)
+    hist = []
+    x_prev = np.zeros(0)
+    nits = []
+    for step in range(5):
+        b = S.b * (1.0 + 0.25 * step) + 1e-3 * np.abs(S.b).max() * rng.standard_normal(S.n) * (S.b != 0)
+        # reference sequence (solvers/assembly.cpp:1850-1868)
+        if len(hist) == 2:
+            x0, hist[1] = ol.oracle_extrapolate(hist[0], hist[1], 1.0)
+        else:
+            x0 = x_prev
+        ret, x_ref, info = ol.oracle_cg(S, x0=x0 if x0.size else None, nssor=32, b=b)
+        hist = [hist[1], x_ref] if len(hist) == 2 else [x_ref * 0., x_ref]
+        x_prev = x_ref
+        # device
+        asm.upload_rhs(b)
+        ok, nit, err, rho = asm.cgsolve_resident()
+        assert ok == bool(ret)
+        assert abs(int(nit) - int(info.nit)) <= 2, (step, nit, info.nit)
+        assert rel_l2(asm.download_x(), x_ref) <= 1e-8, step
+        nits.append(int(nit))
+    # the warm start is worth something: later steps take fewer iterations than the cold first one
+    assert min(nits[2:]) < nits[0], nits
+    asm.close()

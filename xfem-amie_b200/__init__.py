@@ -87,6 +87,10 @@ def lib():
         L.amie_b200_pcg_resident.argtypes = [vp, ci, f64, ci, u64, u64, u64, vp, vp, vp]
         L.amie_b200_bicgstab_resident.argtypes = [vp, ci, f64, ci, vp, vp]
         L.amie_b200_spmv_resident.argtypes = [vp, ci, ci, vp]
+        L.amie_b200_cgsolve_resident.argtypes = [vp, ci, f64, u64, u64, u64, f64, vp, vp, vp]
+        L.amie_b200_extrapolate.argtypes = [vp, f64, vp, vp]
+        L.amie_b200_push_history.argtypes = [vp]
+        L.amie_b200_reset_history.argtypes = [vp]
         L.amie_b200_get_stats.argtypes = [vp, vp]
         L.amie_b200_set_elements.argtypes = [vp, u64, ci, vp]
         L.amie_b200_update_elements.argtypes = [vp, u64, u64, vp, vp]
@@ -355,6 +359,31 @@ class Assembly:
         nit, err = u64(), f64()
         rc = self.check(lib().amie_b200_bicgstab_resident(self.ctx, precond, eps, int(maxit), ctypes.byref(nit), ctypes.byref(err)))
         return bool(rc), nit.value, err.value
+
+    # -- Assembly::cgsolve with displacementHistory in HBM
+    def cgsolve_resident(self, precond=PRECOND_JACOBI, factor=1.0):
+        """x0 = extrapolate(factor), ConjugateGradient::solve with this assembly's epsilon / nssor / rowstart /
+        colstart, history update -- all on the device (solvers/assembly.cpp:1841-1868).  (converged, nit, err, rho)."""
+        nit, err, rho = u64(), f64(), f64()
+        rc = self.check(lib().amie_b200_cgsolve_resident(self.ctx, int(precond), self.epsilon, int(self.nssor), int(self.rowstart),
+                                                         int(self.colstart), float(factor), ctypes.byref(nit), ctypes.byref(err),
+                                                         ctypes.byref(rho)))
+        return bool(rc), nit.value, err.value, rho.value
+
+    def extrapolate(self, factor=1.0):
+        """Assembly::extrapolate (solvers/assembly.cpp:1772-1814) into the resident x: (x0, case) with case 0 = no
+        history (x as it was), 1 = extrapolated, 2 = size mismatch (history cleared, zeros)."""
+        x0 = np.zeros(self.stats().ndof)
+        case = ctypes.c_int()
+        self.check(lib().amie_b200_extrapolate(self.ctx, float(factor), _ptr(x0), ctypes.byref(case)))
+        return x0, case.value
+
+    def push_history(self):
+        """The displacementHistory update of cgsolve (:1859-1868) with the resident x as `displacements`."""
+        self.check(lib().amie_b200_push_history(self.ctx))
+
+    def reset_history(self):
+        self.check(lib().amie_b200_reset_history(self.ctx))
 
     def spmv_resident(self, reps=10, variant=0):
         ms = f64()

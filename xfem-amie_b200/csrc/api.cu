@@ -220,6 +220,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     if(ctx->graph_bicg.exec) cudaGraphExecDestroy(ctx->graph_bicg.exec) ;
     ctx_free_matrix(ctx) ;
     free_vectors(ctx) ;
+    history_destroy(ctx) ;
     dfree(ctx->st) ; dfree(ctx->partials) ; dfree(ctx->flag) ;
     if(ctx->st_host) cudaFreeHost(ctx->st_host) ;
     if(ctx->partials_host) cudaFreeHost(ctx->partials_host) ;

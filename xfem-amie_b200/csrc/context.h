@@ -40,6 +40,11 @@ struct amie_b200_ctx
     double * xc = nullptr, * rc = nullptr, * xmin = nullptr ;
     double * w[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr} ;   // BiCGStab work (lazy)
 
+    // Assembly::displacementHistory in HBM (cgsolve.cu): [0] older, [1] newest; count is 0 or 2 like the reference's
+    double * hist[2] = {nullptr, nullptr} ;
+    int hist_count = 0 ;
+    uint64_t hist_n = 0 ;
+
     KrylovState * st = nullptr ;         // device
     KrylovState * st_host = nullptr ;    // pinned, 4 slots
     double * partials = nullptr ;        // device, 4*AMIE_MAX_PARTIALS
@@ -84,6 +89,7 @@ inline double wall_now()
 // internal entry points shared between translation units
 void assembly_map_destroy(amie_b200_ctx * ctx) ;          // assemble.cu
 void field_map_destroy(amie_b200_ctx * ctx) ;             // fields.cu
+void history_destroy(amie_b200_ctx * ctx) ;               // cgsolve.cu
 void ctx_free_matrix(amie_b200_ctx * ctx) ;               // api.cu: matrix arrays + everything tied to the topology
 int ctx_alloc_vectors(amie_b200_ctx * ctx) ;
 int ctx_ensure_bicg_vectors(amie_b200_ctx * ctx) ;
