@@ -8,6 +8,9 @@
 //
 //   amie_e2e_* 2d <sampling> <out.bin> [dump.bin]   plain-elastic twin of examples/main_tension_benchmark.cpp:119-134
 //   amie_e2e_* 3d|3di <sampling> <out.bin> [dump.bin]   S1 sphere-in-cube of examples/main_3d_benchmark.cpp:184-257 (gridsize 20)
+//   amie_e2e_* 2dst <sampling> <out.bin>            examples/main_tension_benchmark.cpp --space-time (:96-157) with its default
+//                                                   parameters: notched space-time damage sample, first step + 3 load steps;
+//                                                   the solver sees rowstart = colstart > 0 (space-time planes)
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -30,6 +33,9 @@
 #include "features/inclusion3d.h"
 #include "physics/stiffness.h"
 #include "physics/stiffness_with_imposed_deformation.h"
+#include "physics/viscoelasticity_and_fracture.h"
+#include "physics/damagemodels/spacetimeisotropiclineardamage.h"
+#include "physics/fracturecriteria/maxstrain.h"
 #include "utilities/tensor.h"
 #include <cstdio>
 #include <cstring>
@@ -192,7 +198,39 @@ int main(int argc, char ** argv)
     if(argc < 4) { fprintf(stderr, "usage: %s 2d|3d <sampling> <out.bin> [dump.bin]\n", argv[0]) ; return 2 ; }
     const std::string mode = argv[1] ;
     const int sampling = atoi(argv[2]) ;
-    if(mode == "2d")
+    if(mode == "2dst")
+    {
+        const double yieldstrain = 0.0005, maxstrain = 0.0001, young = 10e9, radius = 0.01 ;     // the parser defaults (:45-50)
+        RectangularFeature sample(nullptr, 0.2, 0.1, 0, 0) ;
+        Matrix stiffness = Stiffness(young, 0.2).param ;
+        SpaceTimeNonLocalLinearSofteningMaximumStrain * fracST = new SpaceTimeNonLocalLinearSofteningMaximumStrain(maxstrain, maxstrain*young, yieldstrain) ;
+        fracST->setMaterialCharacteristicRadius(radius) ;
+        SpaceTimeIsotropicLinearDamage * damST = new SpaceTimeIsotropicLinearDamage(1.) ;
+        sample.setBehaviour(new ViscoelasticityAndFracture(PURE_ELASTICITY, stiffness, fracST, damST)) ;
+        FeatureTree F(&sample) ;
+        F.setSamplingNumber(sampling) ;
+        F.setMaxIterationsPerStep(20000) ;
+        F.setMinDeltaTime(1e-9) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, LEFT_AFTER)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM_AFTER)) ;
+        RectangularFeature * notch = new RectangularFeature(nullptr, 0.002, 0.04, 0., 0.05) ;
+        notch->setBehaviour(new VoidForm()) ;
+        F.addFeature(&sample, notch) ;
+        F.setSamplingFactor(notch, 1.5) ;
+        F.step() ;
+        F.getAssembly()->setRemoveZeroOnlyLines(false) ;
+        BoundingBoxDefinedBoundaryCondition * disp = new BoundingBoxDefinedBoundaryCondition(SET_ALONG_XI, RIGHT_AFTER, 0.) ;
+        F.addBoundaryCondition(disp) ;
+        for(size_t i = 0 ; i < 3 ; i++)
+        {
+            disp->setData((i+1)*0.0000001) ;
+            F.step() ;
+        }
+        write_vec(argv[3], F.getDisplacements()) ;
+        if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
+        fprintf(stderr, "2dst: rowstart %zu colstart %zu\n", (size_t)F.getAssembly()->rowstart, (size_t)F.getAssembly()->colstart) ;
+    }
+    else if(mode == "2d")
     {
         RectangularFeature sample(0.2, 0.1, 0., 0.) ;
         sample.setBehaviour(new Stiffness(10e9, 0.2)) ;

@@ -105,3 +105,36 @@ def test_load_steps_on_the_device_follow_the_reference_sequence(pkg, ol, systems
     # the warm start is worth something: later steps take fewer iterations than the cold first one
     assert min(nits[2:]) < nits[0], nits
     asm.close()
+
+
+def test_space_time_tension_benchmark_through_featuretree(tmp_path):
+    """BASELINE.json configs[0] in the form the reference can run (SURVEY.md section 8 config map, row 1):
+    examples/main_tension_benchmark.cpp --space-time, sampling 16 -- a notched space-time damage sample whose
+    solves carry rowstart = colstart > 0 -- through an UNMODIFIED FeatureTree, first step + three load steps, once
+    with the reference solvers and once with the drop-in translation units (oracle/e2e_harness.cpp, mode 2dst)."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exes = [os.path.join(root, "oracle", "_ref", n) for n in ("amie_e2e_ref", "amie_e2e_b200")]
+    if not all(os.path.exists(e) for e in exes):
+        pytest.skip("oracle/_ref e2e binaries not prebuilt (no /root/reference at build time)")
+    res = []
+    for exe in exes:
+        out = os.path.join(str(tmp_path), os.path.basename(exe) + ".bin")
+        p = subprocess.run([exe, "2dst", "16", out], cwd=str(tmp_path), capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert p.returncode == 0, p.stderr[-2000:]
+        cg = [int(m) for m in re.findall(r"CG \d+ converged after (\d+) iterations", p.stderr)]
+        bi = [int(m) for m in re.findall(r"BiCGStab \d+ converged after (\d+) iterations", p.stderr)]
+        rs = re.search(r"2dst: rowstart (\d+) colstart (\d+)", p.stderr)
+        res.append((np.fromfile(out, np.float64, offset=8), cg, bi, rs, p.stderr))
+    (u_ref, cg_ref, bi_ref, rs_ref, _), (u_gpu, cg_gpu, bi_gpu, rs_gpu, log) = res
+    assert "amie_b200:" not in log, log[-1500:]
+    assert rs_ref and int(rs_ref.group(1)) > 0 and rs_ref.group(0) == rs_gpu.group(0)
+    assert len(cg_ref) == len(cg_gpu) >= 6 and len(bi_ref) == len(bi_gpu) >= 3
+    for a, b in zip(cg_ref, cg_gpu):
+        assert abs(a - b) <= 2, (cg_ref, cg_gpu)
+    err = rel_l2(u_gpu, u_ref)
+    print(f"e2e 2dst-16: {u_ref.size} DOF, rowstart {rs_ref.group(1)}, CG {cg_ref} vs {cg_gpu}, BiCGStab {bi_ref} vs {bi_gpu}, rel-L2 {err:.3e}")
+    assert u_ref.size == u_gpu.size and err <= 1e-8, err
