@@ -232,6 +232,9 @@ typedef struct amie_b200_stats
     uint64_t element_blocks ;        /* n_elem * npe^2 elementary blocks held on the device                   */
     double   fields_ms ;             /* last element_fields kernel (device time)                              */
     uint64_t field_elements ;        /* elements held for field recovery                                      */
+    uint64_t early_return ;          /* 1: the last solve returned before its loop -- where the reference prints    */
+                                     /* its "homogeneous" line (conjugategradient.cpp:74-78) or nothing at all      */
+                                     /* (biconjugategradientstabilized.cpp:43-44, :57-63) instead of "converged"    */
 } amie_b200_stats ;
 int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 

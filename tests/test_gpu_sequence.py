@@ -138,3 +138,22 @@ def test_space_time_tension_benchmark_through_featuretree(tmp_path):
     err = rel_l2(u_gpu, u_ref)
     print(f"e2e 2dst-16: {u_ref.size} DOF, rowstart {rs_ref.group(1)}, CG {cg_ref} vs {cg_gpu}, BiCGStab {bi_ref} vs {bi_gpu}, rel-L2 {err:.3e}")
     assert u_ref.size == u_gpu.size and err <= 1e-8, err
+
+
+def test_early_returns_are_flagged_for_the_shim(pkg, systems):
+    """Where the reference returns before its loop it prints "homogeneous" (CG) or nothing (BiCGStab) instead of
+    "converged after": the stats carry that so the drop-in TUs print the same lines."""
+    S = systems("S3-hex", 12)
+    asm = device_assembly(pkg, S)
+    ok, nit, err, rho = asm.pcg_resident(nssor=32)
+    assert ok and nit > 0 and asm.stats().early_return == 0
+    asm.upload_rhs(np.zeros(S.n))
+    asm.upload_x0(None)
+    ok, nit, err, rho = asm.pcg_resident(nssor=32)
+    assert ok and nit == 0 and asm.stats().early_return == 1
+    ok, nit, err = asm.bicgstab_resident()
+    assert ok and nit == 0 and asm.stats().early_return == 1
+    asm.upload_rhs(S.b)
+    ok, nit, err = asm.bicgstab_resident()
+    assert ok and nit > 0 and asm.stats().early_return == 0
+    asm.close()

@@ -45,7 +45,7 @@ class Stats(ctypes.Structure):
                 ("structure_ms", f64), ("values_ms", f64),
                 ("spmv_algorithmic_bytes", u64), ("device_bytes", u64),
                 ("elements_ms", f64), ("assemble_ms", f64), ("bc_ms", f64), ("element_blocks", u64),
-                ("fields_ms", f64), ("field_elements", u64)]
+                ("fields_ms", f64), ("field_elements", u64), ("early_return", u64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

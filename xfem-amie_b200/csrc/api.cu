@@ -135,6 +135,7 @@ void ctx_reset_solve_stats(amie_b200_ctx * ctx)
     ctx->stats.iterations = ctx->stats.restarts = 0 ;
     ctx->stats.spmv_ms_total = 0. ; ctx->stats.spmv_timed = 0 ;
     ctx->stats.solve_ms = 0. ;
+    ctx->stats.early_return = 0 ;
     ctx->ev_used = 0 ;
 }
 

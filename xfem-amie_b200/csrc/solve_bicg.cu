@@ -107,7 +107,7 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     if((rc = after_reduce(ctx, FIN_STORE))) return rc ;
     if((rc = ctx_sync_state(ctx, 2))) return rc ;
     double rho = ctx->st_host[2].dot[0] ;
-    if(std::fabs(rho) < vepsilon*vepsilon) return finish(1) ;                       // :43-44
+    if(std::fabs(rho) < vepsilon*vepsilon) { ctx->stats.early_return = 1 ; return finish(1) ; }   // :43-44 (no cerr line)
 
     // :46-48  p = r ; p_ = P(p)
     CUDA_TRY(ctx, cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, ctx->stream)) ;
@@ -160,6 +160,7 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
             k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;
             ctx->stats.kernel_launches++ ;
             if((rc = after_reduce(ctx, FIN_STORE))) return rc ;
+            ctx->stats.early_return = 1 ;        // :57-63 returns without a cerr line
             return finish(1) ;
         }
     }

@@ -145,6 +145,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->x, 0, vbytes, ctx->stream)) ;
         if(ctx->opt_verbose) fprintf(stderr, "\n CG %llu homogeneous. %g\n", (unsigned long long)N, bmax) ;
+        ctx->stats.early_return = 1 ;
         return finish(1) ;
     }
     // :80-90

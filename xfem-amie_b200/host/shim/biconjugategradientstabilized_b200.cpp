@@ -32,6 +32,9 @@ bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * pr
         std::cerr << "amie_b200: bicgstab: " << amie_b200_last_error(ctx) << std::endl ;
         return false ;
     }
+    amie_b200_stats st ;
+    if(ret == 1 && amie_b200_get_stats(ctx, &st) == 0 && st.early_return)
+        return true ;               // the reference returns from :43-44 / :57-63 without a cerr line
     if(verbose)
     {
         if(ret)

@@ -49,6 +49,13 @@ bool ConjugateGradient::solve(const Vector &x0, Preconditionner * precond, const
         std::cerr << "amie_b200: pcg: " << amie_b200_last_error(ctx) << std::endl ;
         return false ;
     }
+    amie_b200_stats st ;
+    if(ret == 1 && amie_b200_get_stats(ctx, &st) == 0 && st.early_return)
+    {
+        // conjugategradient.cpp:74-78
+        std::cerr << "\n CG "<< x.size() << " homogeneous. " << std::abs(b).max() << std::endl ;
+        return true ;
+    }
     if(ret)
         std::cerr << "\n CG " << x.size() << " converged after " << nit << " iterations. Error : " << err << ", last rho = " << rho << ", max : "  << x.max() << ", min : "  << x.min() << std::endl ;
     else
