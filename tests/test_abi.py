@@ -65,3 +65,37 @@ def test_nccl_load_order_keeps_torch_importable():
         "print('ok')\n" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_ctypes_bindings_match_header_prototypes(pkg):
+    """Every prototype of include/amie_b200.h is bound in the Python mirror with the same number of parameters and
+    the same scalar/pointer kinds (a mismatch would corrupt the call silently)."""
+    txt = open(os.path.join(ROOT, "include", "amie_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    L = pkg.lib()
+    protos = re.findall(r"\b(amie_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt)
+    assert len(protos) >= 45
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_uint64: "u64",
+             ctypes.c_int64: "i64", ctypes.c_double: "f64"}
+    for name, params in protos:
+        params = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        want = []
+        for p in params:
+            if "*" in p:
+                want.append("ptr")
+            elif p.startswith("uint64_t"):
+                want.append("u64")
+            elif p.startswith("int64_t"):
+                want.append("i64")
+            elif p.startswith("double"):
+                want.append("f64")
+            elif p.startswith("int"):
+                want.append("int")
+            else:
+                raise AssertionError(f"{name}: unrecognised parameter {p!r}")
+        fn = getattr(L, name)
+        if not want:
+            continue
+        assert fn.argtypes is not None, f"{name} has no argtypes in the mirror"
+        got = [kinds[t] for t in fn.argtypes]
+        assert got == want, (name, got, want)
