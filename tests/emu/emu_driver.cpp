@@ -1,0 +1,133 @@
+// emu_driver.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_emu.h).  C entry points that run the product's kernel sources
+// on the host in the launch sequences of the C-ABI functions they belong to (assemble.cu, fields.cu, cgsolve.cu,
+// api.cu: ctx_ensure_dinv / set_values).  The grids are small on purpose: every grid-stride loop wraps many times.
+#include "cuda_emu.h"
+#include "kernels_setup.cuh"
+#include "kernels_assemble.cuh"
+#include "kernels_fields.cuh"
+#include "kernels_history.cuh"
+#include <string.h>
+
+static const unsigned GRID = 3, BLOCK = 64 ;
+
+static std::vector<uint32_t> rowptr_of(uint64_t nb, const uint32_t * row_size)
+{
+    std::vector<uint32_t> rp(nb+1, 0) ;
+    for(uint64_t i = 0 ; i < nb ; i++) rp[i+1] = rp[i]+row_size[i] ;
+    return rp ;
+}
+
+#define BY_STRIDE(S, CALL) switch(S) { case 1: { constexpr int N = 1 ; CALL ; } break ; case 2: { constexpr int N = 2 ; CALL ; } break ; \
+    case 3: { constexpr int N = 3 ; CALL ; } break ; case 4: { constexpr int N = 4 ; CALL ; } break ; case 6: { constexpr int N = 6 ; CALL ; } break ; default: return -5 ; }
+
+extern "C" {
+
+// set_values: K-Repack (padded reference layout -> compact), strides 1 and 3; the other strides carry no pad
+int emu_repack(int stride, const double * padded, double * compact, uint64_t nblocks)
+{
+    if(stride == 3)      emu_launch(GRID, BLOCK, [&]() { k_repack<3>(padded, compact, nblocks) ; }) ;
+    else if(stride == 1) emu_launch(GRID, BLOCK, [&]() { k_repack<1>(padded, compact, nblocks) ; }) ;
+    else memcpy(compact, padded, nblocks*stride*stride*sizeof(double)) ;
+    return 0 ;
+}
+
+// ctx_ensure_dinv: kind 0 InverseDiagonal, 2 InverseDiagonalSquared, 3 InverseLumpedDiagonal
+int emu_precond_diagonal(int kind, int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col,
+                         const double * vals, double * d)
+{
+    std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
+    if(kind == 0)      { BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_inverse_diagonal<N>(rp.data(), col, vals, 0u, nb, d) ; })) }
+    else if(kind == 2) { BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_inverse_diagonal_squared<N>(rp.data(), col, vals, nb, d) ; })) }
+    else if(kind == 3) { BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_inverse_lumped_diagonal<N>(rp.data(), col, vals, nb, d) ; })) }
+    else return -2 ;
+    return 0 ;
+}
+
+// set_elements + update_elements + assemble (assemble.cu).  vals (compact) is input and output: with all == 0 only the
+// stored blocks touched by elements [mark_first, mark_first+mark_count) are re-accumulated (k_mark_dirty), like an
+// incremental damage step.  Returns 0, 1 (node id out of range), 2 (pair outside the pattern).
+int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
+                 uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
+                 int all, uint64_t mark_first, uint64_t mark_count, double * vals)
+{
+    std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
+    const uint64_t nsrc = n_elem*(uint64_t)npe*npe ;
+    const uint32_t pp = (uint32_t)(npe*npe) ;
+    std::vector<uint32_t> dest(nsrc ? nsrc : 1), count(nnzb+1, 0), cptr(nnzb+1, 0) ;
+    int flag = 0 ;
+    emu_launch(GRID, BLOCK, [&]() { k_map_dest(rp.data(), col, (uint32_t)nb, ids, nsrc, npe, dest.data(), count.data(), &flag) ; }) ;
+    if(flag) return flag ;
+    for(uint64_t k = 0 ; k < nnzb ; k++) cptr[k+1] = cptr[k]+count[k] ;          // cub::DeviceScan::ExclusiveSum
+    std::vector<uint32_t> csrc(cptr[nnzb] ? cptr[nnzb] : 1) ;
+    std::fill(count.begin(), count.end(), 0u) ;
+    // the device fills the lists in arbitrary order; scramble the order here too (blocks visited backwards)
+    gridDim.x = GRID ; blockDim.x = BLOCK ;
+    for(int b = (int)GRID-1 ; b >= 0 ; b--)
+        for(unsigned t = 0 ; t < BLOCK ; t++)
+        {
+            blockIdx.x = (unsigned)b ; threadIdx.x = t ;
+            k_map_fill(dest.data(), nsrc, cptr.data(), count.data(), csrc.data()) ;
+        }
+    emu_launch(GRID, BLOCK, [&]() { k_map_sort(cptr.data(), csrc.data(), nnzb) ; }) ;
+    std::vector<unsigned char> dirty(nnzb ? nnzb : 1, 0) ;
+    if(!all)
+        emu_launch(GRID, BLOCK, [&]() { k_mark_dirty(dest.data(), mark_first*pp, (mark_first+mark_count)*pp, dirty.data()) ; }) ;
+    const uint64_t nent = nnzb*(uint64_t)stride*stride ;
+    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_assemble_gather<N*N>(cptr.data(), csrc.data(), ke, scales, pp, dirty.data(), all, vals, nent) ; }))
+    emu_launch(GRID, BLOCK, [&]() { k_clear_dirty(dirty.data(), nnzb) ; }) ;
+    for(uint64_t k = 0 ; k < nnzb ; k++) if(dirty[k]) return -1 ;
+    return 0 ;
+}
+
+// set_boundary_conditions (assemble.cu): masks, then the row-owned elimination; dirty_out (nnzb, may be NULL) receives
+// the stored blocks the elimination touched
+int emu_dirichlet(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
+                  double * vals, double * forces, double * natural, const double * add_to_forces,
+                  uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
+{
+    std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
+    std::vector<unsigned char> fixmask(nb ? nb : 1, 0), forcemask(nb ? nb : 1, 0) ;
+    if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask(fix_ids, nfix, stride, fixmask.data()) ; }) ;
+    if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask(force_ids, nforce, stride, forcemask.data()) ; }) ;
+    (void)nnzb ;
+    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N>(rp.data(), col, nb, vals, forces, natural, add_to_forces,
+                                                                       fixmask.data(), fix_ids, fix_values, (uint32_t)nfix,
+                                                                       forcemask.data(), force_ids, force_values, (uint32_t)nforce, dirty_out) ; }))
+    return 0 ;
+}
+
+// set_element_kinematics + element_fields (fields.cu)
+int emu_element_fields(int dim, uint64_t n_elem, int npe, const uint32_t * ids, const double * dshape, const double * jinv,
+                       const double * tensors, const double * istrain, const double * istress, const uint32_t * tensor_of_elem,
+                       const double * u, uint64_t n_u, double * total, double * mech, double * stress)
+{
+    std::vector<uint32_t> ids_t(std::max<uint64_t>(1, n_elem*npe)) ;
+    std::vector<double> ds_t(std::max<uint64_t>(1, n_elem*npe*dim)), ji_t(std::max<uint64_t>(1, n_elem*dim*dim)) ;
+    emu_launch(GRID, BLOCK, [&]() { k_to_component_major<uint32_t>(ids, ids_t.data(), n_elem, npe) ; }) ;
+    emu_launch(GRID, BLOCK, [&]() { k_to_component_major<double>(dshape, ds_t.data(), n_elem, npe*dim) ; }) ;
+    emu_launch(GRID, BLOCK, [&]() { k_to_component_major<double>(jinv, ji_t.data(), n_elem, dim*dim) ; }) ;
+    if(dim == 2)
+        emu_launch_sync(2, FIELD_THREADS, [&]() { k_element_fields<2>(ids_t.data(), ds_t.data(), ji_t.data(), tensors, istrain, istress, tensor_of_elem,
+                                                                    u, n_u, n_elem, npe, total, mech, stress) ; }) ;
+    else if(dim == 3)
+        emu_launch_sync(2, FIELD_THREADS, [&]() { k_element_fields<3>(ids_t.data(), ds_t.data(), ji_t.data(), tensors, istrain, istress, tensor_of_elem,
+                                                                    u, n_u, n_elem, npe, total, mech, stress) ; }) ;
+    else return -5 ;
+    return 0 ;
+}
+
+// cgsolve.cu: Assembly::extrapolate on a two-vector history, and displacements*0.
+int emu_extrapolate(const double * prev, double * back, double * x, uint64_t n, double factor)
+{
+    emu_launch(GRID, BLOCK, [&]() { k_extrapolate(prev, back, x, n, factor) ; }) ;
+    return 0 ;
+}
+
+int emu_times_zero(const double * x, double * out, uint64_t n)
+{
+    emu_launch(GRID, BLOCK, [&]() { k_times_zero(x, out, n) ; }) ;
+    return 0 ;
+}
+
+}

@@ -344,7 +344,16 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
         // K-Repack: stream the padded array through a device staging buffer, 12 -> 9 doubles per block
         const uint64_t chunk_blocks = std::min<uint64_t>(std::max<uint64_t>(ctx->nnzb, 1), (256ull << 20)/(S*cl*8)) ;
         double * stage[2] = {nullptr, nullptr} ;
-        for(int i = 0 ; i < 2 ; i++) CUDA_TRY(ctx, cudaMalloc(&stage[i], chunk_blocks*S*cl*sizeof(double))) ;
+        for(int i = 0 ; i < 2 ; i++)
+        {
+            cudaError_t e = cudaMalloc(&stage[i], chunk_blocks*S*cl*sizeof(double)) ;
+            if(e != cudaSuccess)
+            {
+                if(stage[0]) cudaFree(stage[0]) ;
+                ctx->set_error(std::string("set_values: staging buffer: ")+cudaGetErrorString(e)) ;
+                return AMIE_B200_ERR_CUDA ;
+            }
+        }
         cudaEvent_t done[2] ;
         for(int i = 0 ; i < 2 ; i++) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) ;
         int which = 0 ;

@@ -17,12 +17,11 @@
 // elimination = column indices + a per-node mask byte, values only where a fixed dof is involved.
 #include "context.h"
 #include "launch.cuh"
+#include "kernels_assemble.cuh"
 #include <algorithm>
 #include <vector>
 #include <cub/device/device_scan.cuh>
 
-#define NO_NODE 0xFFFFFFFFu
-#define NO_DEST 0xFFFFFFFFu
 
 struct AssemblyMap
 {
@@ -54,212 +53,6 @@ void assembly_map_destroy(amie_b200_ctx * ctx)
     afree(m->fixmask) ; afree(m->forcemask) ;
     delete m ;
     ctx->amap = nullptr ;
-}
-
-// ---------------------------------------------------------------------------------------------------- map build
-
-// element block (e, j, k) -> stored block (ids[j], ids[k]); counts the contributions of every stored block
-static __global__ void k_map_dest(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint32_t nb,
-                                  const uint32_t * __restrict__ ids, uint64_t nsrc, int npe,
-                                  uint32_t * __restrict__ dest_of_src, uint32_t * __restrict__ count, int * __restrict__ flag)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    const uint32_t pp = (uint32_t)(npe*npe) ;
-    for(uint64_t src = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; src < nsrc ; src += stride)
-    {
-        const uint64_t e = src/pp ;
-        const uint32_t jk = (uint32_t)(src-e*pp) ;
-        const uint32_t rj = __ldg(ids+e*npe+jk/npe), ck = __ldg(ids+e*npe+jk%npe) ;
-        uint32_t d = NO_DEST ;
-        if(rj != NO_NODE && ck != NO_NODE)
-        {
-            if(rj >= nb || ck >= nb) { *flag = 1 ; }
-            else
-            {
-                const uint32_t k1 = __ldg(rowptr+rj+1) ;
-                const uint32_t k = row_lower_bound(col, __ldg(rowptr+rj), k1, ck) ;
-                if(k < k1 && __ldg(col+k) == ck) { d = k ; atomicAdd(count+k, 1u) ; }
-                else *flag = 2 ;
-            }
-        }
-        dest_of_src[src] = d ;
-    }
-}
-
-static __global__ void k_map_fill(const uint32_t * __restrict__ dest_of_src, uint64_t nsrc, const uint32_t * __restrict__ cptr,
-                                  uint32_t * __restrict__ cursor, uint32_t * __restrict__ csrc)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t src = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; src < nsrc ; src += stride)
-    {
-        const uint32_t d = dest_of_src[src] ;
-        if(d == NO_DEST) continue ;
-        const uint32_t pos = atomicAdd(cursor+d, 1u) ;
-        csrc[__ldg(cptr+d)+pos] = (uint32_t)src ;
-    }
-}
-
-// the atomics above fill each list in arbitrary order: sort it (lists are a handful of entries long)
-static __global__ void k_map_sort(const uint32_t * __restrict__ cptr, uint32_t * __restrict__ csrc, uint64_t nnzb)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t d = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; d < nnzb ; d += stride)
-    {
-        const uint32_t p0 = cptr[d], p1 = cptr[d+1] ;
-        for(uint32_t i = p0+1 ; i < p1 ; i++)
-        {
-            const uint32_t v = csrc[i] ;
-            uint32_t j = i ;
-            while(j > p0 && csrc[j-1] > v) { csrc[j] = csrc[j-1] ; j-- ; }
-            csrc[j] = v ;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------- gather
-
-static __global__ void k_mark_dirty(const uint32_t * __restrict__ dest_of_src, uint64_t src0, uint64_t src1,
-                                    unsigned char * __restrict__ dirty)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t src = src0+(uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; src < src1 ; src += stride)
-    {
-        const uint32_t d = dest_of_src[src] ;
-        if(d != NO_DEST) dirty[d] = 1 ;
-    }
-}
-
-// one thread per stored entry: replay `y = scale*Ke - c ; t = a + y ; c = (t - a) - y ; a = t` over the block's
-// contributions in element order (solvers/assembly.cpp:685-690).  Explicit _rn intrinsics: no FMA contraction.
-template<int SS>
-static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
-                                         const double * __restrict__ ke, const double * __restrict__ scales,
-                                         uint32_t pp, unsigned char * __restrict__ dirty, int all,
-                                         double * __restrict__ vals, uint64_t nent)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t idx = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; idx < nent ; idx += stride)
-    {
-        const uint64_t d = idx/SS ;
-        const uint32_t ent = (uint32_t)(idx-d*SS) ;
-        if(!all && !dirty[d]) continue ;
-        const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
-        double a = 0., c = 0. ;
-        for(uint32_t p = p0 ; p < p1 ; p++)
-        {
-            const uint32_t src = __ldg(csrc+p) ;
-            const double sc = __ldg(scales+src/pp) ;
-            const double y = __dsub_rn(__dmul_rn(sc, ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
-            const double t = __dadd_rn(a, y) ;
-            c = __dsub_rn(__dsub_rn(t, a), y) ;
-            a = t ;
-        }
-        vals[idx] = a ;
-    }
-}
-
-static __global__ void k_clear_dirty(unsigned char * __restrict__ dirty, uint64_t n)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n ; i += stride) dirty[i] = 0 ;
-}
-
-// ---------------------------------------------------------------------------------------------------- elimination
-
-// ids ascending and unique: the first thread of every node gathers the node's bits (no atomics)
-static __global__ void k_bc_mask(const uint32_t * __restrict__ ids, uint64_t n, int S, unsigned char * __restrict__ mask)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n ; i += stride)
-    {
-        const uint32_t node = ids[i]/S ;
-        if(i && ids[i-1]/S == node) continue ;
-        unsigned int bits = 0 ;
-        for(uint64_t j = i ; j < n && ids[j]/S == node ; j++) bits |= 1u << (ids[j]-node*S) ;
-        mask[node] = (unsigned char)bits ;
-    }
-}
-
-__device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, const double * __restrict__ values,
-                                           uint32_t n, uint32_t id)
-{
-    const uint32_t k = row_lower_bound(ids, 0, n, id) ;
-    return values[k] ;
-}
-
-// One thread per scalar row (node k, component m).  It walks the row's blocks in storage order and, inside each
-// block, the multipliers of the row's node ("in line", solvers/assembly.cpp:170-207) and then those of the column's
-// node ("in block", :210-253), ascending -- the order in which the reference updates externalForces[k*S+m].
-template<int S>
-static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint64_t nb,
-                                   double * __restrict__ vals, double * __restrict__ forces, double * __restrict__ natural,
-                                   const double * __restrict__ add_to_forces,
-                                   const unsigned char * __restrict__ fixmask, const uint32_t * __restrict__ fix_ids,
-                                   const double * __restrict__ fix_values, uint32_t nfix,
-                                   const unsigned char * __restrict__ forcemask, const uint32_t * __restrict__ force_ids,
-                                   const double * __restrict__ force_values, uint32_t nforce,
-                                   unsigned char * __restrict__ dirty)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    const uint64_t nrows = nb*S ;
-    for(uint64_t row = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; row < nrows ; row += stride)
-    {
-        const uint32_t k = (uint32_t)(row/S) ;
-        const int m = (int)(row-(uint64_t)k*S) ;
-        const unsigned int rm = nfix ? fixmask[k] : 0u ;
-        double f = forces[row] ;
-        double nat = natural ? natural[row] : 0. ;
-        const uint32_t k0 = __ldg(rowptr+k), k1 = __ldg(rowptr+k+1) ;
-        for(uint32_t l = k0 ; nfix && l < k1 ; l++)
-        {
-            const uint32_t cb = __ldg(col+l) ;
-            const unsigned int cm = fixmask[cb] ;
-            if(!(rm | cm)) continue ;
-            double * B = vals+(uint64_t)l*(S*S) ;
-            if(dirty) dirty[l] = 1 ;
-            for(int n0 = 0 ; n0 < S ; n0++)                     // multipliers of the row's node
-            {
-                if(!((rm >> n0) & 1u)) continue ;
-                if(n0 == m)
-                {
-                    for(int n = 0 ; n < S ; n++) B[n*S+m] = (cb == k && n == m) ? 1. : 0. ;
-                }
-                else if(cb == k)
-                {
-                    const double v = bc_value(fix_ids, fix_values, nfix, k*S+n0) ;
-                    const double val = B[n0*S+m] ;
-                    const double prod = __dmul_rn(v, val) ;
-                    f = __dsub_rn(f, prod) ;
-                    nat = __dsub_rn(nat, prod) ;
-                    B[n0*S+m] = 0. ;
-                }
-            }
-            for(int n0 = 0 ; n0 < S ; n0++)                     // multipliers of the column's node
-            {
-                if(!((cm >> n0) & 1u)) continue ;
-                const double v = bc_value(fix_ids, fix_values, nfix, cb*S+n0) ;
-                if(cb == k && n0 == m)
-                {
-                    f = v ;
-                    for(int n = 0 ; n < S ; n++) B[n*S+m] = (n == m) ? 1. : 0. ;
-                }
-                else
-                {
-                    const double val = B[n0*S+m] ;
-                    const double prod = __dmul_rn(v, val) ;
-                    f = __dsub_rn(f, prod) ;
-                    nat = __dsub_rn(nat, prod) ;
-                    B[n0*S+m] = 0. ;
-                }
-            }
-        }
-        if(nforce && ((forcemask[k] >> m) & 1u))                // SET_FORCE_*: externalForces[id] += value (:262-268)
-            f = __dadd_rn(f, bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
-        if(add_to_forces)                                       // externalForces += addToExternalForces (:323-324)
-            f = __dadd_rn(f, ((rm >> m) & 1u) ? 0. : add_to_forces[row]) ;
-        forces[row] = f ;
-        if(natural) natural[row] = nat ;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------- API

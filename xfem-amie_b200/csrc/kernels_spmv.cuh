@@ -29,6 +29,7 @@
 #pragma once
 #include "common.cuh"
 #include "krylov_scalars.cuh"
+#include "device_utils.cuh"
 
 enum { DOT_NONE = 0, DOT_YX = 1, DOT_YY = 2, DOT_YW = 3, DOT_OMEGA = 4 } ;
 
@@ -51,23 +52,6 @@ struct SpmvArgs
     int finalize ;              // FIN_* (krylov_scalars.cuh)
     int check_stop ;
 } ;
-
-__device__ __forceinline__ double ld_stream(const double * p)
-{
-    double v ;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)) ;
-    return v ;
-}
-
-__device__ __forceinline__ uint32_t row_lower_bound(const uint32_t * col, uint32_t k0, uint32_t k1, uint32_t key)
-{
-    while(k0 < k1)
-    {
-        uint32_t mid = k0+((k1-k0) >> 1) ;
-        if(__ldg(col+mid) < key) k0 = mid+1 ; else k1 = mid ;
-    }
-    return k0 ;
-}
 
 // ---------------------------------------------------------------- stride 3 (27 active lanes of 32)
 template<int UMAX>

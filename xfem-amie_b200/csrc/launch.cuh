@@ -7,6 +7,7 @@
 #include "kernels_spmv_rt.cuh"
 #include "kernels_spmv_rt2.cuh"
 #include "kernels_vec.cuh"
+#include "kernels_setup.cuh"
 
 // persistent grids: a multiple of the SM count, never more blocks than there is work, and
 // never more than the fused reductions can hold.
