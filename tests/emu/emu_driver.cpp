@@ -48,7 +48,7 @@ int emu_precond_diagonal(int kind, int stride, uint64_t nb, const uint32_t * row
 // incremental damage step.  Returns 0, 1 (node id out of range), 2 (pair outside the pattern).
 int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
                  uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
-                 int all, uint64_t mark_first, uint64_t mark_count, double * vals)
+                 int all, uint64_t mark_first, uint64_t mark_count, int variant, double * vals)
 {
     std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
     const uint64_t nsrc = n_elem*(uint64_t)npe*npe ;
@@ -73,7 +73,17 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
     if(!all)
         emu_launch(GRID, BLOCK, [&]() { k_mark_dirty(dest.data(), mark_first*pp, (mark_first+mark_count)*pp, dirty.data()) ; }) ;
     const uint64_t nent = nnzb*(uint64_t)stride*stride ;
-    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_assemble_gather<N*N>(cptr.data(), csrc.data(), ke, scales, pp, dirty.data(), all, vals, nent) ; }))
+    if(variant == 2)
+    {
+        int pp_shift = -1 ;
+        if((pp & (pp-1)) == 0) { pp_shift = 0 ; while((1u << pp_shift) < pp) pp_shift++ ; }
+        const unsigned G = 5 ;       // groups per block: a few, so that the group-stride loop wraps many times
+        BY_STRIDE(stride, emu_launch(GRID, N*N*G, [&]() { k_assemble_gather_v2<N*N>(cptr.data(), csrc.data(), ke, scales, pp, pp_shift, dirty.data(), all, vals, (uint32_t)nnzb) ; }))
+    }
+    else
+    {
+        BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_assemble_gather<N*N>(cptr.data(), csrc.data(), ke, scales, pp, dirty.data(), all, vals, nent) ; }))
+    }
     emu_launch(GRID, BLOCK, [&]() { k_clear_dirty(dirty.data(), nnzb) ; }) ;
     for(uint64_t k = 0 ; k < nnzb ; k++) if(dirty[k]) return -1 ;
     return 0 ;
@@ -84,13 +94,23 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
 int emu_dirichlet(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
                   double * vals, double * forces, double * natural, const double * add_to_forces,
                   uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
-                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
+                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, int variant, unsigned char * dirty_out)
 {
     std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
     std::vector<unsigned char> fixmask(nb ? nb : 1, 0), forcemask(nb ? nb : 1, 0) ;
+    (void)nnzb ;
+    if(variant == 1)
+    {
+        std::vector<uint32_t> fixoff(nb ? nb : 1, 0xDEADBEEFu), forceoff(nb ? nb : 1, 0xDEADBEEFu) ;
+        if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask_offsets(fix_ids, nfix, stride, fixmask.data(), fixoff.data()) ; }) ;
+        if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask_offsets(force_ids, nforce, stride, forcemask.data(), forceoff.data()) ; }) ;
+        BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N, true>(rp.data(), col, nb, vals, forces, natural, add_to_forces,
+                                                                             fixmask.data(), fixoff.data(), fix_values, (uint32_t)nfix,
+                                                                             forcemask.data(), forceoff.data(), force_values, (uint32_t)nforce, dirty_out) ; }))
+        return 0 ;
+    }
     if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask(fix_ids, nfix, stride, fixmask.data()) ; }) ;
     if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask(force_ids, nforce, stride, forcemask.data()) ; }) ;
-    (void)nnzb ;
     BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N>(rp.data(), col, nb, vals, forces, natural, add_to_forces,
                                                                        fixmask.data(), fix_ids, fix_values, (uint32_t)nfix,
                                                                        forcemask.data(), force_ids, force_values, (uint32_t)nforce, dirty_out) ; }))

@@ -1,0 +1,81 @@
+"""Opt-in kernel variants of the assembly row (options "assemble_variant" = 2, "dirichlet_variant" = 1) must give the
+bits of the default kernels, which the parity tests pin (their logic is also checked on the CPU by
+tests/test_emu_kernels.py)."""
+import numpy as np
+import pytest
+
+from conftest import random_spd_blocks
+from test_gpu_assembly import device_array, grid_elements, load
+
+pytestmark = pytest.mark.gpu
+
+
+def variant_assembly(pkg, stride, rs, ci):
+    asm = pkg.Assembly(None, None, device=0)
+    asm.set_option("assemble_variant", 2)
+    asm.set_option("dirichlet_variant", 1)
+    asm.set_structure_only(stride, rs, ci)
+    return asm
+
+
+@pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
+def test_variants_reproduce_featuretree_matrix(pkg, ol, name):
+    G = load(name)
+    s, nb = int(G["stride"]), int(G["nb"])
+    el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
+    asm = variant_assembly(pkg, s, G["row_size"], G["column_index"])
+    asm.set_elements(el.ids)
+    asm.update_elements(0, el.ke, el.scales)
+    asm.assemble()
+    assert np.array_equal(device_array(asm), ol.oracle_assemble(s, nb, G["row_size"], G["column_index"], el))
+    asm.upload_rhs(np.zeros(nb * s))
+    asm.set_boundary_conditions(G["fix_ids"], G["fix_values"])
+    assert np.array_equal(device_array(asm), G["array_post"])
+    if bool(G["forces_comparable"]):
+        assert np.array_equal(asm.download_rhs(), G["forces_post"])
+    asm.close()
+
+
+@pytest.mark.parametrize("dims,stride,ragged", [((9, 8), 2, False), ((7, 6, 5), 3, True), ((12, 11), 1, False),
+                                                ((5, 4, 4), 4, False), ((4, 4, 3), 6, True), ((23, 19, 17), 3, False)])
+def test_assemble_variant_matches_oracle_incl_incremental(pkg, ol, dims, stride, ragged):
+    nb, el = grid_elements(ol, dims, stride, seed=sum(dims) + stride, ragged=ragged)
+    rs, ci = el.pattern(nb)
+    asm = variant_assembly(pkg, stride, rs, ci)
+    asm.set_elements(el.ids)
+    asm.update_elements(0, el.ke, el.scales)
+    asm.assemble()
+    assert np.array_equal(device_array(asm), ol.oracle_assemble(stride, nb, rs, ci, el))
+    rng = np.random.default_rng(1)
+    first, count = el.n_elem // 3, max(1, el.n_elem // 5)
+    el.ke[first:first + count] *= rng.uniform(0.1, 0.9, (count, 1, 1, 1))
+    asm.update_elements(first, el.ke[first:first + count], el.scales[first:first + count])
+    asm.assemble()
+    assert np.array_equal(device_array(asm), ol.oracle_assemble(stride, nb, rs, ci, el))
+    asm.close()
+
+
+@pytest.mark.parametrize("stride", [1, 2, 3, 4, 6])
+def test_dirichlet_variant_matches_oracle(pkg, ol, stride):
+    nb = 70
+    rs, ci, arr, b = random_spd_blocks(stride, nb, 500 + stride)
+    n = nb * stride
+    rng = np.random.default_rng(stride)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(rs, ci, stride, arr), b, device=0)
+    asm.set_option("dirichlet_variant", 1)
+    for nfix in (0, 1, n // 4, n):
+        fix = np.sort(rng.choice(n, nfix, replace=False)).astype(np.uint32)
+        fv = rng.standard_normal(nfix)
+        rest = np.setdiff1d(np.arange(n), fix)
+        frc = np.sort(rng.choice(rest, min(9, rest.size), replace=False)).astype(np.uint32)
+        frv = rng.standard_normal(frc.size)
+        nat, add = rng.standard_normal(n), rng.standard_normal(n)
+        a0, f0, n0, _ = ol.oracle_set_bcs(stride, nb, rs, ci, arr, b, fix, fv, frc, frv, nat, add)
+        asm.values_changed()
+        asm.sync_matrix()
+        asm.upload_rhs(b)
+        asm.set_boundary_conditions(fix, fv, frc, frv, add, nat)
+        assert np.array_equal(device_array(asm), a0)
+        assert np.array_equal(asm.download_rhs(), f0)
+        assert np.array_equal(nat, n0)
+    asm.close()

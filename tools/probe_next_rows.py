@@ -68,6 +68,24 @@ def assembly_row(n=64, reps=5):
                assemble_full_ms=min(full), assemble_full_gbs=alg / (min(full) * 1e-3) / 1e9,
                frac_of_peak=alg / (min(full) * 1e-3) / 1e9 / PEAK, assemble_1pct_ms=min(part),
                dirichlet_ms=asm.stats().bc_ms, set_elements_ms=asm.stats().elements_ms)
+    # the opt-in variants (same bits; csrc/kernels_assemble.cuh)
+    ref_vals = None
+    asm.update_elements(0, ke)
+    asm.assemble()
+    ref_vals = asm.download_matrix()[2]
+    asm.set_option("assemble_variant", 2)
+    v2 = []
+    for _ in range(reps):
+        asm.update_elements(0, ke)
+        asm.assemble()
+        v2.append(asm.stats().assemble_ms)
+    rec["assemble_variant2_full_ms"] = min(v2)
+    rec["assemble_variant2_frac_of_peak"] = alg / (min(v2) * 1e-3) / 1e9 / PEAK
+    rec["assemble_variant2_same_bits"] = bool(np.array_equal(asm.download_matrix()[2].view(np.uint64), ref_vals.view(np.uint64)))
+    asm.set_option("dirichlet_variant", 1)
+    asm.upload_rhs(np.zeros(nb * s))
+    asm.set_boundary_conditions(fix, np.ones(fix.size))
+    rec["dirichlet_variant1_ms"] = asm.stats().bc_ms
     asm.close()
     return rec
 

@@ -251,6 +251,8 @@ int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
     else if(k == "verbose") ctx->opt_verbose = (int)value ;
     else if(k == "iters_per_batch") ctx->opt_batch = (int)value ;
     else if(k == "graph") ctx->opt_graph = (int)value ;
+    else if(k == "assemble_variant") ctx->opt_assemble_variant = (int)value ;
+    else if(k == "dirichlet_variant") ctx->opt_dirichlet_variant = (int)value ;
     else { ctx->set_error("unknown option "+k) ; return AMIE_B200_ERR_ARG ; }
     return AMIE_B200_OK ;
 }

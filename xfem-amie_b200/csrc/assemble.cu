@@ -40,6 +40,8 @@ struct AssemblyMap
     // boundary-condition scratch (sized on demand)
     unsigned char * fixmask = nullptr ; // [nb] bit n: dof n of the node is eliminated
     unsigned char * forcemask = nullptr ;
+    uint32_t * fixoff = nullptr ;       // [nb] variant 1 of the elimination: position of the node's first id in the list
+    uint32_t * forceoff = nullptr ;
     uint64_t mask_nb = 0 ;
 } ;
 
@@ -50,7 +52,7 @@ void assembly_map_destroy(amie_b200_ctx * ctx)
     AssemblyMap * m = ctx->amap ;
     if(!m) return ;
     afree(m->dest_of_src) ; afree(m->cptr) ; afree(m->csrc) ; afree(m->ke) ; afree(m->scales) ; afree(m->dirty) ;
-    afree(m->fixmask) ; afree(m->forcemask) ;
+    afree(m->fixmask) ; afree(m->forcemask) ; afree(m->fixoff) ; afree(m->forceoff) ;
     delete m ;
     ctx->amap = nullptr ;
 }
@@ -190,7 +192,15 @@ int amie_b200_assemble(amie_b200_ctx * ctx)
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     if(nent)
     {
-#define GATHER(N) k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent)
+        // variant 2: SS-thread groups, G stored blocks per block and step (kernels_assemble.cuh)
+        const uint32_t G2 = (uint32_t)(AMIE_VEC_THREADS/SS) ;
+        const int grid2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((ctx->nnzb+G2-1)/G2, (uint64_t)ctx->num_sms*8)) ;
+        int pp_shift = -1 ;
+        if((pp & (pp-1)) == 0) { pp_shift = 0 ; while((1u << pp_shift) < pp) pp_shift++ ; }
+#define GATHER(N) do { if(ctx->opt_assemble_variant == 2) \
+            k_assemble_gather_v2<N><<<grid2, N*G2, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, pp_shift, m->dirty, all, ctx->vals, (uint32_t)ctx->nnzb) ; \
+        else \
+            k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent) ; } while(0)
         switch(ctx->S)
         {
             case 1: GATHER(1) ; break ;
@@ -232,11 +242,15 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     AssemblyMap * m = ctx->amap ;
     if(m->mask_nb != ctx->nb)
     {
-        afree(m->fixmask) ; afree(m->forcemask) ;
+        afree(m->fixmask) ; afree(m->forcemask) ; afree(m->fixoff) ; afree(m->forceoff) ;
+        m->mask_nb = 0 ;
         CUDA_TRY(ctx, cudaMalloc(&m->fixmask, std::max<uint64_t>(ctx->nb, 1))) ;
         CUDA_TRY(ctx, cudaMalloc(&m->forcemask, std::max<uint64_t>(ctx->nb, 1))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->fixoff, std::max<uint64_t>(ctx->nb, 1)*sizeof(uint32_t))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->forceoff, std::max<uint64_t>(ctx->nb, 1)*sizeof(uint32_t))) ;
         m->mask_nb = ctx->nb ;
     }
+    const bool offs = ctx->opt_dirichlet_variant == 1 ;
     uint32_t * d_ids = nullptr ;
     double * d_vals = nullptr, * d_add = nullptr, * d_nat = nullptr ;
     const uint64_t nm = nfix+nforce ;
@@ -250,14 +264,16 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
         BC_TRY(cudaMemcpyAsync(d_ids, fix_ids, nfix*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals, fix_values, nfix*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemsetAsync(m->fixmask, 0, ctx->nb, ctx->stream)) ;
-        k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask) ;
+        if(offs) k_bc_mask_offsets<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask, m->fixoff) ;
+        else     k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask) ;
     }
     if(nforce)
     {
         BC_TRY(cudaMemcpyAsync(d_ids+nfix, force_ids, nforce*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals+nfix, force_values, nforce*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemsetAsync(m->forcemask, 0, ctx->nb, ctx->stream)) ;
-        k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask) ;
+        if(offs) k_bc_mask_offsets<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask, m->forceoff) ;
+        else     k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask) ;
     }
     if(add_to_forces)
     {
@@ -272,8 +288,10 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     unsigned char * dirty = (m->built && !m->all_dirty) ? m->dirty : nullptr ;
     BC_TRY(cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     const int grid = vec_grid(ctx, ctx->N) ;
-#define DIRICHLET(N) k_dirichlet<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
-        m->fixmask, d_ids, d_vals, (uint32_t)nfix, m->forcemask, d_ids+nfix, d_vals+nfix, (uint32_t)nforce, dirty)
+#define DIRICHLET(N) do { if(offs) k_dirichlet<N, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
+        m->fixmask, m->fixoff, d_vals, (uint32_t)nfix, m->forcemask, m->forceoff, d_vals+nfix, (uint32_t)nforce, dirty) ; \
+    else k_dirichlet<N, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
+        m->fixmask, d_ids, d_vals, (uint32_t)nfix, m->forcemask, d_ids+nfix, d_vals+nfix, (uint32_t)nforce, dirty) ; } while(0)
     if(ctx->N)
         switch(ctx->S)
         {

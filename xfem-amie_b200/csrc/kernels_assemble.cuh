@@ -108,6 +108,45 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
     }
 }
 
+// Variant 2 (option "assemble_variant" = 2): the same sums with cheaper index arithmetic.  ncu on the plain kernel
+// (profiles/r01c_ncu_assembly.txt) shows it issue-bound, not latency-bound: 58 % of the issue slots busy at 40 % of the
+// DRAM bandwidth, 221 warp instructions per 32 entries -- a 64-bit division by SS per entry and a division by the
+// runtime npe^2 per contribution.  Here a block is G groups of SS threads: a thread's entry (threadIdx.x % SS) and
+// group are fixed once, the stored block advances by G per step in 32-bit arithmetic, and the element of a
+// contribution is a shift when npe^2 is a power of two (linear tetrahedra and hexahedra; pp_shift < 0: divide).
+// Launch with blockDim.x == SS*G.  Per entry the additions and their order are unchanged -> same bits.
+template<int SS>
+static __global__ void k_assemble_gather_v2(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
+                                            const double * __restrict__ ke, const double * __restrict__ scales,
+                                            uint32_t pp, int pp_shift, const unsigned char * __restrict__ dirty, int all,
+                                            double * __restrict__ vals, uint32_t nnzb)
+{
+    const uint32_t G = blockDim.x/SS ;
+    const uint32_t g = threadIdx.x/SS ;
+    const uint32_t ent = threadIdx.x-g*SS ;
+    const uint32_t step = gridDim.x*G ;
+    for(uint32_t d0 = blockIdx.x*G ; d0 < nnzb ; d0 += step)      // d0 is uniform over the block: no early exit
+    {
+        const uint32_t d = d0+g ;
+        if(d < nnzb && (all || dirty[d]))
+        {
+            const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
+            double a = 0., c = 0. ;
+            for(uint32_t p = p0 ; p < p1 ; p++)
+            {
+                const uint32_t src = __ldg(csrc+p) ;
+                const uint32_t e = pp_shift >= 0 ? (src >> pp_shift) : src/pp ;
+                const double y = __dsub_rn(__dmul_rn(__ldg(scales+e), ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
+                const double t = __dadd_rn(a, y) ;
+                c = __dsub_rn(__dsub_rn(t, a), y) ;
+                a = t ;
+            }
+            vals[(uint64_t)d*SS+ent] = a ;
+        }
+        if(step > nnzb-d0) break ;                                  // d0 += step would wrap past 2^32
+    }
+}
+
 static __global__ void k_clear_dirty(unsigned char * __restrict__ dirty, uint64_t n)
 {
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
@@ -130,6 +169,34 @@ static __global__ void k_bc_mask(const uint32_t * __restrict__ ids, uint64_t n, 
     }
 }
 
+// variant 1 of the elimination: besides the mask, the position of the node's first id in the sorted list, so that the
+// value of (node, component n) is values[off[node] + popcount(mask & ((1 << n) - 1))] -- one load instead of a
+// binary search of the whole list per fixed dof met (the plain kernel spends its time in those dependent loads:
+// long_scoreboard 66 warps per issue, profiles/r01c_ncu_assembly.txt)
+static __global__ void k_bc_mask_offsets(const uint32_t * __restrict__ ids, uint64_t n, int S, unsigned char * __restrict__ mask,
+                                         uint32_t * __restrict__ off)
+{
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n ; i += stride)
+    {
+        const uint32_t node = ids[i]/S ;
+        if(i && ids[i-1]/S == node) continue ;
+        unsigned int bits = 0 ;
+        for(uint64_t j = i ; j < n && ids[j]/S == node ; j++) bits |= 1u << (ids[j]-node*S) ;
+        mask[node] = (unsigned char)bits ;
+        off[node] = (uint32_t)i ;
+    }
+}
+
+__device__ __forceinline__ double bc_value_at(const double * __restrict__ values, const uint32_t * __restrict__ off,
+                                              uint32_t node, unsigned int mask, int n)
+{
+    unsigned int below = mask & ((1u << n)-1u) ;
+    unsigned int cnt = 0 ;
+    while(below) { cnt += below & 1u ; below >>= 1 ; }
+    return values[off[node]+cnt] ;
+}
+
 __device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, const double * __restrict__ values,
                                            uint32_t n, uint32_t id)
 {
@@ -140,7 +207,8 @@ __device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, co
 // One thread per scalar row (node k, component m).  It walks the row's blocks in storage order and, inside each
 // block, the multipliers of the row's node ("in line", solvers/assembly.cpp:170-207) and then those of the column's
 // node ("in block", :210-253), ascending -- the order in which the reference updates externalForces[k*S+m].
-template<int S>
+// OFFS: fix_ids / force_ids are the per-node offsets of k_bc_mask_offsets instead of the sorted id lists (variant 1)
+template<int S, bool OFFS = false>
 static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint64_t nb,
                                    double * __restrict__ vals, double * __restrict__ forces, double * __restrict__ natural,
                                    const double * __restrict__ add_to_forces,
@@ -150,6 +218,12 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
                                    const double * __restrict__ force_values, uint32_t nforce,
                                    unsigned char * __restrict__ dirty)
 {
+    // the imposed value of dof (node, n), whose bit is set in the node's mask
+    auto fixed_value = [&](uint32_t node, unsigned int mask, int n)
+    {
+        if(OFFS) return bc_value_at(fix_values, fix_ids, node, mask, n) ;
+        return bc_value(fix_ids, fix_values, nfix, node*S+n) ;
+    } ;
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
     const uint64_t nrows = nb*S ;
     for(uint64_t row = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; row < nrows ; row += stride)
@@ -176,7 +250,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
                 }
                 else if(cb == k)
                 {
-                    const double v = bc_value(fix_ids, fix_values, nfix, k*S+n0) ;
+                    const double v = fixed_value(k, rm, n0) ;
                     const double val = B[n0*S+m] ;
                     const double prod = __dmul_rn(v, val) ;
                     f = __dsub_rn(f, prod) ;
@@ -187,7 +261,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
             for(int n0 = 0 ; n0 < S ; n0++)                     // multipliers of the column's node
             {
                 if(!((cm >> n0) & 1u)) continue ;
-                const double v = bc_value(fix_ids, fix_values, nfix, cb*S+n0) ;
+                const double v = fixed_value(cb, cm, n0) ;
                 if(cb == k && n0 == m)
                 {
                     f = v ;
@@ -204,7 +278,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
             }
         }
         if(nforce && ((forcemask[k] >> m) & 1u))                // SET_FORCE_*: externalForces[id] += value (:262-268)
-            f = __dadd_rn(f, bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
+            f = __dadd_rn(f, OFFS ? bc_value_at(force_values, force_ids, k, forcemask[k], m) : bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
         if(add_to_forces)                                       // externalForces += addToExternalForces (:323-324)
             f = __dadd_rn(f, ((rm >> m) & 1u) ? 0. : add_to_forces[row]) ;
         forces[row] = f ;
