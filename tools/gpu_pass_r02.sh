@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU pass of round 2 (ONE GPU, ~12 min): everything written after round 1's GPU budget was spent gets its first
+# run on hardware, then the probes and captures that decide which prepared variants become defaults.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_pass_r02.sh'
+mkdir -p gpurun_out
+# 1. the GPU tests that have not run on a B200 yet, one file at a time so that one failure does not hide the others
+for f in precond sequence variants recovery; do
+    timeout 400 python -m pytest tests/test_gpu_$f.py -q > gpurun_out/r02_pytest_$f.log 2>&1
+    echo "== $f: $(tail -1 gpurun_out/r02_pytest_$f.log)"
+done
+# 2. the rows next to the solve: defaults vs prepared variants (same bits, times)
+timeout 200 python tools/probe_next_rows.py > gpurun_out/r02_probe_next_rows.jsonl 2> gpurun_out/r02_probe_next_rows.err
+cat gpurun_out/r02_probe_next_rows.jsonl
+# 3. one full capture per kernel of those rows (the assembly part of the probe only: -k filters, -c counts MATCHING launches)
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_gather|k_dirichlet" -c 12 \
+    -o gpurun_out/r02_prof_assembly python tools/probe_next_rows.py assembly > gpurun_out/r02_prof_assembly.log 2>&1
+# 4. the whole suite and the default bench line
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1
+tail -3 gpurun_out/r02_pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err
+tail -c 600 gpurun_out/r02_bench_1gpu.json
