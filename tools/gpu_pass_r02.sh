@@ -12,7 +12,7 @@ done
 timeout 200 python tools/probe_next_rows.py > gpurun_out/r02_probe_next_rows.jsonl 2> gpurun_out/r02_probe_next_rows.err
 cat gpurun_out/r02_probe_next_rows.jsonl
 # 3. one full capture per kernel of those rows (the assembly part of the probe only: -k filters, -c counts MATCHING launches)
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_gather|k_dirichlet" -c 12 \
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_gather|k_dirichlet" -c 20 \
     -o gpurun_out/r02_prof_assembly python tools/probe_next_rows.py assembly > gpurun_out/r02_prof_assembly.log 2>&1
 # 4. the whole suite and the default bench line
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1
