@@ -25,6 +25,9 @@ import time
 
 import numpy as np
 
+# experiment switch read by the library at context creation (include/amie_b200.h, option "split_dot")
+SPLIT_DOT = os.environ.get("AMIE_B200_SPLIT_DOT", "0") not in ("", "0")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -288,7 +291,8 @@ def main():
             "pcg_iteration_gbs": iter_bytes * value / 1e9,
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)" if s == 3 else "k_spmv_s2<DOT_YX>",
+                         "traffic": traffic, "kernel": (("k_spmv_s3_rt<DOT_NONE> (q = A p; p.q as a separate pass: AMIE_B200_SPLIT_DOT)" if SPLIT_DOT else
+                                                          "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)") if s == 3 else "k_spmv_s2<DOT_YX>"),
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "peak_source": peak_src},
             "e2e": e2e, "cpu_baseline": cpu}

@@ -240,6 +240,8 @@ int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 
 /* option keys: "time_spmv" (0/1: record an event pair around every SpMV launch),
  * "spmv_variant" (kernel selection), "compensated" (0/1),
+ * "split_dot" (0/1: PCG's p.q as a separate streaming pass after a plain SpMV instead of the fused form; single
+ * device; same algorithm, another summation order; default from env AMIE_B200_SPLIT_DOT),
  * "iters_per_graph" (iterations captured per CUDA-graph launch), "verbose" (0/1:
  * print the reference's cerr lines), "assemble_variant" (0 | 2) and "dirichlet_variant" (0 | 1): kernel selection
  * of amie_b200_assemble / amie_b200_set_boundary_conditions (same bits, see csrc/kernels_assemble.cuh).                                                     */

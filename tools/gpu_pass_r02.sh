@@ -19,3 +19,6 @@ timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&
 tail -3 gpurun_out/r02_pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err
 tail -c 600 gpurun_out/r02_bench_1gpu.json
+# 5. A/B: p.q as its own pass after a plain SpMV (the fused form costs ~8 % of the SpMV, a pass over p and q ~2 %)
+AMIE_B200_SPLIT_DOT=1 timeout 600 python bench.py --no-cpu --no-e2e > gpurun_out/r02_bench_1gpu_split_dot.json 2> gpurun_out/r02_bench_1gpu_split_dot.err
+tail -c 600 gpurun_out/r02_bench_1gpu_split_dot.json

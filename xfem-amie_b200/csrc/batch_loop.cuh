@@ -8,6 +8,10 @@
 #pragma once
 #include "launch.cuh"
 
+// what a captured batch depends on besides the arguments checked below: the SpMV kernel selection and the shape of
+// an iteration (split_dot adds a kernel)
+static inline int graph_variant_key(const amie_b200_ctx * ctx) { return ctx->opt_variant+(ctx->opt_split_dot ? 1000 : 0) ; }
+
 template<typename QueueOne>
 static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot & slot, bool use_graph, int batch,
                                  int precond, uint64_t rowstart, uint64_t colstart, int kernels_per_iter, int spmv_per_iter,
@@ -15,7 +19,7 @@ static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot &
 {
     if(use_graph)
     {
-        const bool hit = slot.exec && slot.batch == batch && slot.precond == precond && slot.variant == ctx->opt_variant
+        const bool hit = slot.exec && slot.batch == batch && slot.precond == precond && slot.variant == graph_variant_key(ctx)
                          && slot.rowstart == rowstart && slot.colstart == colstart && slot.alloc_gen == ctx->alloc_gen ;
         if(!hit)
         {
@@ -33,7 +37,7 @@ static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot &
             e = cudaGraphInstantiate(&slot.exec, graph, 0) ;
             cudaGraphDestroy(graph) ;
             CUDA_TRY(ctx, e) ;
-            slot.batch = batch ; slot.precond = precond ; slot.variant = ctx->opt_variant ;
+            slot.batch = batch ; slot.precond = precond ; slot.variant = graph_variant_key(ctx) ;
             slot.rowstart = rowstart ; slot.colstart = colstart ; slot.alloc_gen = ctx->alloc_gen ;
         }
     }

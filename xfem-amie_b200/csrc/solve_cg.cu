@@ -90,7 +90,17 @@ void queue_iteration(const CgRun & R)
     SpmvCall c ;
     c.x = ctx->p ; c.y = ctx->q ; c.dot = DOT_YX ; c.finalize = FIN_CG_PQ ; c.check_stop = 1 ;
     c.rowstart = R.rowstart ; c.colstart = R.colstart ;
-    launch_spmv(ctx, c) ;
+    if(ctx->opt_split_dot && !ctx->dist)
+    {
+        // q = A p in the plain form, then p.q over the rows >= rowstart as a streaming pass of its own
+        c.dot = DOT_NONE ; c.finalize = FIN_STORE ;
+        launch_spmv(ctx, c) ;
+        k_dot_checked<<<vec_grid(ctx, ctx->N-R.rowstart), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->p, ctx->q, R.rowstart, ctx->N,
+                                                                                             ctx->st, ctx->partials, FIN_CG_PQ) ;
+        ctx->stats.kernel_launches++ ;
+    }
+    else
+        launch_spmv(ctx, c) ;
     launch_update(R, false) ;
 }
 
@@ -226,7 +236,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         {
             const bool graph = want_graph(ctx, iter_bytes) ;
             const int nb_iter = graph ? (ctx->opt_batch > 0 ? ctx->opt_batch : 32) : batch ;
-            if((rc = run_iteration_batches(ctx, ctx->graph_cg, graph, nb_iter, R.precond, rowstart, colstart, 3, 1,
+            if((rc = run_iteration_batches(ctx, ctx->graph_cg, graph, nb_iter, R.precond, rowstart, colstart, (ctx->opt_split_dot && !ctx->dist) ? 4 : 3, 1,
                                            [&]() { queue_iteration(R) ; }))) return rc ;
         }
         if((rc = ctx_sync_state(ctx, 2))) return rc ;
