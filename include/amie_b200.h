@@ -208,6 +208,12 @@ int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, con
                                     const uint32_t * tensor_of_elem) ;
 int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u,
                              double * total_strain_out, double * mechanical_strain_out, double * real_stress_out) ;
+/* Principal values of a field element_fields left on the device: field 0 total strain, 1 mechanical strain (both with
+ * engineering shears: toPrincipal(..., DOUBLE_OFF_DIAGONAL_VALUES)), 2 real stress (SINGLE_OFF_DIAGONAL_VALUES) --
+ * getField(PRINCIPAL_TOTAL_STRAIN_FIELD | PRINCIPAL_MECHANICAL_STRAIN_FIELD | PRINCIPAL_REAL_STRESS_FIELD),
+ * elements/integrable_entity.cpp:475-596, :1236-1262, :1505-1509.  principal_out[e*dim + i].  2D: the bits of the
+ * reference; 3D: pow / atan2 / cos / sin of the device math library (last-place differences from glibc).            */
+int amie_b200_element_principal(amie_b200_ctx * ctx, int field, double * principal_out) ;
 
 /* ------------------------------------------------------------------ statistics */
 typedef struct amie_b200_stats

@@ -28,6 +28,7 @@
  */
 #include <stdint.h>
 #include <stddef.h>
+#include <math.h>
 
 #define NO_NODE 0xFFFFFFFFu
 
@@ -94,6 +95,75 @@ int amie_oracle_element_fields(int dim, uint64_t n_elem, int npe, const uint32_t
                     s = s + C[i*nc+k]*m[k] ;                                     /* matrixops.h:555 */
                 real_stress[e*nc+i] = imposed_stress ? s-imposed_stress[ti*nc+i] : s ;   /* :1392 */
             }
+        }
+    }
+    return 0 ;
+}
+
+/* toPrincipal(stressOrStrain, composition)  (elements/integrable_entity.cpp:475-596): principal values of a stress
+ * (SINGLE_OFF_DIAGONAL_VALUES, double_offdiag = 0: getField(PRINCIPAL_REAL_STRESS_FIELD), :1505-1509) or of a strain
+ * whose shear components are engineering shears (DOUBLE_OFF_DIAGONAL_VALUES, double_offdiag = 1:
+ * PRINCIPAL_TOTAL_STRAIN_FIELD / PRINCIPAL_MECHANICAL_STRAIN_FIELD, :1236-1262).  2D: closed form (:482-498, :539-555);
+ * 3D: the trigonometric solution of the characteristic cubic (:508-529, :563-584) on
+ * makeStressOrStrainMatrix (:430-452: [0][2] = v[3], [1][2] = v[4], [0][1] = v[5]).
+ * in[e*nc + i], out[e*dim + i].  The 3D branch calls pow / atan2 / cos / sin of the C library, like the reference. */
+int amie_oracle_principal(int dim, uint64_t n_elem, const double * in, int double_offdiag, double * out)
+{
+    if(dim != 2 && dim != 3) return -1 ;
+    const double POINT_TOLERANCE = 1e-12 ;                                       /* geometry/geometry_base.h:292 */
+    for(uint64_t e = 0 ; e < n_elem ; e++)
+    {
+        if(dim == 2)
+        {
+            const double * s = in+e*3 ;
+            double * ret = out+e*2 ;
+            double trace = s[0] + s[1] ;
+            double det = double_offdiag ? s[0]*s[1] - 0.25*s[2]*s[2] : s[0]*s[1] - s[2]*s[2] ;
+            double delta = sqrt(trace*trace - 4.*det) ;
+            double angle = double_offdiag ? 0.5*atan2(0.5*s[2], s[0] - s[1]) : 0.5*atan2(s[2], s[0] - s[1]) ;
+            if(cos(angle) < 0)
+            {
+                ret[0] = (trace + delta)*.5 ;
+                ret[1] = (trace - delta)*.5 ;
+            }
+            else
+            {
+                ret[0] = (trace - delta)*.5 ;
+                ret[1] = (trace + delta)*.5 ;
+            }
+        }
+        else
+        {
+            const double * v = in+e*6 ;
+            double * ret = out+e*3 ;
+            const double m00 = v[0], m11 = v[1], m22 = v[2], m02 = v[3], m12 = v[4], m01 = v[5] ;
+            double tr = 0 ;
+            tr += m00 ; tr += m11 ; tr += m22 ;                                  /* trace(), utilities/matrixops.cpp:213-220 */
+            double trmat, detmat, m2mat ;
+            if(double_offdiag)
+            {
+                trmat = -1.*tr ;
+                detmat = -2.0*m01*m02*m12*0.125 + m00*m12*m12*0.25 + m11*m02*m02*0.25 + 0.25*m22*m01*m01 - m00*m11*m22 ;
+                m2mat = (m00*m11 + m11*m22 + m22*m00) - 0.25*m02*m02 - 0.25*m01*m01 - 0.25*m12*m12 ;
+            }
+            else
+            {
+                trmat = -tr ;
+                detmat = -2.0*m01*m02*m12 + m00*m12*m12 + m11*m02*m02 + m22*m01*m01 - m00*m11*m22 ;
+                m2mat = (m00*m11 + m11*m22 + m22*m00) - m02*m02 - m01*m01 - m12*m12 ;
+            }
+            double q = m2mat/3. - trmat*trmat/9. ;
+            double r = (trmat*m2mat - 3.*detmat)/6. - trmat*trmat*trmat/27. ;
+            double d = q*q*q + r*r ;
+            double r0 = pow(r*r - d, 1./6.) ;
+            double phi = atan2(sqrt(-1.*d), r)/3. ;
+            if(fabs(phi) < POINT_TOLERANCE) phi = 0. ;
+            if(phi < 0.) phi += 3.14159265358979323846 ;                        /* M_PI */
+            double som = r0*cos(phi) ;
+            double dif = r0*sin(phi) ;
+            ret[0] = 2.*som - trmat/3. ;
+            ret[1] = -som - trmat/3. - dif*sqrt(3.) ;
+            ret[2] = -som - trmat/3. + dif*sqrt(3.) ;
         }
     }
     return 0 ;

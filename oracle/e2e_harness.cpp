@@ -25,7 +25,8 @@
 //            jinv f64[n_elem*dim*dim] (row-major, the element's ElementState::JinvCache);
 //            tensor f64[n_elem*nc*nc] (row-major, getBehaviour()->getTensor(p)); imposed strain / stress f64[n_elem*nc] each;
 //            then the reference's own answers: TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD, REAL_STRESS_FIELD f64[n_elem*nc] each,
-//            and ElementState::getDisplacements() f64[n_elem*npe*dim] (what ElementState::step gathered from the solution)
+//            ElementState::getDisplacements() f64[n_elem*npe*dim] (what ElementState::step gathered from the solution),
+//            and PRINCIPAL_TOTAL_STRAIN_FIELD, PRINCIPAL_MECHANICAL_STRAIN_FIELD, PRINCIPAL_REAL_STRESS_FIELD f64[n_elem*dim] each
 // mode 3di = 3d with a non-zero imposed strain in the inclusion (exercises the imposed-strain/-stress terms)
 #include "features/features.h"
 #include "features/sample.h"
@@ -102,6 +103,7 @@ struct FieldDump
     uint64_t n_elem = 0, npe = 0, dim = 0, nc = 0 ;
     std::vector<uint32_t> ids ;
     std::vector<double> dshape, jinv, tensor, istrain, istress, total, mech, stress, disp ;
+    std::vector<double> ptotal, pmech, pstress ;     // PRINCIPAL_TOTAL_STRAIN / _MECHANICAL_STRAIN / _REAL_STRESS, dim values each
 } ;
 
 // every element's operands and the reference's own answers at the element centre (local coordinates)
@@ -143,6 +145,11 @@ static FieldDump collect_fields(MESH * mesh, size_t dim)
         j->getState().getField(TOTAL_STRAIN_FIELD, centre, e, true, &vm) ;
         j->getState().getField(MECHANICAL_STRAIN_FIELD, centre, em, true, &vm) ;
         j->getState().getField(REAL_STRESS_FIELD, centre, sg, true, &vm) ;
+        Vector pe(0., dim), pm(0., dim), ps(0., dim) ;
+        j->getState().getField(PRINCIPAL_TOTAL_STRAIN_FIELD, centre, pe, true, &vm) ;
+        j->getState().getField(PRINCIPAL_MECHANICAL_STRAIN_FIELD, centre, pm, true, &vm) ;
+        j->getState().getField(PRINCIPAL_REAL_STRESS_FIELD, centre, ps, true, &vm) ;
+        for(size_t a = 0 ; a < dim ; a++) { D.ptotal.push_back(pe[a]) ; D.pmech.push_back(pm[a]) ; D.pstress.push_back(ps[a]) ; }
         // the inverse Jacobian getField used: the element's cache (ElementState::JinvCache, filled at the latest by the
         // calls above; it is NOT recomputed per call -- getInverseJacobianMatrix adds the current displacements to the
         // node coordinates, elements/integrable_entity.cpp:657-667, so a fresh evaluation would differ)
@@ -166,7 +173,7 @@ static void write_fields(const char * path, const FieldDump & D)
     uint64_t h[4] = { D.n_elem, D.npe, D.dim, D.nc } ;
     fwrite(h, 8, 4, f) ;
     fwrite(D.ids.data(), 4, D.ids.size(), f) ;
-    for(const std::vector<double> * v : { &D.dshape, &D.jinv, &D.tensor, &D.istrain, &D.istress, &D.total, &D.mech, &D.stress, &D.disp })
+    for(const std::vector<double> * v : { &D.dshape, &D.jinv, &D.tensor, &D.istrain, &D.istress, &D.total, &D.mech, &D.stress, &D.disp, &D.ptotal, &D.pmech, &D.pstress })
         fwrite(v->data(), 8, v->size(), f) ;
     fclose(f) ;
 }

@@ -137,6 +137,17 @@ int emu_element_fields(int dim, uint64_t n_elem, int npe, const uint32_t * ids, 
     return 0 ;
 }
 
+// element_principal (fields.cu)
+int emu_element_principal(int dim, uint64_t n_elem, const double * in, int double_offdiag, double * out)
+{
+    if(dim == 2 && double_offdiag)  emu_launch(GRID, BLOCK, [&]() { k_element_principal<2, true>(in, out, n_elem) ; }) ;
+    else if(dim == 2)               emu_launch(GRID, BLOCK, [&]() { k_element_principal<2, false>(in, out, n_elem) ; }) ;
+    else if(dim == 3 && double_offdiag) emu_launch(GRID, BLOCK, [&]() { k_element_principal<3, true>(in, out, n_elem) ; }) ;
+    else if(dim == 3)               emu_launch(GRID, BLOCK, [&]() { k_element_principal<3, false>(in, out, n_elem) ; }) ;
+    else return -5 ;
+    return 0 ;
+}
+
 // cgsolve.cu: Assembly::extrapolate on a two-vector history, and displacements*0.
 int emu_extrapolate(const double * prev, double * back, double * x, uint64_t n, double factor)
 {

@@ -114,6 +114,14 @@ def element_fields(dim, ids, dshape, jinv, u, tensors, imposed_strain, imposed_s
     return tuple(out)
 
 
+def element_principal(dim, values, double_offdiag):
+    v = np.ascontiguousarray(values, np.float64)
+    out = np.zeros((v.shape[0], int(dim)))
+    rc = emu().emu_element_principal(int(dim), u64(v.shape[0]), _vp(v), int(bool(double_offdiag)), _vp(out))
+    assert rc == 0, rc
+    return out
+
+
 def extrapolate(prev, back, factor):
     prev = np.ascontiguousarray(prev, np.float64)
     back = np.array(back, np.float64)

@@ -4,7 +4,8 @@ container (needs oracle/_ref, built by oracle/build_ref.py); the .npz files are 
 
   AMIE-{2d-s20,3di-s400}-fields.npz : an unmodified FeatureTree run (oracle/e2e_harness.cpp; 3di = the S1
       sphere-in-cube with a non-zero imposed strain in the inclusion).  For every element, at its centre: the
-      answers ElementState::getField gave for TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD and REAL_STRESS_FIELD,
+      answers ElementState::getField gave for TOTAL_STRAIN_FIELD, MECHANICAL_STRAIN_FIELD, REAL_STRESS_FIELD and their
+      PRINCIPAL_* fields,
       and the operands it used (dof ids, shape-function derivatives, the cached inverse Jacobian, the behaviour's
       tensor and imposed strain / stress), plus the solution vector `u` the element states were stepped with.
       Tensors are stored as a table of the distinct ones + one index per element.
@@ -32,7 +33,8 @@ def read_fields(path):
     d = dict(dim=dim, ids=take((ne, npe), np.uint32), dshape=take((ne, npe, dim)), jinv=take((ne, dim, dim)))
     tensor, istrain, istress = take((ne, nc, nc)), take((ne, nc)), take((ne, nc))
     d.update(total_strain=take((ne, nc)), mechanical_strain=take((ne, nc)), real_stress=take((ne, nc)),
-             state_displacements=take((ne, npe, dim)))
+             state_displacements=take((ne, npe, dim)), principal_total_strain=take((ne, dim)),
+             principal_mechanical_strain=take((ne, dim)), principal_real_stress=take((ne, dim)))
     assert off[0] == len(raw)
     # behaviours -> table of distinct (tensor, imposed strain, imposed stress) + index per element
     key = np.concatenate([tensor.reshape(ne, -1), istrain, istress], axis=1)

@@ -311,6 +311,15 @@ def oracle_element_fields(dim, ids, dshape, jinv, u, tensors=None, imposed_strai
     return tot, mech, sig
 
 
+def oracle_principal(dim, values, double_offdiag):
+    """toPrincipal per element: values [n_elem, nc] -> [n_elem, dim] (oracle/amie_oracle_fields.c)."""
+    v = np.ascontiguousarray(values, np.float64)
+    out = np.zeros((v.shape[0], int(dim)))
+    rc = oracle().amie_oracle_principal(int(dim), u64(v.shape[0]), _vp(v), int(bool(double_offdiag)), _vp(out))
+    assert rc == 0
+    return out
+
+
 # ------------------------------------------------------------------ Assembly::extrapolate (SURVEY §8 f3)
 
 def oracle_extrapolate(prev, back, factor=1.0):

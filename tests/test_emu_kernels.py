@@ -136,6 +136,20 @@ def test_field_kernel_against_reference_fixtures(ol, name):
         assert same_bits(a, b)
 
 
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*-fields.npz"))))
+def test_principal_kernel_against_reference_fixtures(ol, name):
+    """On the host the kernel source calls the same C library as the reference: bit for bit in 2D and in 3D."""
+    g = np.load(os.path.join(GOLDEN, name))
+    dim = int(g["dim"])
+    for src, dst, dbl in (("total_strain", "principal_total_strain", 1), ("mechanical_strain", "principal_mechanical_strain", 1),
+                          ("real_stress", "principal_real_stress", 0)):
+        assert same_bits(em.element_principal(dim, g[src], dbl), g[dst]), dst
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal((777, 3 if dim == 2 else 6)) * 10.0 ** rng.integers(-3, 4, (777, 1))
+    for dbl in (0, 1):
+        assert same_bits(em.element_principal(dim, v, dbl), ol.oracle_principal(dim, v, dbl))
+
+
 def test_history_kernels_match_oracle(ol):
     rng = np.random.default_rng(0)
     n = 1234

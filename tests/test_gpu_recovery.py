@@ -59,6 +59,28 @@ def test_fields_match_reference_bits(pkg, path):
     asm.close()
 
 
+@pytest.mark.parametrize("path", FIELDS, ids=[os.path.basename(p)[:-4] for p in FIELDS])
+def test_principal_values_match_reference(pkg, path):
+    """getField(PRINCIPAL_*_FIELD): 2D has the reference's bits; 3D goes through pow / atan2 / cos / sin of the device
+    math library and is held to 1e-12 of the largest principal value of the element."""
+    g = np.load(path)
+    asm, dim = context_for(pkg, g)
+    asm.set_element_kinematics(dim, g["ids"], g["dshape"], g["jinv"])
+    asm.set_element_behaviour(g["tensors"], g["imposed_strain"], g["imposed_stress"], g["tensor_of_elem"])
+    with pytest.raises(pkg.AmieB200Error) as e:                       # nothing to take principal values of yet
+        asm.element_principal(2)
+    assert e.value.code == pkg.ERR_STATE
+    asm.element_fields(g["u"])
+    for field, key in ((0, "principal_total_strain"), (1, "principal_mechanical_strain"), (2, "principal_real_stress")):
+        got, want = asm.element_principal(field), g[key]
+        if dim == 2:
+            assert same_bits(got, want), key
+        else:
+            scale = np.abs(want).max(axis=1, keepdims=True) + 1e-300
+            assert (np.abs(got - want) <= 1e-12 * scale).all(), (key, float((np.abs(got - want) / scale).max()))
+    asm.close()
+
+
 def test_fields_per_element_behaviours_ragged_and_short_vector(pkg, ol):
     """One behaviour per element (damage-like), a random imposed stress, an unused slot, several tiles with a
     partial last one, and a displacement vector shorter than the dofs the elements reference."""

@@ -30,6 +30,18 @@ def test_oracle_fields_match_reference(ol, path):
     assert same_bits(sig, g["real_stress"])
 
 
+@pytest.mark.parametrize("path", FIELDS, ids=[os.path.basename(p)[:-4] for p in FIELDS])
+def test_oracle_principal_values_match_reference(ol, path):
+    """toPrincipal restated: against getField(PRINCIPAL_TOTAL_STRAIN | PRINCIPAL_MECHANICAL_STRAIN | PRINCIPAL_REAL_STRESS)
+    of the same FeatureTree run, bit for bit (the build container's C library serves both)."""
+    g = np.load(path)
+    dim = int(g["dim"])
+    assert same_bits(ol.oracle_principal(dim, g["total_strain"], True), g["principal_total_strain"])
+    assert same_bits(ol.oracle_principal(dim, g["mechanical_strain"], True), g["principal_mechanical_strain"])
+    assert same_bits(ol.oracle_principal(dim, g["real_stress"], False), g["principal_real_stress"])
+    assert np.count_nonzero(g["principal_real_stress"]) > g["ids"].shape[0]
+
+
 def test_oracle_fields_options(ol):
     """Per-element behaviours (no index), absent imposed terms, unused node slots and dof ids beyond the vector."""
     g = np.load([p for p in FIELDS if "3di" in p][0])

@@ -99,6 +99,7 @@ def lib():
         L.amie_b200_set_element_kinematics.argtypes = [vp, u64, ci, ci, vp, vp, vp]
         L.amie_b200_set_element_behaviour.argtypes = [vp, u64, vp, vp, vp, vp]
         L.amie_b200_element_fields.argtypes = [vp, vp, u64, vp, vp, vp]
+        L.amie_b200_element_principal.argtypes = [vp, ci, vp]
         L.amie_b200_set_option.argtypes = [vp, cp, ctypes.c_int64]
         L.amie_b200_synth_create.restype = vp
         L.amie_b200_synth_create.argtypes = [cp, ci, u64]
@@ -307,6 +308,14 @@ class Assembly:
         out = [np.zeros(self._field_shape) for _ in range(3)]
         self.check(lib().amie_b200_element_fields(self.ctx, _ptr(u), 0 if u is None else u.size, *[_ptr(o) for o in out]))
         return tuple(out)
+
+    def element_principal(self, field):
+        """Principal values of field 0 (total strain), 1 (mechanical strain) or 2 (real stress) of the last
+        element_fields(): getField(PRINCIPAL_*_FIELD), elements/integrable_entity.cpp:475-596."""
+        ne, nc = self._field_shape
+        out = np.zeros((ne, 2 if nc == 3 else 3))
+        self.check(lib().amie_b200_element_principal(self.ctx, int(field), _ptr(out)))
+        return out
 
     def stats(self):
         s = Stats()

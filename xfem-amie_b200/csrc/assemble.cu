@@ -16,7 +16,6 @@
 // Traffic: gather = element blocks once (8 s^2 B each) + their 4 B list entries + the stored blocks written once;
 // elimination = column indices + a per-node mask byte, values only where a fixed dof is involved.
 #include "context.h"
-#include "launch.cuh"
 #include "kernels_assemble.cuh"
 #include <algorithm>
 #include <vector>

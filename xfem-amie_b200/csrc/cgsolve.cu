@@ -10,7 +10,6 @@
 // term in dxxddb that is identically zero because the history never holds more than two vectors (:1859-1868 keeps
 // size 2), and the NaN scrub of the newest vector (:1793-1794).
 #include "context.h"
-#include "launch.cuh"
 #include "kernels_history.cuh"
 
 void history_destroy(amie_b200_ctx * ctx)

@@ -106,3 +106,14 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
                       uint64_t rowstart, uint64_t colstart, uint64_t * nit_out, double * err_out, double * rho_out) ;
 int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit,
                         uint64_t * nit_out, double * err_out) ;
+
+// persistent grids: a multiple of the SM count, never more blocks than there is work, and
+// never more than the fused reductions can hold.
+static inline int vec_grid(const amie_b200_ctx * ctx, uint64_t n)
+{
+    uint64_t want = (n+AMIE_VEC_THREADS-1)/AMIE_VEC_THREADS ;
+    uint64_t cap = (uint64_t)ctx->num_sms*8 ;
+    if(cap > AMIE_MAX_PARTIALS) cap = AMIE_MAX_PARTIALS ;
+    uint64_t g = want < cap ? want : cap ;
+    return (int)(g ? g : 1) ;
+}

@@ -29,7 +29,6 @@
 // of the measured copy peak), 0.83 ms with per-element behaviours = 5.0 TB/s (77 %); DRAM traffic 2.08 / 4.39 GB
 // against 1.96 / 4.19 GB algorithmic; stalls are all long_scoreboard at 50 % occupancy (56 registers).
 #include "context.h"
-#include "launch.cuh"
 #include "kernels_fields.cuh"
 #include <algorithm>
 #include <vector>
@@ -48,6 +47,8 @@ struct FieldMap
     double * istress = nullptr ;
     uint32_t * tensor_of_elem = nullptr ; // [n_elem] or nullptr (identity)
     double * out[3] = {nullptr, nullptr, nullptr} ;   // total strain, mechanical strain, real stress: [n_elem][nc]
+    double * principal = nullptr ;    // [n_elem][dim] scratch of element_principal
+    bool have_fields = false ;        // element_fields ran since the last kinematics / behaviour change
     double * u_tmp = nullptr ;        // staging for a host-supplied displacement field
     uint64_t u_tmp_len = 0 ;
     bool have_behaviour = false ;
@@ -60,7 +61,7 @@ void field_map_destroy(amie_b200_ctx * ctx)
     FieldMap * m = ctx->fmap ;
     if(!m) return ;
     ffree(m->ids) ; ffree(m->dshape) ; ffree(m->jinv) ; ffree(m->tensors) ; ffree(m->istrain) ; ffree(m->istress) ;
-    ffree(m->tensor_of_elem) ; ffree(m->u_tmp) ;
+    ffree(m->tensor_of_elem) ; ffree(m->u_tmp) ; ffree(m->principal) ;
     for(int i = 0 ; i < 3 ; i++) ffree(m->out[i]) ;
     delete m ;
     ctx->fmap = nullptr ;
@@ -158,6 +159,7 @@ int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, con
     else ffree(m->tensor_of_elem) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     m->have_behaviour = true ;
+    m->have_fields = false ;
     return AMIE_B200_OK ;
 }
 
@@ -210,8 +212,31 @@ int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b)) ;
     ctx->stats.fields_ms = ms ;
     ctx->stats.field_elements = m->n_elem ;
+    m->have_fields = true ;
     ctx->stats.h2d_bytes = h2d ;
     ctx->stats.d2h_bytes = d2h ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_element_principal(amie_b200_ctx * ctx, int field, double * principal_out)
+{
+    if(!ctx || !principal_out || field < 0 || field > 2) return AMIE_B200_ERR_ARG ;
+    FieldMap * m = ctx->fmap ;
+    if(!m || !m->have_fields) { ctx->set_error("element_principal before element_fields") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    if(!m->principal) CUDA_TRY(ctx, cudaMalloc(&m->principal, std::max<uint64_t>(1, m->n_elem*m->dim)*sizeof(double))) ;
+    if(m->n_elem)
+    {
+        const int grid = vec_grid(ctx, m->n_elem) ;
+        const bool strain = field != 2 ;           // strains carry engineering shears: DOUBLE_OFF_DIAGONAL_VALUES
+        if(m->dim == 2 && strain)       k_element_principal<2, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->out[field], m->principal, m->n_elem) ;
+        else if(m->dim == 2)            k_element_principal<2, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->out[field], m->principal, m->n_elem) ;
+        else if(strain)                 k_element_principal<3, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->out[field], m->principal, m->n_elem) ;
+        else                            k_element_principal<3, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->out[field], m->principal, m->n_elem) ;
+        CUDA_TRY(ctx, cudaGetLastError()) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(principal_out, m->principal, m->n_elem*m->dim*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
     return AMIE_B200_OK ;
 }
 

@@ -128,3 +128,72 @@ k_element_fields(const uint32_t * __restrict__ ids, const double * __restrict__ 
         }
     }
 }
+
+// toPrincipal(v, composition) per element (elements/integrable_entity.cpp:475-596): PRINCIPAL_REAL_STRESS_FIELD
+// (DOUBLE_OFFDIAG = false, :1505-1509) and PRINCIPAL_TOTAL / _MECHANICAL_STRAIN_FIELD (true: engineering shears,
+// :1236-1262) from the element-major fields k_element_fields left in HBM.  One thread per element, the reference's
+// expressions as written -- this translation unit is compiled with -fmad=false, so nothing is contracted.  2D needs
+// sqrt only in its results (same bits as the CPU); 3D goes through pow / atan2 / cos / sin, whose device versions may
+// differ from glibc's in the last place.
+template<int DIM, bool DOUBLE_OFFDIAG>
+static __global__ void k_element_principal(const double * __restrict__ in, double * __restrict__ out, uint64_t n_elem)
+{
+    constexpr int NC = DIM == 2 ? 3 : 6 ;
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    for(uint64_t e = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; e < n_elem ; e += stride)
+    {
+        const double * v = in+e*NC ;
+        double * ret = out+e*DIM ;
+        if constexpr(DIM == 2)
+        {
+            const double s0 = v[0], s1 = v[1], s2 = v[2] ;
+            const double trace = s0 + s1 ;
+            const double det = DOUBLE_OFFDIAG ? s0*s1 - 0.25*s2*s2 : s0*s1 - s2*s2 ;
+            const double delta = sqrt(trace*trace - 4.*det) ;
+            const double angle = DOUBLE_OFFDIAG ? 0.5*atan2(0.5*s2, s0 - s1) : 0.5*atan2(s2, s0 - s1) ;
+            if(cos(angle) < 0)
+            {
+                ret[0] = (trace + delta)*.5 ;
+                ret[1] = (trace - delta)*.5 ;
+            }
+            else
+            {
+                ret[0] = (trace - delta)*.5 ;
+                ret[1] = (trace + delta)*.5 ;
+            }
+        }
+        else
+        {
+            // makeStressOrStrainMatrix (:430-452)
+            const double m00 = v[0], m11 = v[1], m22 = v[2], m02 = v[3], m12 = v[4], m01 = v[5] ;
+            double tr = 0 ;
+            tr += m00 ; tr += m11 ; tr += m22 ;
+            double trmat, detmat, m2mat ;
+            if(DOUBLE_OFFDIAG)
+            {
+                trmat = -1.*tr ;
+                detmat = -2.0*m01*m02*m12*0.125 + m00*m12*m12*0.25 + m11*m02*m02*0.25 + 0.25*m22*m01*m01 - m00*m11*m22 ;
+                m2mat = (m00*m11 + m11*m22 + m22*m00) - 0.25*m02*m02 - 0.25*m01*m01 - 0.25*m12*m12 ;
+            }
+            else
+            {
+                trmat = -tr ;
+                detmat = -2.0*m01*m02*m12 + m00*m12*m12 + m11*m02*m02 + m22*m01*m01 - m00*m11*m22 ;
+                m2mat = (m00*m11 + m11*m22 + m22*m00) - m02*m02 - m01*m01 - m12*m12 ;
+            }
+            const double q = m2mat/3. - trmat*trmat/9. ;
+            const double r = (trmat*m2mat - 3.*detmat)/6. - trmat*trmat*trmat/27. ;
+            const double d = q*q*q + r*r ;
+            const double r0 = pow(r*r - d, 1./6.) ;
+            double phi = atan2(sqrt(-1.*d), r)/3. ;
+            if(fabs(phi) < 1e-12) phi = 0. ;                          // POINT_TOLERANCE, geometry/geometry_base.h:292
+            if(phi < 0.) phi += 3.14159265358979323846 ;
+            const double som = r0*cos(phi) ;
+            const double dif = r0*sin(phi) ;
+            ret[0] = 2.*som - trmat/3. ;
+            ret[1] = -som - trmat/3. - dif*sqrt(3.) ;
+            ret[2] = -som - trmat/3. + dif*sqrt(3.) ;
+        }
+    }
+}
+

@@ -9,17 +9,6 @@
 #include "kernels_vec.cuh"
 #include "kernels_setup.cuh"
 
-// persistent grids: a multiple of the SM count, never more blocks than there is work, and
-// never more than the fused reductions can hold.
-static inline int vec_grid(const amie_b200_ctx * ctx, uint64_t n)
-{
-    uint64_t want = (n+AMIE_VEC_THREADS-1)/AMIE_VEC_THREADS ;
-    uint64_t cap = (uint64_t)ctx->num_sms*8 ;
-    if(cap > AMIE_MAX_PARTIALS) cap = AMIE_MAX_PARTIALS ;
-    uint64_t g = want < cap ? want : cap ;
-    return (int)(g ? g : 1) ;
-}
-
 struct SpmvCall
 {
     const double * x = nullptr ;
