@@ -73,12 +73,20 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
     if(!all)
         emu_launch(GRID, BLOCK, [&]() { k_mark_dirty(dest.data(), mark_first*pp, (mark_first+mark_count)*pp, dirty.data()) ; }) ;
     const uint64_t nent = nnzb*(uint64_t)stride*stride ;
-    if(variant == 2)
+    if(variant == 2 || variant == 3)
     {
-        int pp_shift = -1 ;
-        if((pp & (pp-1)) == 0) { pp_shift = 0 ; while((1u << pp_shift) < pp) pp_shift++ ; }
+        std::vector<uint32_t> order ;
+        if(variant == 3)
+        {
+            // ensure_order (assemble.cu): k_list_lengths, then a stable sort of the block ids by list length, longest first
+            std::vector<uint32_t> len(nnzb ? nnzb : 1), id(nnzb ? nnzb : 1) ;
+            emu_launch(GRID, BLOCK, [&]() { k_list_lengths(cptr.data(), nnzb, len.data(), id.data()) ; }) ;
+            order.assign(id.begin(), id.begin()+nnzb) ;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len[x] > len[y] ; }) ;
+        }
+        const uint32_t * ord = variant == 3 ? order.data() : nullptr ;
         const unsigned G = 5 ;       // groups per block: a few, so that the group-stride loop wraps many times
-        BY_STRIDE(stride, emu_launch(GRID, N*N*G, [&]() { k_assemble_gather_v2<N*N>(cptr.data(), csrc.data(), ke, scales, pp, pp_shift, dirty.data(), all, vals, (uint32_t)nnzb) ; }))
+        BY_STRIDE(stride, emu_launch(GRID, N*N*G, [&]() { k_assemble_gather_v2<N*N>(cptr.data(), csrc.data(), ke, scales, pp, ord, dirty.data(), all, vals, (uint32_t)nnzb) ; }))
     }
     else
     {

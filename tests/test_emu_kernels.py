@@ -39,7 +39,7 @@ def test_preconditioner_diagonals_against_reference_fixtures(name):
         assert same_bits(em.precond_diagonal(kind, s, g["row_size"], g["column_index"], vals), g[f"diag{kind}"]), kind
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 3])
 @pytest.mark.parametrize("dims,stride,ragged", [((9, 8), 2, False), ((6, 5, 7), 3, False), ((7, 6, 5), 3, True),
                                                 ((12, 11), 1, False), ((5, 4, 4), 4, False), ((4, 4, 3), 6, True)])
 def test_assemble_kernels_match_oracle(ol, dims, stride, ragged, variant):
@@ -66,7 +66,7 @@ def test_assemble_kernels_match_oracle(ol, dims, stride, ragged, variant):
         assert rc in (0, 2)          # 2 when that pair is not in the pattern
 
 
-@pytest.mark.parametrize("variants", [(0, 0), (2, 1)])
+@pytest.mark.parametrize("variants", [(0, 0), (2, 1), (3, 1)])
 @pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
 def test_assemble_and_eliminate_reproduce_the_featuretree_matrix(ol, name, variants):
     G = np.load(os.path.join(GOLDEN, name))

@@ -1,4 +1,4 @@
-"""Opt-in kernel variants of the assembly row (options "assemble_variant" = 2, "dirichlet_variant" = 1) must give the
+"""Opt-in kernel variants of the assembly row (options "assemble_variant" = 2 | 3, "dirichlet_variant" = 1) must give the
 bits of the default kernels, which the parity tests pin (their logic is also checked on the CPU by
 tests/test_emu_kernels.py)."""
 import numpy as np
@@ -10,20 +10,21 @@ from test_gpu_assembly import device_array, grid_elements, load
 pytestmark = pytest.mark.gpu
 
 
-def variant_assembly(pkg, stride, rs, ci):
+def variant_assembly(pkg, stride, rs, ci, variant=2):
     asm = pkg.Assembly(None, None, device=0)
-    asm.set_option("assemble_variant", 2)
+    asm.set_option("assemble_variant", variant)
     asm.set_option("dirichlet_variant", 1)
     asm.set_structure_only(stride, rs, ci)
     return asm
 
 
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
-def test_variants_reproduce_featuretree_matrix(pkg, ol, name):
+def test_variants_reproduce_featuretree_matrix(pkg, ol, name, variant):
     G = load(name)
     s, nb = int(G["stride"]), int(G["nb"])
     el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
-    asm = variant_assembly(pkg, s, G["row_size"], G["column_index"])
+    asm = variant_assembly(pkg, s, G["row_size"], G["column_index"], variant)
     asm.set_elements(el.ids)
     asm.update_elements(0, el.ke, el.scales)
     asm.assemble()
@@ -38,10 +39,11 @@ def test_variants_reproduce_featuretree_matrix(pkg, ol, name):
 
 @pytest.mark.parametrize("dims,stride,ragged", [((9, 8), 2, False), ((7, 6, 5), 3, True), ((12, 11), 1, False),
                                                 ((5, 4, 4), 4, False), ((4, 4, 3), 6, True), ((23, 19, 17), 3, False)])
-def test_assemble_variant_matches_oracle_incl_incremental(pkg, ol, dims, stride, ragged):
+@pytest.mark.parametrize("variant", [2, 3])
+def test_assemble_variant_matches_oracle_incl_incremental(pkg, ol, dims, stride, ragged, variant):
     nb, el = grid_elements(ol, dims, stride, seed=sum(dims) + stride, ragged=ragged)
     rs, ci = el.pattern(nb)
-    asm = variant_assembly(pkg, stride, rs, ci)
+    asm = variant_assembly(pkg, stride, rs, ci, variant)
     asm.set_elements(el.ids)
     asm.update_elements(0, el.ke, el.scales)
     asm.assemble()

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <vector>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 
 struct AssemblyMap
@@ -30,6 +31,7 @@ struct AssemblyMap
     uint32_t * dest_of_src = nullptr ;  // [nsrc] stored block each element block lands on (NO_DEST: unused node slot)
     uint32_t * cptr = nullptr ;         // [nnzb+1] contribution lists per stored block
     uint32_t * csrc = nullptr ;         // [ncontrib] element-block indices, ascending within a list
+    uint32_t * order = nullptr ;        // [nnzb] stored blocks by list length, longest first (variant 3; built on first use)
     double * ke = nullptr ;             // [nsrc*S*S] elementary matrices (blocks column-major)
     double * scales = nullptr ;         // [n_elem]
     unsigned char * dirty = nullptr ;   // [nnzb] stored blocks to re-accumulate at the next assemble
@@ -50,7 +52,7 @@ void assembly_map_destroy(amie_b200_ctx * ctx)
 {
     AssemblyMap * m = ctx->amap ;
     if(!m) return ;
-    afree(m->dest_of_src) ; afree(m->cptr) ; afree(m->csrc) ; afree(m->ke) ; afree(m->scales) ; afree(m->dirty) ;
+    afree(m->dest_of_src) ; afree(m->cptr) ; afree(m->csrc) ; afree(m->order) ; afree(m->ke) ; afree(m->scales) ; afree(m->dirty) ;
     afree(m->fixmask) ; afree(m->forcemask) ; afree(m->fixoff) ; afree(m->forceoff) ;
     delete m ;
     ctx->amap = nullptr ;
@@ -70,6 +72,33 @@ static bool ascending_unique(const uint32_t * ids, uint64_t n, uint64_t limit)
     for(uint64_t i = 0 ; i < n ; i++)
         if(ids[i] >= limit || (i && ids[i-1] >= ids[i])) return false ;
     return true ;
+}
+
+// variant 3: the visiting order of the stored blocks, by contribution-list length (descending, stable)
+static int ensure_order(amie_b200_ctx * ctx, AssemblyMap * m)
+{
+    if(m->order || !ctx->nnzb) return AMIE_B200_OK ;
+    const uint64_t n = ctx->nnzb ;
+    uint32_t * len = nullptr, * len_sorted = nullptr, * id = nullptr ;
+    void * tmp = nullptr ;
+    size_t tmp_bytes = 0 ;
+    auto cleanup = [&]() { afree(len) ; afree(len_sorted) ; afree(id) ; if(tmp) cudaFree(tmp) ; tmp = nullptr ; } ;
+#define ORD_TRY(expr) do { cudaError_t _e = (expr) ; if(_e != cudaSuccess) { cleanup() ; afree(m->order) ; \
+        ctx->set_error(std::string(#expr)+": "+cudaGetErrorString(_e)) ; return AMIE_B200_ERR_CUDA ; } } while(0)
+    ORD_TRY(cudaMalloc(&len, n*sizeof(uint32_t))) ;
+    ORD_TRY(cudaMalloc(&len_sorted, n*sizeof(uint32_t))) ;
+    ORD_TRY(cudaMalloc(&id, n*sizeof(uint32_t))) ;
+    ORD_TRY(cudaMalloc(&m->order, n*sizeof(uint32_t))) ;
+    k_list_lengths<<<vec_grid(ctx, n), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, n, len, id) ;
+    ORD_TRY(cudaGetLastError()) ;
+    // lists are a handful of entries long: 16 key bits are plenty, but a list may in principle be longer -> all 32
+    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len, len_sorted, id, m->order, (int)n, 0, 32, ctx->stream)) ;
+    ORD_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16))) ;
+    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len, len_sorted, id, m->order, (int)n, 0, 32, ctx->stream)) ;
+    ORD_TRY(cudaStreamSynchronize(ctx->stream)) ;
+#undef ORD_TRY
+    cleanup() ;
+    return AMIE_B200_OK ;
 }
 
 extern "C" {
@@ -191,13 +220,14 @@ int amie_b200_assemble(amie_b200_ctx * ctx)
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     if(nent)
     {
-        // variant 2: SS-thread groups, G stored blocks per block and step (kernels_assemble.cuh)
+        // variants 2 / 3: SS-thread groups, G stored blocks per block and step; 3 visits them by list length (kernels_assemble.cuh)
+        const int variant = ctx->opt_assemble_variant ;
         const uint32_t G2 = (uint32_t)(AMIE_VEC_THREADS/SS) ;
         const int grid2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((ctx->nnzb+G2-1)/G2, (uint64_t)ctx->num_sms*8)) ;
-        int pp_shift = -1 ;
-        if((pp & (pp-1)) == 0) { pp_shift = 0 ; while((1u << pp_shift) < pp) pp_shift++ ; }
-#define GATHER(N) do { if(ctx->opt_assemble_variant == 2) \
-            k_assemble_gather_v2<N><<<grid2, N*G2, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, pp_shift, m->dirty, all, ctx->vals, (uint32_t)ctx->nnzb) ; \
+        if(variant == 3) { int rc = ensure_order(ctx, m) ; if(rc) return rc ; }
+        const uint32_t * order = variant == 3 ? m->order : nullptr ;
+#define GATHER(N) do { if(variant == 2 || variant == 3) \
+            k_assemble_gather_v2<N><<<grid2, N*G2, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, order, m->dirty, all, ctx->vals, (uint32_t)ctx->nnzb) ; \
         else \
             k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent) ; } while(0)
         switch(ctx->S)

@@ -108,42 +108,62 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
     }
 }
 
-// Variant 2 (option "assemble_variant" = 2): the same sums with cheaper index arithmetic.  ncu on the plain kernel
-// (profiles/r01c_ncu_assembly.txt) shows it issue-bound, not latency-bound: 58 % of the issue slots busy at 40 % of the
-// DRAM bandwidth, 221 warp instructions per 32 entries -- a 64-bit division by SS per entry and a division by the
-// runtime npe^2 per contribution.  Here a block is G groups of SS threads: a thread's entry (threadIdx.x % SS) and
-// group are fixed once, the stored block advances by G per step in 32-bit arithmetic, and the element of a
-// contribution is a shift when npe^2 is a power of two (linear tetrahedra and hexahedra; pp_shift < 0: divide).
+// Variants 2 and 3 (option "assemble_variant").  ncu and the SASS of the plain kernel (profiles/r01c_ncu_assembly.txt,
+// profiles/r01_notes.md): it is issue-bound at 40 % of the DRAM bandwidth, and the instructions go into DIVERGENCE --
+// a warp holds 3.5 stored blocks whose contribution lists are 1 to 8 long (2.3 on average for hexahedra), the loop is
+// unrolled by four with predicated remainders, and every lane waits for the longest list of its warp: 221 warp
+// instructions per 32 entries where ~100 would do.  (The division by the runtime npe^2 is not the cost: the compiler
+// hoists the reciprocal out of the loop.)
+//   variant 2: a block is G groups of SS threads, a thread's entry (threadIdx.x % SS) and group are fixed once and the
+//              stored block advances by G per step in 32-bit arithmetic (no 64-bit division per entry);
+//   variant 3: the same, visiting the stored blocks in the order of `order` -- sorted by list length, longest first,
+//              ties in storage order (k_list_lengths + a stable radix sort, once per topology) -- so the lanes of a
+//              warp walk lists of (almost) one length.
 // Launch with blockDim.x == SS*G.  Per entry the additions and their order are unchanged -> same bits.
 template<int SS>
 static __global__ void k_assemble_gather_v2(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
                                             const double * __restrict__ ke, const double * __restrict__ scales,
-                                            uint32_t pp, int pp_shift, const unsigned char * __restrict__ dirty, int all,
+                                            uint32_t pp, const uint32_t * __restrict__ order,
+                                            const unsigned char * __restrict__ dirty, int all,
                                             double * __restrict__ vals, uint32_t nnzb)
 {
     const uint32_t G = blockDim.x/SS ;
     const uint32_t g = threadIdx.x/SS ;
     const uint32_t ent = threadIdx.x-g*SS ;
     const uint32_t step = gridDim.x*G ;
-    for(uint32_t d0 = blockIdx.x*G ; d0 < nnzb ; d0 += step)      // d0 is uniform over the block: no early exit
+    for(uint32_t d0 = blockIdx.x*G ; d0 < nnzb ; d0 += step)      // d0 is uniform over the block
     {
-        const uint32_t d = d0+g ;
-        if(d < nnzb && (all || dirty[d]))
+        if(d0+g < nnzb)
         {
-            const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
-            double a = 0., c = 0. ;
-            for(uint32_t p = p0 ; p < p1 ; p++)
+            const uint32_t d = order ? __ldg(order+d0+g) : d0+g ;
+            if(all || dirty[d])
             {
-                const uint32_t src = __ldg(csrc+p) ;
-                const uint32_t e = pp_shift >= 0 ? (src >> pp_shift) : src/pp ;
-                const double y = __dsub_rn(__dmul_rn(__ldg(scales+e), ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
-                const double t = __dadd_rn(a, y) ;
-                c = __dsub_rn(__dsub_rn(t, a), y) ;
-                a = t ;
+                const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
+                double a = 0., c = 0. ;
+                for(uint32_t p = p0 ; p < p1 ; p++)
+                {
+                    const uint32_t src = __ldg(csrc+p) ;
+                    const double y = __dsub_rn(__dmul_rn(__ldg(scales+src/pp), ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
+                    const double t = __dadd_rn(a, y) ;
+                    c = __dsub_rn(__dsub_rn(t, a), y) ;
+                    a = t ;
+                }
+                vals[(uint64_t)d*SS+ent] = a ;
             }
-            vals[(uint64_t)d*SS+ent] = a ;
         }
         if(step > nnzb-d0) break ;                                  // d0 += step would wrap past 2^32
+    }
+}
+
+// keys and values of the length sort of variant 3: len[k] = length of the contribution list of stored block k, id[k] = k
+static __global__ void k_list_lengths(const uint32_t * __restrict__ cptr, uint64_t nnzb, uint32_t * __restrict__ len,
+                                      uint32_t * __restrict__ id)
+{
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    for(uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; k < nnzb ; k += stride)
+    {
+        len[k] = cptr[k+1]-cptr[k] ;
+        id[k] = (uint32_t)k ;
     }
 }
 
