@@ -249,8 +249,9 @@ int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
  * "split_dot" (0/1: PCG's p.q as a separate streaming pass after a plain SpMV instead of the fused form; single
  * device; same algorithm, another summation order; default from env AMIE_B200_SPLIT_DOT),
  * "iters_per_graph" (iterations captured per CUDA-graph launch), "verbose" (0/1:
- * print the reference's cerr lines), "assemble_variant" (0 | 2 | 3) and "dirichlet_variant" (0 | 1): kernel selection
- * of amie_b200_assemble / amie_b200_set_boundary_conditions (same bits, see csrc/kernels_assemble.cuh).                                                     */
+ * print the reference's cerr lines), "assemble_variant" (0 | 2 | 3), "dirichlet_variant" (0 | 1) and "fields_variant" (0 | 1):
+ * kernel selection of amie_b200_assemble / amie_b200_set_boundary_conditions / amie_b200_element_fields (same bits, see
+ * csrc/kernels_assemble.cuh, csrc/kernels_fields.cuh).                                                     */
 int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value) ;
 
 /* ------------------------------------------------------------------ synthetic problems

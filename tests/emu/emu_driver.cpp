@@ -128,14 +128,21 @@ int emu_dirichlet(int stride, uint64_t nb, const uint32_t * row_size, const uint
 // set_element_kinematics + element_fields (fields.cu)
 int emu_element_fields(int dim, uint64_t n_elem, int npe, const uint32_t * ids, const double * dshape, const double * jinv,
                        const double * tensors, const double * istrain, const double * istress, const uint32_t * tensor_of_elem,
-                       const double * u, uint64_t n_u, double * total, double * mech, double * stress)
+                       const double * u, uint64_t n_u, int variant, double * total, double * mech, double * stress)
 {
     std::vector<uint32_t> ids_t(std::max<uint64_t>(1, n_elem*npe)) ;
     std::vector<double> ds_t(std::max<uint64_t>(1, n_elem*npe*dim)), ji_t(std::max<uint64_t>(1, n_elem*dim*dim)) ;
     emu_launch(GRID, BLOCK, [&]() { k_to_component_major<uint32_t>(ids, ids_t.data(), n_elem, npe) ; }) ;
     emu_launch(GRID, BLOCK, [&]() { k_to_component_major<double>(dshape, ds_t.data(), n_elem, npe*dim) ; }) ;
     emu_launch(GRID, BLOCK, [&]() { k_to_component_major<double>(jinv, ji_t.data(), n_elem, dim*dim) ; }) ;
-    if(dim == 2)
+    // "fields_variant" = 1: the unrolled, phase-split instantiations for linear triangles / tetrahedra
+    if(variant == 1 && dim == 2 && npe == 3)
+        emu_launch_sync(2, FIELD_THREADS, [&]() { k_element_fields<2, 3>(ids_t.data(), ds_t.data(), ji_t.data(), tensors, istrain, istress, tensor_of_elem,
+                                                                       u, n_u, n_elem, npe, total, mech, stress) ; }) ;
+    else if(variant == 1 && dim == 3 && npe == 4)
+        emu_launch_sync(2, FIELD_THREADS, [&]() { k_element_fields<3, 4>(ids_t.data(), ds_t.data(), ji_t.data(), tensors, istrain, istress, tensor_of_elem,
+                                                                       u, n_u, n_elem, npe, total, mech, stress) ; }) ;
+    else if(dim == 2)
         emu_launch_sync(2, FIELD_THREADS, [&]() { k_element_fields<2>(ids_t.data(), ds_t.data(), ji_t.data(), tensors, istrain, istress, tensor_of_elem,
                                                                     u, n_u, n_elem, npe, total, mech, stress) ; }) ;
     else if(dim == 3)

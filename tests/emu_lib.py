@@ -96,7 +96,7 @@ def dirichlet(stride, row_size, column_index, vals_compact, forces, fix_ids, fix
     return vals, forces, nat, dirty[:ci.size]
 
 
-def element_fields(dim, ids, dshape, jinv, u, tensors, imposed_strain, imposed_stress, tensor_of_elem):
+def element_fields(dim, ids, dshape, jinv, u, tensors, imposed_strain, imposed_stress, tensor_of_elem, variant=0):
     ids = np.ascontiguousarray(ids, np.uint32)
     ne, npe = ids.shape
     nc = 3 if dim == 2 else 6
@@ -109,7 +109,7 @@ def element_fields(dim, ids, dshape, jinv, u, tensors, imposed_strain, imposed_s
     u = c(u)
     out = [np.zeros((ne, nc)) for _ in range(3)]
     rc = emu().emu_element_fields(int(dim), u64(ne), int(npe), _vp(ids), _vp(c(dshape)), _vp(c(jinv)), _vp(tensors), _vp(es), _vp(ss),
-                                  _vp(c(tensor_of_elem, np.uint32)), _vp(u), u64(u.size), *[_vp(o) for o in out])
+                                  _vp(c(tensor_of_elem, np.uint32)), _vp(u), u64(u.size), int(variant), *[_vp(o) for o in out])
     assert rc == 0, rc
     return tuple(out)
 

@@ -108,3 +108,36 @@ def test_pcg_with_split_dot_matches_oracle(pkg, ol, systems, preset, n, graph):
     assert cg.solve(None, None, 1e-10, -1) == bool(ret)
     assert abs(int(cg.nit) - int(info.nit)) <= 2 and rel_l2(cg.x, x_ref) <= 1e-8
     asm.close()
+
+
+def test_fields_variant_matches_reference_bits(pkg, ol):
+    """Option "fields_variant" = 1: the unrolled, phase-split field kernel for linear triangles / tetrahedra."""
+    import glob
+    import os
+    from test_gpu_recovery import context_for, same_bits
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*-fields.npz"))):
+        g = np.load(path)
+        asm, dim = context_for(pkg, g)
+        asm.set_option("fields_variant", 1)
+        asm.set_element_kinematics(dim, g["ids"], g["dshape"], g["jinv"])
+        asm.set_element_behaviour(g["tensors"], g["imposed_strain"], g["imposed_stress"], g["tensor_of_elem"])
+        tot, mech, sig = asm.element_fields(g["u"])
+        assert same_bits(tot, g["total_strain"]) and same_bits(mech, g["mechanical_strain"]) and same_bits(sig, g["real_stress"])
+        # unused slots inside the element with garbage derivatives, per-element behaviours
+        rng = np.random.default_rng(5)
+        ne = g["ids"].shape[0]
+        nc = tot.shape[1]
+        idsr, dsr = g["ids"].copy(), g["dshape"].copy()
+        hole = rng.integers(0, idsr.shape[1], ne)
+        pick = rng.random(ne) < 0.3
+        idsr[pick, hole[pick]] = 0xFFFFFFFF
+        dsr[pick, hole[pick], :] = np.nan
+        C = g["tensors"][g["tensor_of_elem"]] * rng.uniform(0.2, 1.0, (ne, 1, 1))
+        es, ss = 1e-4 * rng.standard_normal((ne, nc)), rng.standard_normal((ne, nc))
+        asm.set_element_kinematics(dim, idsr, dsr, g["jinv"])
+        asm.set_element_behaviour(C, es, ss, None)
+        got = asm.element_fields(g["u"])
+        want = ol.oracle_element_fields(dim, idsr, dsr, g["jinv"], g["u"], C, es, ss, None)
+        for a, b in zip(got, want):
+            assert same_bits(a, b)
+        asm.close()

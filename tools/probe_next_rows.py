@@ -2,6 +2,7 @@
 """First device timings of the SURVEY section 8(f) rows next to the solve: value assembly + Dirichlet elimination (f1)
 and field recovery (f2), at sizes well beyond L2.  Prints one JSON line per row; run under ncu to capture the kernels
 (k_assemble_gather, k_dirichlet, k_element_fields)."""
+import ctypes
 import json
 import os
 import sys
@@ -127,6 +128,19 @@ def fields_row(n=100, reps=5):
             alg += ne * 8 * nc * (nc + 2)
         out[label] = dict(ms=min(ms), algorithmic_bytes=alg, gbs=alg / (min(ms) * 1e-3) / 1e9,
                           frac_of_peak=alg / (min(ms) * 1e-3) / 1e9 / PEAK, melem_per_s=ne / (min(ms) * 1e-3) / 1e6)
+        # the unrolled, phase-split kernel (option "fields_variant" = 1; same bits)
+        ref = [np.zeros((ne, nc)) for _ in range(3)]
+        asm.check(lib.amie_b200_element_fields(ctx, None, 0, *[r.ctypes.data_as(ctypes.c_void_p) for r in ref]))
+        asm.set_option("fields_variant", 1)
+        got = [np.zeros((ne, nc)) for _ in range(3)]
+        ms1 = []
+        for _ in range(reps):
+            asm.check(lib.amie_b200_element_fields(ctx, None, 0, None, None, None))
+            ms1.append(asm.stats().fields_ms)
+        asm.check(lib.amie_b200_element_fields(ctx, None, 0, *[r.ctypes.data_as(ctypes.c_void_p) for r in got]))
+        asm.set_option("fields_variant", 0)
+        out[label].update(variant1_ms=min(ms1), variant1_frac_of_peak=alg / (min(ms1) * 1e-3) / 1e9 / PEAK,
+                          variant1_same_bits=bool(all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for a, b in zip(ref, got))))
     asm.close()
     return dict(row="f2 element fields", elements=ne, nodes=nb, **out)
 

@@ -255,6 +255,7 @@ int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
     else if(k == "split_dot") ctx->opt_split_dot = (int)value ;
     else if(k == "assemble_variant") ctx->opt_assemble_variant = (int)value ;
     else if(k == "dirichlet_variant") ctx->opt_dirichlet_variant = (int)value ;
+    else if(k == "fields_variant") ctx->opt_fields_variant = (int)value ;
     else { ctx->set_error("unknown option "+k) ; return AMIE_B200_ERR_ARG ; }
     return AMIE_B200_OK ;
 }

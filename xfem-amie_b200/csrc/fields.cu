@@ -189,12 +189,13 @@ int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u
     if(m->n_elem)
     {
         const int grid = field_grid(ctx, m->n_elem) ;
-        if(m->dim == 2)
-            k_element_fields<2><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress,
-                    m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2]) ;
-        else
-            k_element_fields<3><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress,
-                    m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2]) ;
+#define FIELDS(D, P) k_element_fields<D, P><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress, \
+                    m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2])
+        // "fields_variant" = 1: the unrolled, phase-split form for linear triangles / tetrahedra (kernels_fields.cuh)
+        const bool unrolled = ctx->opt_fields_variant == 1 ;
+        if(m->dim == 2) { if(unrolled && m->npe == 3) FIELDS(2, 3) ; else FIELDS(2, 0) ; }
+        else            { if(unrolled && m->npe == 4) FIELDS(3, 4) ; else FIELDS(3, 0) ; }
+#undef FIELDS
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream)) ;
     CUDA_TRY(ctx, cudaGetLastError()) ;

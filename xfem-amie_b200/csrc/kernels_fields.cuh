@@ -24,7 +24,11 @@ static __global__ void k_to_component_major(const T * __restrict__ in, T * __res
 
 // One thread per element.  g[c][l] accumulates d(shape_j)/d(local_l) * u_j[c] over the element's slots in slot
 // order, exactly as the reference's x_xi ... z_zeta accumulators do.
-template<int DIM>
+// NPE > 0 (option "fields_variant" = 1, elements of exactly NPE slots): the slot loop is unrolled and split into phases --
+// every id and derivative first, then every gathered dof, then the sums in slot order -- so that a thread has all its
+// loads in flight at once instead of one dependent id -> dof pair per slot (the plain form stalls on exactly that:
+// long_scoreboard only, profiles/r01b_ncu_element_fields.txt).  Same products, same sums, same order -> same bits.
+template<int DIM, int NPE = 0>
 static __global__ void __launch_bounds__(FIELD_THREADS)
 k_element_fields(const uint32_t * __restrict__ ids, const double * __restrict__ dshape, const double * __restrict__ jinv,
                  const double * __restrict__ tensors, const double * __restrict__ istrain, const double * __restrict__ istress,
@@ -51,6 +55,39 @@ k_element_fields(const uint32_t * __restrict__ ids, const double * __restrict__ 
             for(int c = 0 ; c < DIM ; c++)
                 #pragma unroll
                 for(int l = 0 ; l < DIM ; l++) g[c][l] = 0. ;
+            if constexpr(NPE > 0)
+            {
+                uint32_t idj[NPE] ;
+                double f[NPE][DIM], uj[NPE][DIM] ;
+                #pragma unroll
+                for(int j = 0 ; j < NPE ; j++) idj[j] = __ldg(ids+(uint64_t)j*n_elem+e) ;
+                #pragma unroll
+                for(int j = 0 ; j < NPE ; j++)
+                    #pragma unroll
+                    for(int l = 0 ; l < DIM ; l++) f[j][l] = __ldg(dshape+(uint64_t)(j*DIM+l)*n_elem+e) ;   // (ld_stream is a volatile asm: it would pin the load next to its use)
+                #pragma unroll
+                for(int j = 0 ; j < NPE ; j++)
+                    #pragma unroll
+                    for(int c = 0 ; c < DIM ; c++)
+                    {
+                        const uint64_t k = (uint64_t)idj[j]*DIM+c ;
+                        uj[j][c] = (idj[j] != NO_NODE && k < n_u) ? __ldg(u+k) : 0. ;
+                    }
+                #pragma unroll
+                for(int j = 0 ; j < NPE ; j++)
+                {
+                    const bool used = idj[j] != NO_NODE ;         // selects, not a branch: a branch would sink the loads back
+                    #pragma unroll
+                    for(int c = 0 ; c < DIM ; c++)
+                        #pragma unroll
+                        for(int l = 0 ; l < DIM ; l++)
+                        {
+                            const double sum = __dadd_rn(g[c][l], __dmul_rn(f[j][l], uj[j][c])) ;
+                            g[c][l] = used ? sum : g[c][l] ;
+                        }
+                }
+            }
+            else
             for(int j = 0 ; j < npe ; j++)
             {
                 const uint32_t id = __ldg(ids+(uint64_t)j*n_elem+e) ;
