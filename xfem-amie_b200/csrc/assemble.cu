@@ -92,9 +92,9 @@ static int ensure_order(amie_b200_ctx * ctx, AssemblyMap * m)
     k_list_lengths<<<vec_grid(ctx, n), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, n, len, id) ;
     ORD_TRY(cudaGetLastError()) ;
     // lists are a handful of entries long: 16 key bits are plenty, but a list may in principle be longer -> all 32
-    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len, len_sorted, id, m->order, (int)n, 0, 32, ctx->stream)) ;
+    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len, len_sorted, id, m->order, n, 0, 32, ctx->stream)) ;
     ORD_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16))) ;
-    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len, len_sorted, id, m->order, (int)n, 0, 32, ctx->stream)) ;
+    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len, len_sorted, id, m->order, n, 0, 32, ctx->stream)) ;
     ORD_TRY(cudaStreamSynchronize(ctx->stream)) ;
 #undef ORD_TRY
     cleanup() ;
