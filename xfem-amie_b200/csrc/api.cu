@@ -39,6 +39,9 @@ static uint64_t device_bytes(const amie_b200_ctx * ctx)
     for(int i = 0 ; i < 8 ; i++) if(ctx->w[i]) nv++ ;
     uint64_t bytes = ctx->vec_len*8*nv ;
     if(ctx->have_structure) bytes += (ctx->nb+1)*4+ctx->nnzb*4+ctx->nnzb*(uint64_t)(ctx->S*ctx->S)*8+ctx->N*8 ;
+    if(ctx->user_diag) bytes += ctx->N*8 ;
+    if(ctx->hist[0]) bytes += 2*ctx->hist_n*8 ;
+    bytes += assembly_map_bytes(ctx)+field_map_bytes(ctx) ;       // rows next to the solve (assemble.cu, fields.cu)
     return bytes ;
 }
 

@@ -58,6 +58,22 @@ void assembly_map_destroy(amie_b200_ctx * ctx)
     ctx->amap = nullptr ;
 }
 
+uint64_t assembly_map_bytes(const amie_b200_ctx * ctx)
+{
+    const AssemblyMap * m = ctx->amap ;
+    if(!m) return 0 ;
+    uint64_t b = 0 ;
+    if(m->built)
+    {
+        const uint64_t SS = (uint64_t)ctx->S*ctx->S ;
+        b += m->nsrc*4+(ctx->nnzb+1)*4+ctx->nnzb+m->nsrc*SS*8+m->n_elem*8 ;     // dest_of_src, cptr, dirty, ke, scales
+        b += m->nsrc*4 ;                                                         // csrc: at most one entry per element block
+        if(m->order) b += ctx->nnzb*4 ;
+    }
+    if(m->fixmask) b += 2*m->mask_nb+2*m->mask_nb*4 ;
+    return b ;
+}
+
 // ---------------------------------------------------------------------------------------------------- API
 
 static int require_single(amie_b200_ctx * ctx, const char * what)

@@ -93,6 +93,8 @@ inline double wall_now()
 // internal entry points shared between translation units
 void assembly_map_destroy(amie_b200_ctx * ctx) ;          // assemble.cu
 void field_map_destroy(amie_b200_ctx * ctx) ;             // fields.cu
+uint64_t assembly_map_bytes(const amie_b200_ctx * ctx) ;  // HBM held by the gather lists, element matrices and masks
+uint64_t field_map_bytes(const amie_b200_ctx * ctx) ;     // ... by the element kinematics, behaviours and results
 void history_destroy(amie_b200_ctx * ctx) ;               // cgsolve.cu
 void ctx_free_matrix(amie_b200_ctx * ctx) ;               // api.cu: matrix arrays + everything tied to the topology
 int ctx_alloc_vectors(amie_b200_ctx * ctx) ;

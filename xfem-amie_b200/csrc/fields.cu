@@ -67,6 +67,19 @@ void field_map_destroy(amie_b200_ctx * ctx)
     ctx->fmap = nullptr ;
 }
 
+uint64_t field_map_bytes(const amie_b200_ctx * ctx)
+{
+    const FieldMap * m = ctx->fmap ;
+    if(!m) return 0 ;
+    const uint64_t nc = m->nc ;
+    uint64_t b = m->n_elem*((uint64_t)m->npe*4+(uint64_t)m->npe*m->dim*8+(uint64_t)m->dim*m->dim*8+3*nc*8) ;
+    b += m->n_tensors*(nc*nc+2*nc)*8 ;
+    if(m->tensor_of_elem) b += m->n_elem*4 ;
+    if(m->principal) b += m->n_elem*m->dim*8 ;
+    b += m->u_tmp_len*8 ;
+    return b ;
+}
+
 static int field_grid(const amie_b200_ctx * ctx, uint64_t n_elem)
 {
     const uint64_t tiles = (n_elem+FIELD_THREADS-1)/FIELD_THREADS ;
