@@ -283,6 +283,17 @@ int amie_b200_partition_rows(uint64_t nb, const uint32_t * row_size, int nparts,
 int amie_b200_partition_halo(uint64_t r0, uint64_t r1, const uint32_t * row_size_local,
                              const uint32_t * column_index_local, uint32_t * halo_out, uint64_t * nhalo_out) ;
 
+/* ------------------------------------------------------------------ node renumbering (host-only)
+ * The mesher's numbering has no locality; these are the host half of a renumbering applied once per topology
+ * (csrc/reorder.cpp; the device half -- values gathered through block_from, vectors through perm -- is not wired
+ * into the context yet).  perm_out[old node] = new node: reverse Cuthill-McKee on the block graph.               */
+int amie_b200_rcm_order(uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint32_t * perm_out) ;
+/* The structure in the new numbering (columns ascending inside each row) and, for every stored block of it, the
+ * stored block of the old structure it is (block_from_out[new k] = old k): array_new block k = array_old block
+ * block_from[k].  AMIE_B200_ERR_ARG if perm is not a permutation.                                                  */
+int amie_b200_permute_structure(uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, const uint32_t * perm,
+                                uint32_t * row_size_out, uint32_t * column_index_out, uint32_t * block_from_out) ;
+
 /* ------------------------------------------------------------------ distributed context (one process per GPU)
  * Rank r owns block rows [bounds[r], bounds[r+1]).  The NCCL communicator is created inside the
  * library from a 128-byte ncclUniqueId the caller broadcasts (e.g. with torch.distributed).   */

@@ -110,6 +110,8 @@ def lib():
         L.amie_b200_synth_to_device.argtypes = [vp, vp]
         L.amie_b200_partition_rows.argtypes = [u64, vp, ci, vp]
         L.amie_b200_partition_halo.argtypes = [u64, u64, vp, vp, vp, vp]
+        L.amie_b200_rcm_order.argtypes = [u64, vp, vp, vp]
+        L.amie_b200_permute_structure.argtypes = [u64, vp, vp, vp, vp, vp, vp]
         L.amie_b200_nccl_unique_id.argtypes = [vp]
         L.amie_b200_dist_init.argtypes = [vp, ci, ci, vp, vp]
         L.amie_b200_dist_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
@@ -674,3 +676,27 @@ def partition_halo(r0, r1, row_size_local, column_index_local):
     halo = np.zeros(n.value, np.uint32)
     lib().amie_b200_partition_halo(int(r0), int(r1), _ptr(rs), _ptr(ci), _ptr(halo), ctypes.byref(n))
     return halo
+
+
+def rcm_order(row_size, column_index):
+    """perm[old node] = new node: reverse Cuthill-McKee on the block graph (host only)."""
+    rs = np.ascontiguousarray(row_size, np.uint32)
+    ci = np.ascontiguousarray(column_index, np.uint32)
+    perm = np.zeros(rs.size, np.uint32)
+    rc = lib().amie_b200_rcm_order(rs.size, _ptr(rs), _ptr(ci), _ptr(perm))
+    if rc:
+        raise AmieB200Error(rc, "rcm_order")
+    return perm
+
+
+def permute_structure(row_size, column_index, perm):
+    """(row_size, column_index, block_from) of the renumbered structure; block_from[new k] = old k (host only)."""
+    rs = np.ascontiguousarray(row_size, np.uint32)
+    ci = np.ascontiguousarray(column_index, np.uint32)
+    perm = np.ascontiguousarray(perm, np.uint32)
+    rs2, ci2, frm = np.zeros_like(rs), np.zeros_like(ci), np.zeros_like(ci)
+    rc = lib().amie_b200_permute_structure(rs.size, _ptr(rs), _ptr(ci), _ptr(perm), _ptr(rs2), _ptr(ci2), _ptr(frm))
+    if rc:
+        raise AmieB200Error(rc, "permute_structure: perm is not a permutation of the nodes")
+    return rs2, ci2, frm
+
