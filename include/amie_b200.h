@@ -70,6 +70,13 @@ int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb,
  * array[k*s*cl], element (r,c) at + c*cl + r, cl = s + s%2 (pad slots ignored).      */
 int amie_b200_set_values(amie_b200_ctx * ctx, const double * array_padded_colmajor) ;
 
+/* The `array` given to set_values is in ANOTHER block order than the structure given to set_structure: block k of the
+ * array is stored block block_to[k] (a permutation of 0 .. nnzb-1; NULL removes the map).  This is how a host keeps its
+ * own numbering -- AMIE's mesher numbering has no locality -- while the device works on a renumbered matrix
+ * (amie_b200_rcm_order / amie_b200_permute_structure below: block_to is the inverse of block_from); the host then
+ * permutes b, x0 and x at the boundary (host/shim does, env AMIE_B200_RENUMBER=1).                                 */
+int amie_b200_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to) ;
+
 /* ------------------------------------------------------------------ solvers */
 
 /* ConjugateGradient::solve(x0, precond, eps, maxit) with members nssor/rowstart/colstart

@@ -31,6 +31,13 @@ int emu_repack(int stride, const double * padded, double * compact, uint64_t nbl
     return 0 ;
 }
 
+// set_values with a block map (amie_b200_set_block_map): block k of the host array -> stored block block_to[k]
+int emu_repack_scatter(int stride, const double * padded, const uint32_t * block_to, uint64_t nblocks, double * compact)
+{
+    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_repack_scatter<N>(padded, compact, block_to, nblocks) ; }))
+    return 0 ;
+}
+
 // ctx_ensure_dinv: kind 0 InverseDiagonal, 2 InverseDiagonalSquared, 3 InverseLumpedDiagonal
 int emu_precond_diagonal(int kind, int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col,
                          const double * vals, double * d)

@@ -45,6 +45,17 @@ def compact(array_padded, stride):
     return out
 
 
+def compact_scatter(array_padded, stride, block_to):
+    """K-Repack through a block map: block k of the host array lands on stored block block_to[k]."""
+    s = int(stride)
+    cl = s + s % 2
+    arr = np.ascontiguousarray(array_padded, np.float64)
+    bt = np.ascontiguousarray(block_to, np.uint32)
+    out = np.zeros(bt.size * s * s)
+    assert emu().emu_repack_scatter(s, _vp(arr), _vp(bt), u64(bt.size), _vp(out)) == 0
+    return out
+
+
 def padded(vals_compact, stride):
     s = int(stride)
     cl = s + s % 2

@@ -30,6 +30,20 @@ def test_repack_and_preconditioner_diagonals(ol, stride):
         assert same_bits(em.precond_diagonal(kind, stride, rs, ci, vals), ol.oracle_precond_diagonal(S, kind)), kind
 
 
+@pytest.mark.parametrize("stride", [1, 2, 3, 4, 6])
+def test_repack_through_a_block_map(pkg, stride):
+    """set_values on a renumbered structure: the values of the caller's array land where the renumbered structure
+    stores them (csrc/reorder.cpp gives block_from; block_to is its inverse)."""
+    rs, ci, arr, b = random_spd_blocks(stride, 50, 90 + stride)
+    perm = pkg.rcm_order(rs, ci)
+    rs2, ci2, frm = pkg.permute_structure(rs, ci, perm)
+    block_to = np.empty_like(frm)
+    block_to[frm] = np.arange(frm.size, dtype=np.uint32)
+    cl = stride + stride % 2
+    want = em.compact(arr.reshape(-1, stride * cl)[frm].reshape(-1), stride)
+    assert same_bits(em.compact_scatter(arr, stride, block_to), want)
+
+
 @pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "precond-*.npz"))))
 def test_preconditioner_diagonals_against_reference_fixtures(name):
     g = np.load(os.path.join(GOLDEN, name))

@@ -71,6 +71,7 @@ def lib():
         L.amie_b200_last_error.argtypes = [vp]
         L.amie_b200_set_structure.argtypes = [vp, ci, u64, vp, vp, u64]
         L.amie_b200_set_values.argtypes = [vp, vp]
+        L.amie_b200_set_block_map.argtypes = [vp, vp]
         L.amie_b200_pcg.argtypes = [vp, vp, vp, u64, ci, f64, ci, u64, u64, u64, vp, vp, vp, vp]
         L.amie_b200_bicgstab.argtypes = [vp, vp, vp, u64, ci, f64, ci, vp, vp, vp]
         L.amie_b200_spmv.argtypes = [vp, vp, vp, u64, u64, vp]
@@ -151,7 +152,13 @@ class Assembly:
     (nssor, rowstart, colstart, epsilon; solvers/assembly.cpp:1829-1850).
     Owns the device context (one per Assembly)."""
 
-    def __init__(self, matrix=None, forces=None, device=None):
+    def __init__(self, matrix=None, forces=None, device=None, renumber=False):
+        """renumber=True: the device works on the matrix renumbered by reverse Cuthill-McKee (the mesher's numbering has
+        no locality); this object keeps the caller's numbering and permutes b, x0, x and the other host vectors at the
+        boundary, as host/shim does under AMIE_B200_RENUMBER=1.  The *_resident calls, the assembly and field rows then
+        see the DEVICE numbering (use `self.perm`: perm[old node] = new node)."""
+        self.renumber = bool(renumber)
+        self.perm = None
         self.coordinateIndexedMatrix = matrix
         self.externalForces = None if forces is None else np.ascontiguousarray(forces, np.float64)
         self.displacements = np.zeros(0)
@@ -219,13 +226,40 @@ class Assembly:
             return          # matrix was generated on the device (Synth.to_device)
         key = (A.stride, A.row_size.size, A.column_index.size, A.column_index.ctypes.data)
         if key != self._structure_key:
-            self.check(L.amie_b200_set_structure(self.ctx, A.stride, A.row_size.size, _ptr(A.row_size),
-                                                 _ptr(A.column_index), A.column_index.size))
+            if self.renumber:
+                self.perm = rcm_order(A.row_size, A.column_index)
+                rs2, ci2, frm = permute_structure(A.row_size, A.column_index, self.perm)
+                block_to = np.empty_like(frm)
+                block_to[frm] = np.arange(frm.size, dtype=np.uint32)
+                self.check(L.amie_b200_set_structure(self.ctx, A.stride, rs2.size, _ptr(rs2), _ptr(ci2), ci2.size))
+                self.check(L.amie_b200_set_block_map(self.ctx, _ptr(block_to)))
+            else:
+                self.check(L.amie_b200_set_structure(self.ctx, A.stride, A.row_size.size, _ptr(A.row_size),
+                                                     _ptr(A.column_index), A.column_index.size))
             self._structure_key = key
             self._values_dirty = True
         if self._values_dirty:
             self.check(L.amie_b200_set_values(self.ctx, _ptr(A.array)))
             self._values_dirty = False
+
+    # ---- host vectors across the renumbering (identity when renumber is off)
+    def to_device_order(self, v):
+        if v is None or self.perm is None:
+            return v
+        v = np.ascontiguousarray(v, np.float64)
+        s = self.coordinateIndexedMatrix.stride
+        n = self.perm.size * s
+        full = np.zeros(n)
+        full[:min(v.size, n)] = v[:n]          # a shorter x0 is a prefix in the caller's numbering (conjugategradient.cpp:100-104)
+        out = np.empty(n)
+        out.reshape(-1, s)[self.perm] = full.reshape(-1, s)
+        return out
+
+    def from_device_order(self, v):
+        if self.perm is None:
+            return v
+        s = self.coordinateIndexedMatrix.stride
+        return np.ascontiguousarray(v.reshape(-1, s)[self.perm].reshape(-1))
 
     # ---- device-side value assembly + Dirichlet elimination
     def set_structure_only(self, stride, row_size, column_index):
@@ -429,27 +463,29 @@ class Assembly:
     def spmv(self, x, minus_b=None, rowstart=0, colstart=0):
         """assign(y, A*x [- b], rowstart, colstart)"""
         self.sync_matrix()
-        x = np.ascontiguousarray(x, np.float64)
+        if self.perm is not None and (rowstart or colstart):
+            raise AmieB200Error(ERR_UNSUPPORTED, "rowstart / colstart address the caller's numbering: not with renumber=True")
+        x = self.to_device_order(np.ascontiguousarray(x, np.float64))
         y = np.zeros_like(x)
-        b = None if minus_b is None else np.ascontiguousarray(minus_b, np.float64)
+        b = None if minus_b is None else self.to_device_order(np.ascontiguousarray(minus_b, np.float64))
         self.check(lib().amie_b200_spmv(self.ctx, _ptr(x), _ptr(b), rowstart, colstart, _ptr(y)))
-        return y
+        return self.from_device_order(y)
 
     def residual(self, u, f=None):
         """r = K u - f and |r| (features/features.cpp:4766-4768)."""
         self.sync_matrix()
-        u = np.ascontiguousarray(u, np.float64)
-        f = self.getForces() if f is None else np.ascontiguousarray(f, np.float64)
+        u = self.to_device_order(np.ascontiguousarray(u, np.float64))
+        f = self.to_device_order(self.getForces() if f is None else np.ascontiguousarray(f, np.float64))
         r = np.zeros_like(u)
         nrm = f64()
         self.check(lib().amie_b200_residual(self.ctx, _ptr(u), _ptr(f), _ptr(r), ctypes.byref(nrm)))
-        return r, nrm.value
+        return self.from_device_order(r), nrm.value
 
     def inverse_diagonal(self):
         self.sync_matrix()
         d = np.zeros(self.coordinateIndexedMatrix.row_size.size * self.coordinateIndexedMatrix.stride)
         self.check(lib().amie_b200_inverse_diagonal(self.ctx, _ptr(d)))
-        return d
+        return self.from_device_order(d)
 
     def preconditioner_diagonal(self, kind):
         """The `diagonal` member of the reference's preconditioner class `kind` (PRECOND_JACOBI, _DIAGONAL_SQUARED,
@@ -457,7 +493,7 @@ class Assembly:
         self.sync_matrix()
         d = np.zeros(self.stats().ndof)
         self.check(lib().amie_b200_preconditioner_diagonal(self.ctx, int(kind), _ptr(d)))
-        return d
+        return self.from_device_order(d)
 
     def cgsolve(self, maxit=-1, verbose=False):
         """Assembly::cgsolve for an assembled symmetric system (solvers/assembly.cpp:1841-1858)."""
@@ -523,6 +559,7 @@ class LinearSolver:
                 d = precond.diagonal
                 if d is None or d.size != self.assembly.getForces().size:
                     raise ValueError("DiagonalPreconditionner: one entry per degree of freedom")
+                d = self.assembly.to_device_order(d)
                 self.assembly.check(lib().amie_b200_set_preconditioner_diagonal(self.assembly.ctx, _ptr(d)))
             return precond.kind
         raise AmieB200Error(ERR_UNSUPPORTED, "only diagonal preconditioners (nullptr -> InverseDiagonal, InverseDiagonalSquared, "
@@ -542,15 +579,19 @@ class ConjugateGradient(LinearSolver):
         A.sync_matrix()
         if verbose:
             A.set_option("verbose", 1)
-        b = A.getForces()
+        if A.perm is not None and (self.rowstart or self.colstart):
+            raise AmieB200Error(ERR_UNSUPPORTED, "rowstart / colstart address the caller's numbering: not with renumber=True")
+        b = A.to_device_order(A.getForces())
         x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
+        if x0.size:
+            x0 = A.to_device_order(x0)
         x = np.zeros(b.size)
         nit, err, rho = u64(), f64(), f64()
         rc = lib().amie_b200_pcg(A.ctx, _ptr(b), _ptr(x0) if x0.size else None, x0.size, self._kind(precond),
                                  eps, int(maxit), int(self.nssor), int(self.rowstart), int(self.colstart),
                                  _ptr(x), ctypes.byref(nit), ctypes.byref(err), ctypes.byref(rho))
         A.check(rc)
-        self.x, self.nit, self.last_error, self.last_rho = x, nit.value, err.value, rho.value
+        self.x, self.nit, self.last_error, self.last_rho = A.from_device_order(x), nit.value, err.value, rho.value
         return bool(rc)
 
 
@@ -565,14 +606,16 @@ class BiConjugateGradientStabilized(LinearSolver):
         A.sync_matrix()
         if verbose:
             A.set_option("verbose", 1)
-        b = A.getForces()
+        b = A.to_device_order(A.getForces())
         x0 = np.zeros(0) if x0 is None else np.ascontiguousarray(x0, np.float64)
+        if x0.size == b.size:
+            x0 = A.to_device_order(x0)         # (any other size is ignored by the reference, :21-24)
         x = np.zeros(b.size)
         nit, err = u64(), f64()
         rc = lib().amie_b200_bicgstab(A.ctx, _ptr(b), _ptr(x0) if x0.size else None, x0.size, self._kind(precond),
                                       eps, int(maxit), _ptr(x), ctypes.byref(nit), ctypes.byref(err))
         A.check(rc)
-        self.x, self.nit, self.last_error = x, nit.value, err.value
+        self.x, self.nit, self.last_error = A.from_device_order(x), nit.value, err.value
         return bool(rc)
 
 

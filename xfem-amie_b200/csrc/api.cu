@@ -20,7 +20,7 @@ void ctx_free_matrix(amie_b200_ctx * ctx)
     ctx->alloc_gen++ ;
     assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
     field_map_destroy(ctx) ;             // element data belongs to the topology too
-    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ;
+    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ; dfree(ctx->block_to) ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }
 
@@ -345,11 +345,12 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     const int S = ctx->S ;
     const int cl = S+S%2 ;
-    if(cl == S)
+    if(cl == S && !ctx->block_to)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vals, array, ctx->nnzb*S*S*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
     else
     {
         // K-Repack: stream the padded array through a device staging buffer, 12 -> 9 doubles per block
+        // (with a block map: every stride goes this way and the blocks are scattered to their stored positions)
         const uint64_t chunk_blocks = std::min<uint64_t>(std::max<uint64_t>(ctx->nnzb, 1), (256ull << 20)/(S*cl*8)) ;
         double * stage[2] = {nullptr, nullptr} ;
         for(int i = 0 ; i < 2 ; i++)
@@ -370,7 +371,17 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
             uint64_t nblk = std::min(chunk_blocks, ctx->nnzb-k) ;
             cudaEventSynchronize(done[which]) ;
             cudaMemcpyAsync(stage[which], array+k*S*cl, nblk*S*cl*sizeof(double), cudaMemcpyHostToDevice, ctx->stream) ;
-            if(S == 3)      k_repack<3><<<vec_grid(ctx, nblk*9), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k*9, nblk) ;
+            if(ctx->block_to)
+            {
+                const int g = vec_grid(ctx, nblk*S*S) ;
+                const uint32_t * map = ctx->block_to+k ;
+                if(S == 3)      k_repack_scatter<3><<<g, 256, 0, ctx->stream>>>(stage[which], ctx->vals, map, nblk) ;
+                else if(S == 2) k_repack_scatter<2><<<g, 256, 0, ctx->stream>>>(stage[which], ctx->vals, map, nblk) ;
+                else if(S == 1) k_repack_scatter<1><<<g, 256, 0, ctx->stream>>>(stage[which], ctx->vals, map, nblk) ;
+                else if(S == 4) k_repack_scatter<4><<<g, 256, 0, ctx->stream>>>(stage[which], ctx->vals, map, nblk) ;
+                else            k_repack_scatter<6><<<g, 256, 0, ctx->stream>>>(stage[which], ctx->vals, map, nblk) ;
+            }
+            else if(S == 3) k_repack<3><<<vec_grid(ctx, nblk*9), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k*9, nblk) ;
             else            k_repack<1><<<vec_grid(ctx, nblk), 256, 0, ctx->stream>>>(stage[which], ctx->vals+k, nblk) ;
             cudaEventRecord(done[which], ctx->stream) ;
         }
@@ -383,6 +394,27 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
     ctx->have_values = true ;
     ctx->dinv_valid = false ;
     ctx->stats.values_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
+}
+
+int amie_b200_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to)
+{
+    if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(!ctx->have_structure) { ctx->set_error("set_block_map before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    if(ctx->dist) { ctx->set_error("set_block_map: not available on a row-partitioned context") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    if(!block_to) { dfree(ctx->block_to) ; return AMIE_B200_OK ; }
+    std::vector<bool> seen(ctx->nnzb, false) ;
+    for(uint64_t k = 0 ; k < ctx->nnzb ; k++)
+    {
+        if(block_to[k] >= ctx->nnzb || seen[block_to[k]]) { ctx->set_error("set_block_map: not a permutation of the stored blocks") ; return AMIE_B200_ERR_ARG ; }
+        seen[block_to[k]] = true ;
+    }
+    if(!ctx->block_to) CUDA_TRY(ctx, cudaMalloc(&ctx->block_to, std::max<uint64_t>(ctx->nnzb, 1)*sizeof(uint32_t))) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->block_to, block_to, ctx->nnzb*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    ctx->have_values = false ;            // whatever was uploaded before was in the other order
+    ctx->dinv_valid = false ;
     return AMIE_B200_OK ;
 }
 

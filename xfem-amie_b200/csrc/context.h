@@ -32,6 +32,7 @@ struct amie_b200_ctx
     bool have_structure = false, have_values = false, dinv_valid = false ;
     int dinv_kind = AMIE_B200_PRECOND_JACOBI ;   // which diagonal preconditioner `dinv` holds while dinv_valid
     double * user_diag = nullptr ;               // AMIE_B200_PRECOND_DIAGONAL: the caller's diagonal (N doubles)
+    uint32_t * block_to = nullptr ;              // amie_b200_set_block_map: block k of the host array -> stored block (nnzb)
     bool have_rhs = false ;
 
     // ---- vectors (device); x-like vectors that are SpMV inputs have room for the halo tail

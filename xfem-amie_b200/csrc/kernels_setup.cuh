@@ -84,6 +84,22 @@ __global__ void k_repack(const double * padded, double * compact, uint64_t nbloc
     }
 }
 
+// K-Repack through a block map (amie_b200_set_block_map): block k of the chunk goes to stored block block_to[k] --
+// the host array is in another block order than the structure on the device (a renumbered matrix, csrc/reorder.cpp)
+template<int S>
+__global__ void k_repack_scatter(const double * padded, double * compact, const uint32_t * block_to, uint64_t nblocks)
+{
+    constexpr int CL = S+S%2 ;
+    constexpr int SS = S*S ;
+    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < nblocks*SS ; i += (uint64_t)gridDim.x*blockDim.x)
+    {
+        const uint64_t k = i/SS ;
+        const int e = (int)(i-k*SS) ;
+        const int c = e/S, r = e-c*S ;
+        compact[(uint64_t)block_to[k]*SS+e] = padded[k*(S*CL)+c*CL+r] ;
+    }
+}
+
 static __global__ void k_rowptr_from_sizes_check(const uint32_t * col, const uint32_t * rowptr, uint64_t nb, uint32_t ncols, int * bad)
 {
     for(uint64_t r = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; r < nb ; r += (uint64_t)gridDim.x*blockDim.x)

@@ -21,12 +21,23 @@ bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * pr
     if(!ctx)
         return false ;
     const Vector & b = assembly->getForces() ;
-    if(!AmieB200Shim::upload_diagonal(ctx, diagonal, b.size()))
+    if(!AmieB200Shim::upload_diagonal(ctx, diagonal, b.size(), assembly))
         return false ;
     x.resize(b.size(), 0.) ;
     uint64_t n = 0 ;
     double err = 0 ;
-    int ret = amie_b200_bicgstab(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, epsilon, maxit, &x[0], &n, &err) ;
+    int ret ;
+    if(const std::vector<uint32_t> * perm = AmieB200Shim::permutation_for(assembly))
+    {
+        const size_t stride = b.size()/perm->size() ;
+        Vector bp, x0p, xp(0., b.size()) ;
+        AmieB200Shim::to_device_order(*perm, stride, b, bp) ;
+        if(x0.size() == b.size()) AmieB200Shim::to_device_order(*perm, stride, x0, x0p) ;   // any other size is ignored (:21-24)
+        ret = amie_b200_bicgstab(ctx, &bp[0], x0p.size() ? &x0p[0] : nullptr, x0p.size(), kind, epsilon, maxit, &xp[0], &n, &err) ;
+        if(ret >= 0) AmieB200Shim::from_device_order(*perm, stride, xp, x) ;
+    }
+    else
+        ret = amie_b200_bicgstab(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, epsilon, maxit, &x[0], &n, &err) ;
     if(ret < 0)
     {
         std::cerr << "amie_b200: bicgstab: " << amie_b200_last_error(ctx) << std::endl ;

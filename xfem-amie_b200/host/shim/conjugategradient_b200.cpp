@@ -28,13 +28,26 @@ bool ConjugateGradient::solve(const Vector &x0, Preconditionner * precond, const
     if(!ctx)
         return false ;
     const Vector & b = assembly->getForces() ;
-    if(!AmieB200Shim::upload_diagonal(ctx, diagonal, b.size()))
+    if(!AmieB200Shim::upload_diagonal(ctx, diagonal, b.size(), assembly))
         return false ;
     if(x.size() != b.size())
         x.resize(b.size(), 0.) ;
     uint64_t n = 0 ;
     double err = 0, rho = 0 ;
-    int ret = amie_b200_pcg(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, eps, maxit, nssor,
+    int ret ;
+    if(const std::vector<uint32_t> * perm = AmieB200Shim::permutation_for(assembly))
+    {
+        // the device holds the renumbered matrix (AMIE_B200_RENUMBER): b, x0 in, x out across the permutation
+        const size_t stride = b.size()/perm->size() ;
+        Vector bp, x0p, xp(0., b.size()) ;
+        AmieB200Shim::to_device_order(*perm, stride, b, bp) ;
+        if(x0.size()) AmieB200Shim::to_device_order(*perm, stride, x0, x0p) ;
+        ret = amie_b200_pcg(ctx, &bp[0], x0p.size() ? &x0p[0] : nullptr, x0p.size(), kind, eps, maxit, nssor,
+                            0, 0, &xp[0], &n, &err, &rho) ;
+        if(ret >= 0) AmieB200Shim::from_device_order(*perm, stride, xp, x) ;
+    }
+    else
+        ret = amie_b200_pcg(ctx, &b[0], x0.size() ? &x0[0] : nullptr, x0.size(), kind, eps, maxit, nssor,
                             rowstart, colstart, &x[0], &n, &err, &rho) ;
     nit = n ;
     if(ret == AMIE_B200_ERR_NAN)
