@@ -11,6 +11,8 @@ done
 # 2. the rows next to the solve: defaults vs prepared variants (same bits, times)
 timeout 200 python tools/probe_next_rows.py > gpurun_out/r02_probe_next_rows.jsonl 2> gpurun_out/r02_probe_next_rows.err
 cat gpurun_out/r02_probe_next_rows.jsonl
+timeout 300 python tools/probe_renumber.py 96 > gpurun_out/r02_probe_renumber.json 2> gpurun_out/r02_probe_renumber.err
+cat gpurun_out/r02_probe_renumber.json
 # 3. one full capture per kernel of those rows (the assembly part of the probe only: -k filters, -c counts MATCHING launches)
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_assemble_gather|k_dirichlet" -c 20 \
     -o gpurun_out/r02_prof_assembly python tools/probe_next_rows.py assembly > gpurun_out/r02_prof_assembly.log 2>&1
