@@ -1,7 +1,7 @@
 #!/bin/bash
-# First GPU pass of round 2 (ONE GPU, ~12 min): everything written after round 1's GPU budget was spent gets its first
+# First GPU pass of round 2 (ONE GPU, ~20 min): everything written after round 1's GPU budget was spent gets its first
 # run on hardware, then the probes and captures that decide which prepared variants become defaults.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_pass_r02.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_pass_r02.sh'      (about 20 min of box time)
 mkdir -p gpurun_out
 # 1. the GPU tests that have not run on a B200 yet, one file at a time so that one failure does not hide the others
 for f in precond sequence variants recovery; do
