@@ -16,6 +16,13 @@ PRECOND = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pr
 X_TOL, NIT_TOL = 1e-8, 2
 
 
+def nit_tol(kind, ref_nit):
+    """+-2 iterations as on the Jacobi path, except for InverseDiagonalSquared / InverseLumpedDiagonal, whose iteration
+    count the reference itself moves by a few when only its thread count changes (S3-hex-12: 427, 429, 427, 428 at
+    1, 3, 7, 16 threads): 2 % there."""
+    return NIT_TOL if kind == 4 else max(NIT_TOL, int(0.02 * ref_nit))
+
+
 def assembly_of(pkg, S):
     return pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
 
@@ -61,7 +68,7 @@ def test_against_reference_precond_golden(pkg, path):
         cg = pkg.ConjugateGradient(asm)
         cg.nssor = 32
         assert cg.solve(None, P, 1e-10, -1)
-        assert abs(int(cg.nit) - int(g[f"cg{kind}_nit"])) <= NIT_TOL, (kind, cg.nit, int(g[f"cg{kind}_nit"]))
+        assert abs(int(cg.nit) - int(g[f"cg{kind}_nit"])) <= nit_tol(kind, int(g[f"cg{kind}_nit"])), (kind, cg.nit, int(g[f"cg{kind}_nit"]))
         assert rel_l2(cg.x, g[f"cg{kind}_x"]) <= X_TOL, kind
         bi = pkg.BiConjugateGradientStabilized(asm)
         assert bi.solve(None, P, 1e-10, -1) == bool(g[f"bicg{kind}_ok"])
@@ -81,7 +88,7 @@ def test_pcg_and_bicgstab_with_diagonal_preconditioners(pkg, ol, systems, preset
         cg = pkg.ConjugateGradient(asm)
         cg.nssor = 32
         assert cg.solve(None, P, 1e-10, -1) == bool(ret)
-        assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (kind, cg.nit, info.nit)
+        assert abs(int(cg.nit) - int(info.nit)) <= nit_tol(kind, info.nit), (kind, cg.nit, info.nit)
         assert rel_l2(cg.x, x_ref) <= X_TOL, kind
         ret, x_ref, info = ol.oracle_bicgstab(S, precond=kind, diag=ud)
         bi = pkg.BiConjugateGradientStabilized(asm)
@@ -112,7 +119,7 @@ def test_lumped_diagonal_solves_and_value_updates(pkg, ol):
             cg = pkg.ConjugateGradient(asm)
             cg.nssor = 32
             assert cg.solve(None, precond_object(pkg, kind, None), 1e-10, -1) == bool(ret)
-            assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL and rel_l2(cg.x, x_ref) <= X_TOL, (scale, kind)
+            assert abs(int(cg.nit) - int(info.nit)) <= nit_tol(kind, info.nit) and rel_l2(cg.x, x_ref) <= X_TOL, (scale, kind)
     asm.close()
 
 
