@@ -70,24 +70,32 @@ int amie_b200_permute_structure(uint64_t nb, const uint32_t * row_size, const ui
         if(perm[i] >= nb || inv[perm[i]] != 0xffffffffu) return AMIE_B200_ERR_ARG ;
         inv[perm[i]] = (uint32_t)i ;
     }
-    uint64_t pos = 0 ;
-    std::vector<std::pair<uint32_t, uint32_t> > row ;          // (new column, old block)
+    for(uint64_t k = 0 ; k < acc[nb] ; k++) if(column_index[k] >= nb) return AMIE_B200_ERR_ARG ;
+    // offsets of the new rows, then every row on its own (rows are independent: OpenMP over them)
+    std::vector<uint64_t> accn(nb+1, 0) ;
     for(uint64_t r = 0 ; r < nb ; r++)
     {
-        const uint32_t old = inv[r] ;
-        row_size_out[r] = row_size[old] ;
-        row.clear() ;
-        for(uint64_t k = acc[old] ; k < acc[old+1] ; k++)
+        row_size_out[r] = row_size[inv[r]] ;
+        accn[r+1] = accn[r]+row_size_out[r] ;
+    }
+    #pragma omp parallel
+    {
+        std::vector<std::pair<uint32_t, uint32_t> > row ;      // (new column, old block)
+        #pragma omp for schedule(dynamic, 4096)
+        for(int64_t r = 0 ; r < (int64_t)nb ; r++)
         {
-            if(column_index[k] >= nb) return AMIE_B200_ERR_ARG ;
-            row.push_back(std::make_pair(perm[column_index[k]], (uint32_t)k)) ;
-        }
-        std::sort(row.begin(), row.end()) ;
-        for(const auto & e : row)
-        {
-            column_index_out[pos] = e.first ;
-            block_from_out[pos] = e.second ;
-            pos++ ;
+            const uint32_t old = inv[r] ;
+            row.clear() ;
+            for(uint64_t k = acc[old] ; k < acc[old+1] ; k++)
+                row.push_back(std::make_pair(perm[column_index[k]], (uint32_t)k)) ;
+            std::sort(row.begin(), row.end()) ;
+            uint64_t pos = accn[r] ;
+            for(const auto & e : row)
+            {
+                column_index_out[pos] = e.first ;
+                block_from_out[pos] = e.second ;
+                pos++ ;
+            }
         }
     }
     return AMIE_B200_OK ;
