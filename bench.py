@@ -116,14 +116,22 @@ def cpu_reference_rate(pkg, n_cpu, threads=0):
         cores = threads or len(os.sched_getaffinity(0)) or ol.ref_max_threads()
         ok, x, nit, wall, _ = ol.ref_cg(S, nssor=32, nthreads=cores)
         kind = "reference"
+        # the reference's own SpMV, assign(y, A*x), 20 launches: GB/s by the algorithmic bytes
+        # every roofline here uses, and by the bytes of the reference's padded layout
+        _, spmv_s = ol.ref_spmv(S, b, mode=0, nthreads=cores, reps=20)
+        st, cl = S.stride, S.stride + S.stride % 2
+        spmv = {"ms": 1e3 * spmv_s,
+                "gbs_algorithmic": (S.nnzb * (8 * st * st + 4) + 4 * (S.nb + 1) + 16 * S.n) / spmv_s / 1e9,
+                "gbs_padded_layout": (S.nnzb * (8 * st * cl + 4) + 8 * S.nb + 16 * S.n) / spmv_s / 1e9}
     else:
         cores = 1
         t0 = time.time()
         ok, x, info = ol.oracle_cg(S, nssor=32)
         wall, nit = time.time() - t0, info.nit
         kind = "port"
+        spmv = None
     return dict(dof_iter_per_s=S.n * nit / wall, it_per_s=nit / wall, nit=int(nit), wall=wall, cores=int(cores),
-                kind=kind, n=n_cpu, ndof=S.n, converged=bool(ok))
+                kind=kind, n=n_cpu, ndof=S.n, converged=bool(ok), spmv=spmv)
 
 
 def run_reference_arm(args, pkg, rank):
@@ -148,7 +156,7 @@ def run_reference_arm(args, pkg, rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"S3-hex-{args.n}", "ndof": N_work, "eps": 1e-10, "nssor": 32, "maxit": -1},
             "dof_iter_per_s": dof_it,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample, "spmv": r["spmv"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -269,7 +277,7 @@ def main():
     if not args.no_cpu:
         r = cpu_reference_rate(pkg, args.cpu_n)
         cpu = {"value": r["dof_iter_per_s"] / N, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-               "dof_iter_per_s": r["dof_iter_per_s"],
+               "dof_iter_per_s": r["dof_iter_per_s"], "spmv": r["spmv"],
                "sample": f"one full ConjugateGradient::solve of S3-hex-{r['n']} ({r['ndof']} DOF, {r['nit']} it, {r['wall']:.1f} s); "
                          f"DOF*iter/s scaled by the DOF ratio to this workload ({N} DOF)"}
 
