@@ -300,7 +300,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": (("k_spmv_s3_rt<DOT_NONE> (q = A p; p.q as a separate pass: AMIE_B200_SPLIT_DOT)" if SPLIT_DOT else
-                                                          "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)") if s == 3 else "k_spmv_s2<DOT_YX>"),
+                                                          "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)") if s == 3 else "k_spmv_s2_rt<DOT_YX> (row-thread TMA pipeline, 2x2 blocks)"),
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "peak_source": peak_src},
             "e2e": e2e, "cpu_baseline": cpu}

@@ -24,3 +24,8 @@ tail -c 600 gpurun_out/r02_bench_1gpu.json
 # 5. A/B: p.q as its own pass after a plain SpMV (the fused form costs ~8 % of the SpMV, a pass over p and q ~2 %)
 AMIE_B200_SPLIT_DOT=1 timeout 600 python bench.py --no-cpu --no-e2e > gpurun_out/r02_bench_1gpu_split_dot.json 2> gpurun_out/r02_bench_1gpu_split_dot.err
 tail -c 600 gpurun_out/r02_bench_1gpu_split_dot.json
+# 6. the other shapes of BASELINE.json's configs as bench lines (tetrahedra: 15 blocks per row; 2D: 2x2 blocks)
+timeout 400 python bench.py --preset S3-tet --mesh-n 256 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_bench_S3tet256.json 2> gpurun_out/r02_bench_S3tet256.err
+tail -c 400 gpurun_out/r02_bench_S3tet256.json
+timeout 600 python bench.py --preset S2-tri --mesh-n 4096 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02_bench_S2tri4096.json 2> gpurun_out/r02_bench_S2tri4096.err
+tail -c 400 gpurun_out/r02_bench_S2tri4096.json
