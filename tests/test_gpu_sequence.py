@@ -178,3 +178,45 @@ def test_featuretree_step_with_renumbered_device_matrix(tmp_path, monkeypatch, m
     loose = d > 1e-7 * np.abs(u_ref).max()          # the rounding-sensitive DOFs of the 3D case (tests/test_gpu_e2e.py)
     assert loose.sum() <= (0 if mode == "2d" else 24)
     assert rel_l2(u_gpu[~loose], u_ref[~loose]) <= 1e-8
+
+
+def test_a_whole_step_without_host_vectors(pkg, ol):
+    """INTEGRATION.md section 6 on the 2D FeatureTree run of the fixtures: elements -> assemble -> eliminate -> cgsolve
+    with the history in HBM -> strains / stresses from the resident solution.  Only the elementary matrices and the
+    multipliers go in, only the fields come out; neither the matrix nor x0 nor x crosses PCIe.  The device-assembled
+    matrix and forces equal AMIE's bit for bit, the fields equal ElementState::getField applied to the downloaded x
+    bit for bit, and they match the fields AMIE itself computed from its own solve to the solvers' tolerance."""
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    A = np.load(os.path.join(golden, "AMIE-2d-s20-assembly.npz"))
+    F = np.load(os.path.join(golden, "AMIE-2d-s20-fields.npz"))
+    s, nb = int(A["stride"]), int(A["nb"])
+    assert np.array_equal(A["elem_ids"], F["ids"])                      # the two fixtures are one FeatureTree run
+    asm = pkg.Assembly(None, None, device=0)
+    asm.nssor = 32
+    asm.set_structure_only(s, A["row_size"], A["column_index"])
+    asm.set_elements(A["elem_ids"])
+    asm.set_element_kinematics(s, F["ids"], F["dshape"], F["jinv"])
+    asm.set_element_behaviour(F["tensors"], F["imposed_strain"], F["imposed_stress"], F["tensor_of_elem"])
+    for step in range(3):                                              # history: none -> [0, x] (x0 = 2x) -> [x, x] (x0 = x)
+        asm.update_elements(0, A["elem_ke"], A["scales"])
+        asm.assemble()
+        asm.upload_rhs(np.zeros(nb * s))
+        asm.set_boundary_conditions(A["fix_ids"], A["fix_values"])
+        ok, nit, err, rho = asm.cgsolve_resident()
+        assert ok
+        tot, mech, sig = asm.element_fields()                          # resident x
+        if step == 0:
+            nit0 = nit
+    assert nit < nit0 // 2                                             # third step: x0 = x + (x - x), the answer is already there
+    rs, ci, arr, f = asm.download_matrix()
+    assert np.array_equal(arr, A["array_post"]) and np.array_equal(f, A["forces_post"])
+    x = asm.download_x()
+    want = ol.oracle_element_fields(s, F["ids"], F["dshape"], F["jinv"], x, F["tensors"], F["imposed_strain"],
+                                    F["imposed_stress"], F["tensor_of_elem"])
+    for a, b in zip((tot, mech, sig), want):
+        assert same_bits(a, b)
+    assert rel_l2(x, F["u"]) <= 1e-8
+    assert rel_l2(tot.reshape(-1), F["total_strain"].reshape(-1)) <= 1e-7
+    assert rel_l2(sig.reshape(-1), F["real_stress"].reshape(-1)) <= 1e-7
+    asm.close()
