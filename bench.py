@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("AMIE_BENCH_CPU_N", 64)), help="size of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--spmv-variant", type=int, default=0, help="kernel selection for A/B runs (option spmv_variant; 0 = the shipped default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -208,6 +209,8 @@ def main():
     syn.to_device(asm)
     gen_s = time.time() - t0
     asm.set_option("time_spmv", 1)
+    if args.spmv_variant:
+        asm.set_option("spmv_variant", args.spmv_variant)
     st = asm.stats()
     N, nb, nnzb, s = st.ndof, st.nb, st.nnzb, st.stride
     algo_bytes = st.spmv_algorithmic_bytes

@@ -1,0 +1,203 @@
+"""ONE context over several GPUs, driven from one caller thread: amie_b200_create(devices, ndev > 1) (csrc/group.cu).
+
+The reference's caller is a single thread of a single process (Assembly::cgsolve, solvers/assembly.cpp:1841-1850); a
+group context keeps that shape -- global host arrays in and out through the usual C-ABI calls -- and partitions the
+block rows inside the library.  Every part runs the per-rank code of csrc/dist.cu (interior SpMV overlapped with peer
+halo pushes, mailbox reductions, identical loop decisions everywhere).
+
+`devices` may name the SAME ordinal several times: the parts then live side by side on one GPU, with the same kernels,
+the same halo pushes and device-side flags.  That is how the whole multi-part path is covered on a one-GPU box; with
+two or more GPUs the same tests also run across distinct devices (NVLink peer stores).
+
+Bars as everywhere (BASELINE.json north_star): PCG iteration count within +-2 of the reference, x within 1e-8 relative
+L2; SpMV at 1e-13 relative; BiCGStab on convergence and solution error.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-8
+NIT_TOL = 2
+SPMV_TOL = 1e-13
+
+
+def device_sets():
+    import torch
+    n = torch.cuda.device_count()
+    sets = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        sets += [[0, 1]]
+    if n >= 4:
+        sets += [[0, 1, 2, 3]]
+    if n >= 8:
+        sets += [list(range(8))]
+    return sets
+
+
+def pytest_generate_tests(metafunc):
+    if "devices" in metafunc.fixturenames:
+        try:
+            sets = device_sets()
+        except Exception:
+            sets = [[0, 0]]
+        metafunc.parametrize("devices", sets, ids=["dev" + "".join(map(str, s)) for s in sets])
+
+
+def group_assembly(pkg, S, devices):
+    return pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, devices=devices)
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 14), ("S3-tet", 12), ("S2-tri", 40), ("ASR-hex", 12)])
+def test_group_pcg_and_bicgstab_parity(pkg, ol, systems, devices, preset, n):
+    S = systems(preset, n)
+    asm = group_assembly(pkg, S, devices)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+    st = asm.stats()
+    assert st.ndof == S.n and st.nnzb == S.column_index.size and st.iterations == cg.nit
+    # same matrix, second solve from a warm start shorter than N (conjugategradient.cpp:95-104): values stay resident
+    x0 = x_ref[:S.n // 2].copy()
+    ret2, x_ref2, info2 = ol.oracle_cg(S, x0=x0, nssor=32)
+    ok2 = cg.solve(x0, None, 1e-10, -1)
+    assert ok2 == bool(ret2) and abs(int(cg.nit) - int(info2.nit)) <= NIT_TOL
+    assert rel_l2(cg.x, x_ref2) <= X_TOL
+    # BiCGStab on the same context
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    okb = bi.solve(None, None, 1e-10, -1)
+    retb, xb_ref, _ = ol.oracle_bicgstab(S)
+    assert okb == bool(retb) and rel_l2(bi.x, xb_ref) <= X_TOL
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 12), ("S2-tri", 30)])
+def test_group_spmv_modes_residual_diagonal(pkg, ol, systems, devices, preset, n):
+    S = systems(preset, n)
+    asm = group_assembly(pkg, S, devices)
+    v = np.random.default_rng(11).standard_normal(S.n)
+    scale = np.abs(S.to_scipy()).dot(np.abs(v)).max()
+    assert np.abs(asm.spmv(v) - ol.oracle_assign(S, v)).max() <= SPMV_TOL * scale
+    assert np.abs(asm.spmv(v, minus_b=S.b) - ol.oracle_assign(S, v, S.b)).max() <= SPMV_TOL * (scale + np.abs(S.b).max())
+    # rowstart / colstart cut through the partition at different places: inside part 0, on a part boundary's far side
+    for frac in (5, 2):
+        rs = S.stride * (S.nb // frac)
+        y = asm.spmv(v, minus_b=S.b, rowstart=rs, colstart=rs)
+        assert not y[:rs].any()
+        assert np.abs(y - ol.oracle_assign(S, v, S.b, rs, rs)).max() <= SPMV_TOL * (scale + np.abs(S.b).max())
+        y = asm.spmv(v, rowstart=0, colstart=rs)
+        assert np.abs(y - ol.oracle_assign(S, v, None, 0, rs)).max() <= SPMV_TOL * scale
+    u = np.random.default_rng(4).standard_normal(S.n)
+    r, nrm = asm.residual(u)
+    ro = ol.oracle_spmv_serial(S, u, S.b)
+    assert np.abs(r - ro).max() <= 1e-13 * np.abs(ro).max()
+    assert nrm == pytest.approx(np.linalg.norm(ro), rel=1e-12)
+    assert np.array_equal(asm.inverse_diagonal(), ol.oracle_inverse_diagonal(S))
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n,frac", [("S3-hex", 12, 4), ("S2-tri", 40, 3), ("S2-tri", 40, 2)])
+def test_group_pcg_rowstart(pkg, ol, systems, devices, preset, n, frac):
+    """rowstart = colstart > 0 (space-time planes, solvers/assembly.cpp:327-343) on a partitioned matrix: the cut falls
+    inside one part, the parts in front of it own no active row at all."""
+    S = systems(preset, n)
+    asm = group_assembly(pkg, S, devices)
+    rs = S.stride * (S.nb // frac)
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32, rowstart=rs, colstart=rs)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor, cg.rowstart, cg.colstart = 32, rs, rs
+    ok = cg.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret)
+    assert abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+    assert np.array_equal(cg.x[:rs], S.b[:rs])
+    asm.close()
+
+
+def test_group_resident_sequence_and_generator(pkg, ol, systems, devices):
+    """The device-resident calls and the generator on a group: synth_to_device == uploaded host arrays, bit for bit;
+    cgsolve_resident keeps displacementHistory per part (extrapolation and history shift are per entry)."""
+    preset, n = "S3-hex", 14
+    S = systems(preset, n)
+    syn = pkg.Synth(preset, n)
+    a1 = group_assembly(pkg, S, devices)
+    a1.sync_matrix()
+    a1.upload_rhs(S.b)
+    a1.upload_x0(None)
+    ok1, nit1, _, _ = a1.pcg_resident(nssor=32)
+    x1 = a1.download_x()
+    a2 = pkg.Assembly(devices=devices)
+    syn.to_device(a2)
+    a2.upload_x0(None)
+    ok2, nit2, _, _ = a2.pcg_resident(nssor=32)
+    x2 = a2.download_x()
+    assert ok1 and ok2 and nit1 == nit2 and np.array_equal(x1, x2)
+    assert np.array_equal(a2.download_rhs(), S.b)
+    # load-step loop without host vectors against the single-device context doing the same
+    ref = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+    ref.sync_matrix()
+    for step, f in enumerate((1.0, 1.5, 2.25)):
+        for a in (a2, ref):
+            a.upload_rhs(S.b * f)
+        okg, nitg, _, _ = a2.cgsolve_resident()
+        okr, nitr, _, _ = ref.cgsolve_resident()
+        assert okg == okr and abs(int(nitg) - int(nitr)) <= NIT_TOL, (step, nitg, nitr)
+        assert rel_l2(a2.download_x(), ref.download_x()) <= X_TOL
+    x0g, caseg = a2.extrapolate()
+    x0r, caser = ref.extrapolate()
+    assert caseg == caser == 1 and rel_l2(x0g, x0r) <= 1e-7
+    for a in (a1, a2, ref):
+        a.close()
+
+
+def test_group_matches_single_device_iterates(pkg, systems, devices):
+    """Same system, a fixed number of iterations: the partitioned iterate equals the single-device one up to the
+    rounding of the dot products (the parts sum their rows in another order)."""
+    S = systems("S3-tet", 14)
+    one = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+    grp = group_assembly(pkg, S, devices)
+    xs = []
+    for a in (one, grp):
+        cg = pkg.ConjugateGradient(a)
+        cg.nssor = 32
+        cg.solve(None, None, 1e-10, 40)
+        assert cg.nit == 40
+        xs.append(cg.x.copy())
+        a.close()
+    assert rel_l2(xs[1], xs[0]) <= 1e-9
+
+
+def test_group_errors(pkg, systems):
+    S = systems("S3-hex", 6)
+    L = pkg.lib()
+    # a device that does not exist
+    import ctypes
+    bad = (ctypes.c_int * 2)(0, 99)
+    assert not L.amie_b200_create(bad, 2)
+    assert b"no such CUDA device" in L.amie_b200_global_error()
+    asm = group_assembly(pkg, S, [0, 0])
+    with pytest.raises(pkg.AmieB200Error) as e:
+        asm.upload_rhs(S.b)                 # before set_structure
+    assert e.value.code == pkg.ERR_STATE
+    asm.sync_matrix()
+    with pytest.raises(pkg.AmieB200Error) as e:
+        asm.download_matrix()
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    with pytest.raises(pkg.AmieB200Error) as e:
+        asm.set_elements(np.zeros((1, 8), np.uint32))
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    asm.close()
+    # strides other than 2 and 3 stay on one device
+    from conftest import random_spd_blocks
+    rs, ci, arr, b = random_spd_blocks(4, 10, 3)
+    a4 = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(rs, ci, 4, arr), b, devices=[0, 0])
+    with pytest.raises(pkg.AmieB200Error) as e:
+        a4.sync_matrix()
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    a4.close()

@@ -152,8 +152,10 @@ class Assembly:
     (nssor, rowstart, colstart, epsilon; solvers/assembly.cpp:1829-1850).
     Owns the device context (one per Assembly)."""
 
-    def __init__(self, matrix=None, forces=None, device=None, renumber=False):
-        """renumber=True: the device works on the matrix renumbered by reverse Cuthill-McKee (the mesher's numbering has
+    def __init__(self, matrix=None, forces=None, device=None, renumber=False, devices=None):
+        """devices=[0, 1, ...]: ONE context over several GPUs (amie_b200_create(devices, ndev > 1)): the same calls with
+        the same global host arrays, the block rows partitioned inside the library (csrc/group.cu).
+        renumber=True: the device works on the matrix renumbered by reverse Cuthill-McKee (the mesher's numbering has
         no locality); this object keeps the caller's numbering and permutes b, x0, x and the other host vectors at the
         boundary, as host/shim does under AMIE_B200_RENUMBER=1.  The *_resident calls, the assembly and field rows then
         see the DEVICE numbering (use `self.perm`: perm[old node] = new node)."""
@@ -167,6 +169,7 @@ class Assembly:
         self.colstart = 0
         self.epsilon = default_solver_precision
         self._device = device
+        self._devices = None if devices is None else [int(d) for d in devices]
         self._ctx = None
         self._structure_key = None
         self._values_dirty = True
@@ -176,7 +179,10 @@ class Assembly:
     def ctx(self):
         if self._ctx is None:
             L = lib()
-            if self._device is None:
+            if self._devices is not None:
+                d = (ctypes.c_int * len(self._devices))(*self._devices)
+                h = L.amie_b200_create(d, len(self._devices))
+            elif self._device is None:
                 h = L.amie_b200_create(None, 0)
             else:
                 d = (ctypes.c_int * 1)(int(self._device))

@@ -2,6 +2,7 @@
 // The solvers are in solve_cg.cu and solve_bicg.cu.  No CPU fallback anywhere: every compute
 // entry point needs a CUDA device and reports AMIE_B200_ERR_CUDA without one.
 #include "launch.cuh"
+#include "group.h"
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
@@ -182,7 +183,23 @@ const char * amie_b200_last_error(const amie_b200_ctx * ctx) { return ctx ? ctx-
 
 amie_b200_ctx * amie_b200_create(const int * devices, int ndev)
 {
-    if(ndev > 1) { g_error = "amie_b200_create: ndev > 1 needs the distributed entry points (one context per device)" ; return nullptr ; }
+    // env AMIE_B200_DEVICES="0,1,2,3": what a host that cannot pass arguments (the drop-in shim) uses
+    std::vector<int> env_devs ;
+    if((!devices || ndev < 1))
+        if(const char * e = getenv("AMIE_B200_DEVICES"))
+        {
+            for(const char * q = e ; *q ; )
+            {
+                char * end = nullptr ;
+                long v = strtol(q, &end, 10) ;
+                if(end == q) break ;
+                env_devs.push_back((int)v) ;
+                q = (*end == ',') ? end+1 : end ;
+                if(*end && *end != ',') break ;
+            }
+            if(!env_devs.empty()) { devices = env_devs.data() ; ndev = (int)env_devs.size() ; }
+        }
+    if(ndev > 1) return group_create(devices, ndev, g_error) ;
     int dev = 0 ;
     if(devices && ndev == 1) dev = devices[0] ;
     else if(const char * e = getenv("AMIE_B200_DEVICE")) dev = atoi(e) ;
@@ -218,6 +235,7 @@ amie_b200_ctx * amie_b200_create(const int * devices, int ndev)
 void amie_b200_destroy(amie_b200_ctx * ctx)
 {
     if(!ctx) return ;
+    if(ctx->group) { group_destroy(ctx) ; return ; }
     cudaSetDevice(ctx->device) ;
     cudaStreamSynchronize(ctx->stream) ;
     dist_destroy(ctx) ;
@@ -240,6 +258,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
 int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
 {
     if(!ctx || !key) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_set_option(ctx, key, value) ;
     std::string k(key) ;
     if(k == "time_spmv")
     {
@@ -266,6 +285,7 @@ int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
 int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
 {
     if(!ctx || !out) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_get_stats(ctx, out) ;
     *out = ctx->stats ;
     out->stride = ctx->S ; out->nb = ctx->nb ; out->nnzb = ctx->nnzb ; out->ndof = ctx->N ;
     out->spmv_algorithmic_bytes = ctx->nnzb*(uint64_t)(8*ctx->S*ctx->S+4)+4*(ctx->nb+1)+16*ctx->N ;
@@ -276,6 +296,7 @@ int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
 int amie_b200_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32_t * row_size,
                             const uint32_t * column_index, uint64_t nnzb)
 {
+    if(ctx && ctx->group) return group_set_structure(ctx, stride, nb, row_size, column_index, nnzb) ;
     if(ctx && ctx->dist) { ctx->set_error("set_structure on a distributed context: use amie_b200_dist_set_structure") ; return AMIE_B200_ERR_STATE ; }
     return ctx_set_structure(ctx, stride, nb, row_size, column_index, nnzb, nb) ;
 }
@@ -340,6 +361,7 @@ extern "C" {
 int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
 {
     if(!ctx || (!array && ctx->nnzb)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_set_values(ctx, array) ;
     if(!ctx->have_structure) { ctx->set_error("set_values before set_structure") ; return AMIE_B200_ERR_STATE ; }
     double t0 = wall_now() ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
@@ -400,6 +422,7 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
 int amie_b200_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_unsupported(ctx, "set_block_map") ;
     if(!ctx->have_structure) { ctx->set_error("set_block_map before set_structure") ; return AMIE_B200_ERR_STATE ; }
     if(ctx->dist) { ctx->set_error("set_block_map: not available on a row-partitioned context") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
@@ -421,6 +444,12 @@ int amie_b200_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to)
 int amie_b200_upload_rhs(amie_b200_ctx * ctx, const double * b)
 {
     if(!ctx || !b) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+    {
+        int rc = group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_upload_rhs(c, b+d0) ; }) ;
+        if(!rc) ctx->have_rhs = true ;
+        return rc ;
+    }
     if(!ctx->have_structure) { ctx->set_error("upload_rhs before set_structure") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->b, b, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
@@ -432,6 +461,12 @@ int amie_b200_upload_rhs(amie_b200_ctx * ctx, const double * b)
 int amie_b200_upload_x0(amie_b200_ctx * ctx, const double * x0, uint64_t nx0)
 {
     if(!ctx || (!x0 && nx0)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+        return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t nd)
+        {
+            const uint64_t n0 = nx0 > d0 ? std::min<uint64_t>(nx0-d0, nd) : 0 ;
+            return amie_b200_upload_x0(c, n0 ? x0+d0 : nullptr, n0) ;
+        }) ;
     if(!ctx->have_structure) { ctx->set_error("upload_x0 before set_structure") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->x, 0, ctx->vec_len*sizeof(double), ctx->stream)) ;
@@ -444,6 +479,7 @@ int amie_b200_upload_x0(amie_b200_ctx * ctx, const double * x0, uint64_t nx0)
 int amie_b200_download_x(amie_b200_ctx * ctx, double * x_out)
 {
     if(!ctx || !x_out) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_download_x(c, x_out+d0) ; }) ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(x_out, ctx->x, ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
@@ -453,6 +489,7 @@ int amie_b200_download_x(amie_b200_ctx * ctx, double * x_out)
 int amie_b200_download_rhs(amie_b200_ctx * ctx, double * b_out)
 {
     if(!ctx || !b_out) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_download_rhs(c, b_out+d0) ; }) ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(b_out, ctx->b, ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
@@ -462,6 +499,7 @@ int amie_b200_download_rhs(amie_b200_ctx * ctx, double * b_out)
 int amie_b200_download_vector(amie_b200_ctx * ctx, int which, double * out)
 {
     if(!ctx || !out || which < 0 || which > 3) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_download_vector(c, which, out+d0) ; }) ;
     const double * v[] = { ctx->x, ctx->q, ctx->r, ctx->p } ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(out, v[which], ctx->N*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
@@ -472,6 +510,7 @@ int amie_b200_download_vector(amie_b200_ctx * ctx, int which, double * out)
 int amie_b200_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out, double * array_padded_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_unsupported(ctx, "download_matrix") ;
     if(!ctx->have_structure) { ctx->set_error("download_matrix: no matrix") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     if(row_size_out)
@@ -499,6 +538,7 @@ int amie_b200_pcg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, in
                            uint64_t rowstart, uint64_t colstart, uint64_t * nit_out, double * err_out, double * rho_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_solve(ctx, false, true, nullptr, nullptr, 0, precond_kind, eps, maxit, nssor, rowstart, colstart, nullptr, nit_out, err_out, rho_out) ;
     if(!ctx->have_values || !ctx->have_rhs) { ctx->set_error("pcg: matrix values / rhs not on the device") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     return solve_cg_resident(ctx, precond_kind, eps, maxit, nssor, rowstart, colstart, nit_out, err_out, rho_out) ;
@@ -507,6 +547,7 @@ int amie_b200_pcg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, in
 int amie_b200_bicgstab_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t * nit_out, double * err_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_solve(ctx, true, true, nullptr, nullptr, 0, precond_kind, eps, maxit, 0, 0, 0, nullptr, nit_out, err_out, nullptr) ;
     if(!ctx->have_values || !ctx->have_rhs) { ctx->set_error("bicgstab: matrix values / rhs not on the device") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     return solve_bicg_resident(ctx, precond_kind, eps, maxit, nit_out, err_out) ;
@@ -553,6 +594,7 @@ int amie_b200_pcg(amie_b200_ctx * ctx, const double * b, const double * x0, uint
                   double * x_out, uint64_t * nit_out, double * err_out, double * rho_out)
 {
     if(!ctx || !b || !x_out || (!x0 && nx0)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_solve(ctx, false, false, b, x0, nx0, precond_kind, eps, maxit, nssor, rowstart, colstart, x_out, nit_out, err_out, rho_out) ;
     int rc = host_call_prologue(ctx, b, x0, nx0, false) ;
     if(rc) return rc ;
     int ret = solve_cg_resident(ctx, precond_kind, eps, maxit, nssor, rowstart, colstart, nit_out, err_out, rho_out) ;
@@ -565,6 +607,7 @@ int amie_b200_bicgstab(amie_b200_ctx * ctx, const double * b, const double * x0,
                        int precond_kind, double eps, int maxit, double * x_out, uint64_t * nit_out, double * err_out)
 {
     if(!ctx || !b || !x_out || (!x0 && nx0)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_solve(ctx, true, false, b, x0, nx0, precond_kind, eps, maxit, 0, 0, 0, x_out, nit_out, err_out, nullptr) ;
     int rc = host_call_prologue(ctx, b, x0, nx0, true) ;
     if(rc) return rc ;
     int ret = solve_bicg_resident(ctx, precond_kind, eps, maxit, nit_out, err_out) ;
@@ -576,8 +619,11 @@ int amie_b200_bicgstab(amie_b200_ctx * ctx, const double * b, const double * x0,
 int amie_b200_spmv(amie_b200_ctx * ctx, const double * x, const double * b, uint64_t rowstart, uint64_t colstart, double * y_out)
 {
     if(!ctx || !x || !y_out) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+        return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_spmv(c, x+d0, b ? b+d0 : nullptr, rowstart, colstart, y_out+d0) ; }) ;
     if(!ctx->have_values) { ctx->set_error("spmv before set_values") ; return AMIE_B200_ERR_STATE ; }
-    if(rowstart%ctx->S || colstart%ctx->S || rowstart > ctx->N) { ctx->set_error("spmv: rowstart/colstart must be multiples of the stride") ; return AMIE_B200_ERR_ARG ; }
+    if(rowstart%ctx->S || colstart%ctx->S || rowstart > ctx->nb_global*(uint64_t)ctx->S) { ctx->set_error("spmv: rowstart/colstart must be multiples of the stride") ; return AMIE_B200_ERR_ARG ; }
+    if(ctx->dist) rowstart = dist_local_rowstart(ctx, rowstart) ;      // rows local, columns global (dist_spmv)
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->p, x, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
     if(b) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->z, b, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
@@ -596,6 +642,16 @@ int amie_b200_spmv(amie_b200_ctx * ctx, const double * x, const double * b, uint
 int amie_b200_residual(amie_b200_ctx * ctx, const double * u, const double * f, double * r_out, double * norm_out)
 {
     if(!ctx || !u || !f) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+    {
+        double norms[GROUP_MAX] = {} ;
+        int rc = group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t)
+        {
+            return amie_b200_residual(c, u+d0, f+d0, r_out ? r_out+d0 : nullptr, norms+dist_rank(c)) ;
+        }) ;
+        if(!rc && norm_out) *norm_out = norms[0] ;
+        return rc ;
+    }
     if(!ctx->have_values) { ctx->set_error("residual before set_values") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->p, u, ctx->N*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
@@ -618,6 +674,13 @@ int amie_b200_residual(amie_b200_ctx * ctx, const double * u, const double * f, 
 int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double * ms_out)
 {
     if(!ctx || reps < 1) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+    {
+        double ms[GROUP_MAX] = {} ;
+        int rc = group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t, uint64_t) { return amie_b200_spmv_resident(c, reps, variant, ms+dist_rank(c)) ; }) ;
+        if(!rc && ms_out) *ms_out = *std::max_element(ms, ms+GROUP_MAX) ;
+        return rc ;
+    }
     if(!ctx->have_values) { ctx->set_error("spmv before set_values") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int saved = ctx->opt_variant, saved_t = ctx->opt_time_spmv ;
@@ -729,6 +792,7 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
 int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d)
 {
     if(!ctx || !d) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_set_preconditioner_diagonal(c, d+d0) ; }) ;
     if(!ctx->have_structure) { ctx->set_error("set_preconditioner_diagonal before set_structure") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     if(!ctx->user_diag) CUDA_TRY(ctx, cudaMalloc(&ctx->user_diag, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
@@ -741,6 +805,7 @@ int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d)
 int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, double * d_out)
 {
     if(!ctx || !d_out || precond_kind == AMIE_B200_PRECOND_NULL) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_preconditioner_diagonal(c, precond_kind, d_out+d0) ; }) ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int rc = ctx_ensure_dinv(ctx, precond_kind) ;
     if(rc) return rc ;
@@ -752,6 +817,7 @@ int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, dou
 int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out)
 {
     if(!ctx || !d_out) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_inverse_diagonal(c, d_out+d0) ; }) ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int rc = ctx_ensure_dinv(ctx) ;
     if(rc) return rc ;

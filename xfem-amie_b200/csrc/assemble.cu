@@ -78,7 +78,7 @@ uint64_t assembly_map_bytes(const amie_b200_ctx * ctx)
 
 static int require_single(amie_b200_ctx * ctx, const char * what)
 {
-    if(ctx->dist) { ctx->set_error(std::string(what)+": not available on a row-partitioned context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    if(ctx->dist || ctx->group) { ctx->set_error(std::string(what)+": not available on a row-partitioned / multi-device context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     if(!ctx->have_structure) { ctx->set_error(std::string(what)+" before set_structure") ; return AMIE_B200_ERR_STATE ; }
     return AMIE_B200_OK ;
 }

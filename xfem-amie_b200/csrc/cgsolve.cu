@@ -10,7 +10,10 @@
 // term in dxxddb that is identically zero because the history never holds more than two vectors (:1859-1868 keeps
 // size 2), and the NaN scrub of the newest vector (:1793-1794).
 #include "context.h"
+#include "group.h"
+#include "dist.h"
 #include "kernels_history.cuh"
+#include <algorithm>
 
 void history_destroy(amie_b200_ctx * ctx)
 {
@@ -70,7 +73,24 @@ int amie_b200_cgsolve_resident(amie_b200_ctx * ctx, int precond_kind, double eps
                                uint64_t * nit_out, double * err_out, double * rho_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
-    if(ctx->dist) { ctx->set_error("cgsolve_resident: not available on a row-partitioned context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    if(ctx->group)
+    {
+        // extrapolation and history shift are per entry: every device does them on its own rows
+        uint64_t nit[GROUP_MAX] = {} ;
+        double err[GROUP_MAX] = {}, rho[GROUP_MAX] = {} ;
+        int rets[GROUP_MAX] = {} ;
+        int rc = group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t, uint64_t)
+        {
+            const int r = dist_rank(c) ;
+            rets[r] = amie_b200_cgsolve_resident(c, precond_kind, eps, nssor, rowstart, colstart, factor, nit+r, err+r, rho+r) ;
+            return rets[r] < 0 ? rets[r] : 0 ;
+        }) ;
+        if(rc) return rc ;
+        if(nit_out) *nit_out = nit[0] ;
+        if(err_out) *err_out = err[0] ;
+        if(rho_out) *rho_out = rho[0] ;
+        return rets[0] ;
+    }
     if(!ctx->have_structure || !ctx->have_values || !ctx->have_rhs)
     { ctx->set_error("cgsolve_resident needs the matrix (set_values / assemble) and the forces (upload_rhs) on the device") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
@@ -88,6 +108,7 @@ int amie_b200_cgsolve_resident(amie_b200_ctx * ctx, int precond_kind, double eps
 int amie_b200_reset_history(amie_b200_ctx * ctx)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t, uint64_t) { return amie_b200_reset_history(c) ; }) ;
     ctx->hist_count = 0 ;
     return AMIE_B200_OK ;
 }
@@ -95,6 +116,13 @@ int amie_b200_reset_history(amie_b200_ctx * ctx)
 int amie_b200_extrapolate(amie_b200_ctx * ctx, double factor, double * x0_out, int * case_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+    {
+        int cases[GROUP_MAX] = {} ;
+        int rc = group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_extrapolate(c, factor, x0_out ? x0_out+d0 : nullptr, cases+dist_rank(c)) ; }) ;
+        if(!rc && case_out) *case_out = cases[0] ;
+        return rc ;
+    }
     if(!ctx->have_structure) { ctx->set_error("extrapolate before set_structure") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int used = 0 ;
@@ -109,6 +137,7 @@ int amie_b200_extrapolate(amie_b200_ctx * ctx, double factor, double * x0_out, i
 int amie_b200_push_history(amie_b200_ctx * ctx)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t, uint64_t) { return amie_b200_push_history(c) ; }) ;
     if(!ctx->have_structure) { ctx->set_error("push_history before set_structure") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int rc = history_push(ctx) ;

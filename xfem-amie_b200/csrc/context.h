@@ -9,6 +9,7 @@
 struct DistState ;   // dist.cu
 struct AssemblyMap ; // assemble.cu
 struct FieldMap ;    // fields.cu
+struct LocalGroup ;  // group.h
 
 struct amie_b200_ctx
 {
@@ -70,6 +71,7 @@ struct amie_b200_ctx
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll[2] = {nullptr, nullptr} ;
 
     DistState * dist = nullptr ;
+    LocalGroup * group = nullptr ;     // != nullptr: this is the caller-facing context of several devices (group.cu); it holds no device memory itself
     AssemblyMap * amap = nullptr ;     // element -> stored-block gather lists (device-side value assembly)
     FieldMap * fmap = nullptr ;        // element kinematics + behaviours (field recovery after the solve)
 

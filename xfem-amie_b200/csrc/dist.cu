@@ -20,6 +20,7 @@
 #include "launch.cuh"
 #include "synth.h"
 #include "dist.h"
+#include "group.h"
 #include <nccl.h>
 #include <dlfcn.h>
 #include <thrust/device_ptr.h>
@@ -126,6 +127,14 @@ __global__ void k_pack(const double * v, const uint32_t * idx, uint64_t n, doubl
         const uint64_t k = i/S ;
         out[i] = v[(uint64_t)idx[k]*S+(i-k*S)] ;
     }
+}
+
+// a SpMV whose first row range is empty (rowstart beyond the interior rows): red_local = 0 before the others add to it
+__global__ void k_reset_red(KrylovState * st, int check_stop)
+{
+    if(check_stop && st->stop) return ;
+    st->red_local[0] = 0. ;
+    st->red_local[1] = 0. ;
 }
 
 __global__ void k_finalize(KrylovState * st, int kind)
@@ -326,9 +335,52 @@ struct DistState
     std::vector<VecMap> vec_maps ;                   // SpMV input vectors already exchanged
     unsigned int * push_ticket = nullptr ;
     unsigned long long * counters = nullptr ;        // device: executed reductions / halo pushes (never reset)
+
+    // ---- in-process group (group.h): set-up collectives through shared host memory instead of NCCL / cudaIpc
+    LocalGroup * local = nullptr ;
+    std::vector<uint32_t> halo_host ;                // this rank's halo list while the send lists are being built
+    double * cs_save = nullptr ;                     // colstart > 0: the owned entries in front of colstart, parked during a SpMV
+    uint64_t cs_save_len = 0 ;
 } ;
 
+// ---- collectives used at set-up time, on either plumbing -------------------------------------------------------
+#define GROUP_TRY(ctx, ok) do { if(!(ok)) { (ctx)->set_error("group: a collective step was abandoned (another device failed)") ; return AMIE_B200_ERR_STATE ; } } while(0)
+
+// op: 0 min, 1 max
+static int comm_allreduce_scalar(amie_b200_ctx * ctx, double * value, int op)
+{
+    DistState * d = ctx->dist ;
+    if(d->local)
+    {
+        LocalGroup * g = d->local ;
+        g->dbl[d->rank] = *value ;
+        GROUP_TRY(ctx, g->barrier()) ;
+        double m = g->dbl[0] ;
+        for(int r = 1 ; r < d->world ; r++)
+        {
+            const double y = g->dbl[r] ;
+            if(op == 0 ? (y < m) : (y > m || y != y)) m = y ;
+        }
+        GROUP_TRY(ctx, g->barrier()) ;
+        *value = m ;
+        return AMIE_B200_OK ;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d->scratch, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, op == 0 ? ncclMin : ncclMax, d->comm, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(value, d->scratch+1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    return AMIE_B200_OK ;
+}
+
 int dist_world(const amie_b200_ctx * ctx) { return ctx->dist ? ctx->dist->world : 1 ; }
+int dist_rank(const amie_b200_ctx * ctx) { return ctx->dist ? ctx->dist->rank : 0 ; }
+
+uint64_t dist_local_rowstart(const amie_b200_ctx * ctx, uint64_t rowstart_global)
+{
+    const uint64_t base = ctx->row_base*(uint64_t)ctx->S ;
+    if(rowstart_global <= base) return 0 ;
+    return std::min<uint64_t>(rowstart_global-base, ctx->N) ;
+}
 
 void dist_destroy(amie_b200_ctx * ctx)
 {
@@ -341,6 +393,7 @@ void dist_destroy(amie_b200_ctx * ctx)
     if(d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm) ;
     if(d->send_idx) cudaFree(d->send_idx) ;
     if(d->sendbuf) cudaFree(d->sendbuf) ;
+    if(d->cs_save) cudaFree(d->cs_save) ;
     if(d->scratch) cudaFree(d->scratch) ;
     if(d->ev_pack) cudaEventDestroy(d->ev_pack) ;
     if(d->ev_comm) cudaEventDestroy(d->ev_comm) ;
@@ -376,12 +429,7 @@ int dist_finalize(amie_b200_ctx * ctx, int kind)
 
 int dist_allreduce_max(amie_b200_ctx * ctx, double * value)
 {
-    DistState * d = ctx->dist ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(d->scratch, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-    NCCL_TRY(ctx, g_nccl.AllReduce(d->scratch, d->scratch+1, 1, ncclDouble, ncclMax, d->comm, ctx->stream)) ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(value, d->scratch+1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
-    return AMIE_B200_OK ;
+    return comm_allreduce_scalar(ctx, value, 1) ;
 }
 
 int dist_inverse_diagonal(amie_b200_ctx * ctx)
@@ -398,6 +446,17 @@ int dist_inverse_diagonal(amie_b200_ctx * ctx)
 static int ipc_exchange(amie_b200_ctx * ctx, void * mine, bool only_peers, std::vector<void *> & out)
 {
     DistState * d = ctx->dist ;
+    if(d->local)
+    {
+        // one address space, peer access enabled at group creation: the pointers themselves travel
+        LocalGroup * g = d->local ;
+        (void)only_peers ;
+        g->ptr[d->rank] = mine ;
+        GROUP_TRY(ctx, g->barrier()) ;
+        out.assign(g->ptr, g->ptr+d->world) ;
+        GROUP_TRY(ctx, g->barrier()) ;
+        return AMIE_B200_OK ;
+    }
     cudaIpcMemHandle_t h ;
     CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, mine)) ;
     unsigned char * dbuf = nullptr ;
@@ -447,6 +506,22 @@ static int peer_setup(amie_b200_ctx * ctx)
 {
     DistState * d = ctx->dist ;
     d->peer_on = false ;
+    if(d->local)
+    {
+        // the only transport of an in-process group (group_create refused devices without a peer path)
+        int rc = peer_setup_local(ctx) ;
+        double ok = rc == AMIE_B200_OK ? 1. : 0. ;
+        CUDA_TRY(ctx, cudaDeviceSynchronize()) ;           // the memsets above are done before anybody signals
+        int rc2 = comm_allreduce_scalar(ctx, &ok, 0) ;
+        if(rc2) return rc2 ;
+        if(ok < 1.) return rc ? rc : AMIE_B200_ERR_CUDA ;
+        std::vector<void *> out ;
+        if((rc = ipc_exchange(ctx, d->sync, false, out))) return rc ;
+        d->sync_of.resize(d->world) ;
+        for(int r = 0 ; r < d->world ; r++) d->sync_of[r] = static_cast<unsigned char *>(out[r]) ;
+        d->peer_on = true ;
+        return AMIE_B200_OK ;
+    }
     const char * e = getenv("AMIE_B200_TRANSPORT") ;
     const bool want = !(e && std::string(e) == "nccl") && d->world <= PEER_MAX && (int)d->peers.size() <= PEER_MAX ;
     double ok = want ? 1. : 0. ;
@@ -496,14 +571,30 @@ static int peer_vector(amie_b200_ctx * ctx, const double * base, const std::vect
 int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
 {
     DistState * d = ctx->dist ;
-    if(c.rowstart || c.colstart)
-    {
-        ctx->set_error("distributed SpMV: rowstart/colstart are not supported on a row-partitioned context") ;
-        return AMIE_B200_ERR_UNSUPPORTED ;
-    }
     const int S = ctx->S ;
     double * xv = const_cast<double *>(c.x) ;
     const bool dot = c.dot != DOT_NONE ;
+    // c.rowstart is LOCAL (dist_local_rowstart), c.colstart GLOBAL.  Skipping the block columns < colstart is the same
+    // as multiplying by a vector whose entries in front of colstart are zero: every rank parks the owned part of that
+    // prefix, zeroes it for the duration of this SpMV (the halo pushes then carry zeros too) and puts it back.
+    // The local column numbering (owned | halo) is not ascending, so the kernels' lower_bound skip cannot be used.
+    uint64_t cs_local = 0 ;
+    if(c.colstart > d->bounds[d->rank]*S)
+        cs_local = std::min<uint64_t>(c.colstart-d->bounds[d->rank]*S, ctx->N) ;
+    if(cs_local)
+    {
+        if(d->cs_save_len < cs_local)
+        {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+            if(d->cs_save) cudaFree(d->cs_save) ;
+            d->cs_save = nullptr ; d->cs_save_len = 0 ;
+            CUDA_TRY(ctx, cudaMalloc(&d->cs_save, ctx->N*sizeof(double))) ;
+            d->cs_save_len = ctx->N ;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(d->cs_save, xv, cs_local*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
+        CUDA_TRY(ctx, cudaMemsetAsync(xv, 0, cs_local*sizeof(double), ctx->stream)) ;
+    }
+    const uint32_t row_lo = (uint32_t)(c.rowstart/S) ;
     cudaEvent_t e0 = nullptr, e1 = nullptr ;
     if(ctx->opt_time_spmv && ctx->ev_used+2 <= ctx->ev_pool.size())
     {
@@ -556,10 +647,13 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
     }
     int rc ;
     bool first = true ;
+    SpmvCall cl = c ;
+    cl.colstart = 0 ;                                                     // done through the zeroed prefix above
     auto part = [&](uint32_t a, uint32_t b) -> int
     {
+        if(a < row_lo) a = row_lo ;                                       // rows < rowstart keep what they hold
         if(b <= a) return AMIE_B200_OK ;
-        int r = launch_spmv_range(ctx, c, a, b-a, dot ? (first ? FIN_DEFER_SET : FIN_DEFER_ADD) : FIN_STORE) ;
+        int r = launch_spmv_range(ctx, cl, a, b-a, dot ? (first ? FIN_DEFER_SET : FIN_DEFER_ADD) : FIN_STORE) ;
         first = false ;
         return r ;
     } ;
@@ -577,10 +671,17 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
     else if(!d->peers.empty()) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, d->ev_comm, 0)) ;
     if((rc = part(0, d->int_a))) return rc ;                              // boundary rows
     if((rc = part(d->int_b, (uint32_t)ctx->nb))) return rc ;
+    if(dot && first)
+    {
+        // no local row at or after rowstart: this rank adds nothing to the sums
+        k_reset_red<<<1, 1, 0, ctx->stream>>>(ctx->st, c.check_stop) ;
+        ctx->stats.kernel_launches++ ;
+    }
     if(dot && (rc = dist_finalize(ctx, c.finalize))) return rc ;
     // no reduction follows a plain SpMV: a mailbox round keeps a fast neighbour from overwriting this rank's halo
     // tail with its NEXT push while the boundary rows above still read it
     if(!dot && peer) launch_finalize_peer(ctx, FIN_DEFER_SET) ;
+    if(cs_local) CUDA_TRY(ctx, cudaMemcpyAsync(xv, d->cs_save, cs_local*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
     if(e1) cudaEventRecord(e1, ctx->stream) ;
     ctx->stats.spmv_launches++ ;
     if(c.smoothing) ctx->stats.smoothing_spmv++ ;
@@ -624,15 +725,28 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     for(int q = 0 ; q < d->world ; q++) need_off[q+1] = need_off[q]+(uint64_t)need[q] ;
 
     // ---- all ranks learn the whole need matrix; then the lists travel
-    long long * dneed = nullptr, * dall = nullptr ;
-    CUDA_TRY(ctx, cudaMalloc(&dneed, d->world*sizeof(long long))) ;
-    CUDA_TRY(ctx, cudaMalloc(&dall, (size_t)d->world*d->world*sizeof(long long))) ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(dneed, need.data(), d->world*sizeof(long long), cudaMemcpyHostToDevice, st)) ;
-    NCCL_TRY(ctx, g_nccl.AllGather(dneed, dall, d->world, ncclInt64, d->comm, st)) ;
     std::vector<long long> all((size_t)d->world*d->world) ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), dall, all.size()*sizeof(long long), cudaMemcpyDeviceToHost, st)) ;
-    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
-    cudaFree(dneed) ; cudaFree(dall) ;
+    if(d->local)
+    {
+        LocalGroup * g = d->local ;
+        g->ll[d->rank] = need ;
+        d->halo_host = halo ;
+        g->cptr[d->rank] = d ;
+        GROUP_TRY(ctx, g->barrier()) ;
+        for(int i = 0 ; i < d->world ; i++)
+            for(int j = 0 ; j < d->world ; j++) all[(size_t)i*d->world+j] = g->ll[i][j] ;
+    }
+    else
+    {
+        long long * dneed = nullptr, * dall = nullptr ;
+        CUDA_TRY(ctx, cudaMalloc(&dneed, d->world*sizeof(long long))) ;
+        CUDA_TRY(ctx, cudaMalloc(&dall, (size_t)d->world*d->world*sizeof(long long))) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dneed, need.data(), d->world*sizeof(long long), cudaMemcpyHostToDevice, st)) ;
+        NCCL_TRY(ctx, g_nccl.AllGather(dneed, dall, d->world, ncclInt64, d->comm, st)) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), dall, all.size()*sizeof(long long), cudaMemcpyDeviceToHost, st)) ;
+        CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+        cudaFree(dneed) ; cudaFree(dall) ;
+    }
 
     d->need_all = all ;
     d->peers.clear() ;
@@ -650,29 +764,47 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     }
     if(d->send_idx) { cudaFree(d->send_idx) ; d->send_idx = nullptr ; }
     if(d->sendbuf) { cudaFree(d->sendbuf) ; d->sendbuf = nullptr ; }
-    uint32_t * dhalo = nullptr ;
     CUDA_TRY(ctx, cudaMalloc(&d->send_idx, std::max<uint64_t>(d->nsend, 1)*sizeof(uint32_t))) ;
     CUDA_TRY(ctx, cudaMalloc(&d->sendbuf, std::max<uint64_t>(d->nsend, 1)*ctx->S*sizeof(double))) ;
-    CUDA_TRY(ctx, cudaMalloc(&dhalo, std::max<uint64_t>(d->nhalo, 1)*sizeof(uint32_t))) ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(dhalo, halo.data(), d->nhalo*sizeof(uint32_t), cudaMemcpyHostToDevice, st)) ;
-    NCCL_TRY(ctx, g_nccl.GroupStart()) ;
-    for(const DistPeer & p : d->peers)
-    {
-        if(p.recv_cnt) NCCL_TRY(ctx, g_nccl.Send(dhalo+p.recv_off, p.recv_cnt, ncclUint32, p.rank, d->comm, st)) ;      // "I need these columns of yours"
-        if(p.send_cnt) NCCL_TRY(ctx, g_nccl.Recv(d->send_idx+p.send_off, p.send_cnt, ncclUint32, p.rank, d->comm, st)) ;
-    }
-    NCCL_TRY(ctx, g_nccl.GroupEnd()) ;
-    // global column -> local row of mine
     std::vector<uint32_t> sidx(d->nsend) ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(sidx.data(), d->send_idx, d->nsend*sizeof(uint32_t), cudaMemcpyDeviceToHost, st)) ;
-    CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+    if(d->local)
+    {
+        // "I need these columns of yours": read straight out of the peers' halo lists (owner-grouped, ascending)
+        LocalGroup * g = d->local ;
+        for(const DistPeer & p : d->peers)
+        {
+            if(!p.send_cnt) continue ;
+            const DistState * dq = static_cast<const DistState *>(g->cptr[p.rank]) ;
+            uint64_t off = 0 ;
+            for(int j = 0 ; j < d->rank ; j++) off += (uint64_t)all[(size_t)p.rank*d->world+j] ;
+            std::copy(dq->halo_host.begin()+off, dq->halo_host.begin()+off+p.send_cnt, sidx.begin()+p.send_off) ;
+        }
+        GROUP_TRY(ctx, g->barrier()) ;                     // everybody is done reading everybody's list
+        d->halo_host.clear() ; d->halo_host.shrink_to_fit() ;
+    }
+    else
+    {
+        uint32_t * dhalo = nullptr ;
+        CUDA_TRY(ctx, cudaMalloc(&dhalo, std::max<uint64_t>(d->nhalo, 1)*sizeof(uint32_t))) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dhalo, halo.data(), d->nhalo*sizeof(uint32_t), cudaMemcpyHostToDevice, st)) ;
+        NCCL_TRY(ctx, g_nccl.GroupStart()) ;
+        for(const DistPeer & p : d->peers)
+        {
+            if(p.recv_cnt) NCCL_TRY(ctx, g_nccl.Send(dhalo+p.recv_off, p.recv_cnt, ncclUint32, p.rank, d->comm, st)) ;      // "I need these columns of yours"
+            if(p.send_cnt) NCCL_TRY(ctx, g_nccl.Recv(d->send_idx+p.send_off, p.send_cnt, ncclUint32, p.rank, d->comm, st)) ;
+        }
+        NCCL_TRY(ctx, g_nccl.GroupEnd()) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(sidx.data(), d->send_idx, d->nsend*sizeof(uint32_t), cudaMemcpyDeviceToHost, st)) ;
+        CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
+        cudaFree(dhalo) ;
+    }
+    // global column -> local row of mine
     for(auto & v : sidx)
     {
         if(v < r0 || v >= r1) { ctx->set_error("distributed structure: a peer asked for a column this rank does not own") ; return AMIE_B200_ERR_ARG ; }
         v -= r0 ;
     }
     CUDA_TRY(ctx, cudaMemcpy(d->send_idx, sidx.data(), d->nsend*sizeof(uint32_t), cudaMemcpyHostToDevice)) ;
-    cudaFree(dhalo) ;
 
     // ---- interior rows: the longest run of rows that reference no halo column
     unsigned char * dflag = nullptr ;
@@ -735,6 +867,28 @@ int amie_b200_dist_init(amie_b200_ctx * ctx, int rank, int world, const void * i
 int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_global,
                                  const uint32_t * row_size_local, const uint32_t * column_index_local, uint64_t nnzb_local)
 {
+    return dist_set_structure_local(ctx, stride, nb_global, row_size_local, column_index_local, nnzb_local) ;
+}
+
+}
+
+// rank `rank` of an in-process group: no communicator, no second stream -- peer memory is the only transport
+int dist_init_local(amie_b200_ctx * ctx, int rank, LocalGroup * g)
+{
+    if(!ctx || !g || rank < 0 || rank >= g->world) return AMIE_B200_ERR_ARG ;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    dist_destroy(ctx) ;
+    DistState * d = new DistState ;
+    ctx->dist = d ;
+    d->rank = rank ; d->world = g->world ;
+    d->bounds = g->bounds ;
+    d->local = g ;
+    return AMIE_B200_OK ;
+}
+
+int dist_set_structure_local(amie_b200_ctx * ctx, int stride, uint64_t nb_global, const uint32_t * row_size_local,
+                             const uint32_t * column_index_local, uint64_t nnzb_local)
+{
     if(!ctx || !ctx->dist) return AMIE_B200_ERR_STATE ;
     DistState * d = ctx->dist ;
     if(d->bounds.back() != nb_global) { ctx->set_error("dist_set_structure: bounds do not cover nb_global") ; return AMIE_B200_ERR_ARG ; }
@@ -746,6 +900,8 @@ int amie_b200_dist_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb_gl
     ctx->row_base = d->bounds[d->rank] ;
     return dist_finish_structure(ctx) ;
 }
+
+extern "C" {
 
 int amie_b200_dist_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s)
 {

@@ -6,11 +6,14 @@
 struct SpmvCall ;
 
 int  dist_world(const amie_b200_ctx * ctx) ;
+int  dist_rank(const amie_b200_ctx * ctx) ;
 void dist_destroy(amie_b200_ctx * ctx) ;
 int  dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c) ;
 int  dist_finalize(amie_b200_ctx * ctx, int kind) ;              // allreduce of st->red_local + scalar step on every rank
 int  dist_allreduce_max(amie_b200_ctx * ctx, double * value) ;
 int  dist_inverse_diagonal(amie_b200_ctx * ctx) ;
+// a GLOBAL rowstart (DOF units) in the local row numbering of this rank: 0 .. N_local
+uint64_t dist_local_rowstart(const amie_b200_ctx * ctx, uint64_t rowstart_global) ;
 
 // synth_device.cu
 int synth_rows_to_device(amie_b200_ctx * ctx, const SynthRecipe & R, uint64_t row0, uint64_t row1,

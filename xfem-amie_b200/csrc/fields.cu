@@ -93,7 +93,7 @@ int amie_b200_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int n
                                      const double * dshape, const double * jinv)
 {
     if(!ctx || npe < 1 || npe > 64 || (n_elem && (!elem_ids || !dshape || !jinv))) return AMIE_B200_ERR_ARG ;
-    if(ctx->dist) { ctx->set_error("set_element_kinematics: not available on a row-partitioned context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    if(ctx->dist || ctx->group) { ctx->set_error("set_element_kinematics: not available on a row-partitioned / multi-device context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     if(!ctx->have_structure) { ctx->set_error("set_element_kinematics before set_structure") ; return AMIE_B200_ERR_STATE ; }
     if((dim != 2 && dim != 3) || dim != ctx->S)
     {

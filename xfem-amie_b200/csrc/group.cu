@@ -1,0 +1,387 @@
+// group.cu -- amie_b200_create(devices, ndev > 1): several GPUs behind one context and one caller thread.
+//
+// What the caller sees is the single-device C-ABI: global host arrays in, global host arrays out
+// (Assembly::cgsolve, solvers/assembly.cpp:1841-1850, stays one thread in one process).  Inside, the block rows are
+// split into contiguous ranges balanced by stored blocks; child context r (device devices[r], worker thread r) holds
+// range r and runs the per-rank code of dist.cu: interior SpMV overlapped with NVLink halo pushes, mailbox
+// reductions, identical loop decisions on every device.  Host<->device copies of the slices run concurrently, one
+// PCIe link per GPU.  See group.h.
+#include "group.h"
+#include "dist.h"
+#include "synth.h"
+#include <algorithm>
+#include <cstring>
+
+// ------------------------------------------------------------------ barrier + worker pool
+
+bool LocalGroup::barrier()
+{
+    std::unique_lock<std::mutex> lk(bm) ;
+    if(aborted) return false ;
+    const uint64_t gen = generation ;
+    if(++waiting == world)
+    {
+        waiting = 0 ;
+        generation++ ;
+        bcv.notify_all() ;
+        return true ;
+    }
+    bcv.wait(lk, [&] { return generation != gen || aborted ; }) ;
+    return !aborted ;
+}
+
+void LocalGroup::abort()
+{
+    std::lock_guard<std::mutex> lk(bm) ;
+    aborted = true ;
+    broken = true ;
+    bcv.notify_all() ;
+}
+
+void LocalGroup::worker(int rank)
+{
+    uint64_t seen = 0 ;
+    for( ;; )
+    {
+        const std::function<int(int)> * f = nullptr ;
+        {
+            std::unique_lock<std::mutex> lk(jm) ;
+            jcv.wait(lk, [&] { return quit || job_gen != seen ; }) ;
+            if(quit) return ;
+            seen = job_gen ;
+            f = job ;
+        }
+        int rc = (*f)(rank) ;
+        // a rank that failed may have left the others inside a collective: release them, the group is unusable afterwards
+        if(rc < 0 && world > 1) abort() ;
+        {
+            std::lock_guard<std::mutex> lk(jm) ;
+            results[rank] = rc ;
+            if(--job_left == 0) dcv.notify_all() ;
+        }
+    }
+}
+
+void LocalGroup::start(int w)
+{
+    world = w ;
+    for(int r = 0 ; r < w ; r++) workers.emplace_back([this, r] { worker(r) ; }) ;
+}
+
+void LocalGroup::stop()
+{
+    {
+        std::lock_guard<std::mutex> lk(jm) ;
+        quit = true ;
+    }
+    jcv.notify_all() ;
+    for(auto & t : workers) t.join() ;
+    workers.clear() ;
+}
+
+int LocalGroup::run(const std::function<int(int)> & f)
+{
+    {
+        std::unique_lock<std::mutex> lk(jm) ;
+        job = &f ;
+        job_left = world ;
+        job_gen++ ;
+        jcv.notify_all() ;
+        dcv.wait(lk, [&] { return job_left == 0 ; }) ;
+        job = nullptr ;
+    }
+    for(int r = 0 ; r < world ; r++) if(results[r] < 0) return results[r] ;
+    return results[0] ;
+}
+
+// ------------------------------------------------------------------ helpers
+
+namespace {
+
+// first failing child's message becomes the group's
+int harvest(amie_b200_ctx * ctx, int rc)
+{
+    if(rc >= 0) return rc ;
+    LocalGroup * g = ctx->group ;
+    for(int r = 0 ; r < g->world ; r++)
+        if(g->results[r] < 0 && !g->child[r]->err.empty())
+        {
+            ctx->set_error("device "+std::to_string(g->child[r]->device)+" (part "+std::to_string(r)+"): "+g->child[r]->err) ;
+            return rc ;
+        }
+    ctx->set_error("group: a device failed") ;
+    return rc ;
+}
+
+int check_usable(amie_b200_ctx * ctx)
+{
+    if(ctx->group->broken)
+    {
+        ctx->set_error("group context: an earlier call failed on one device and left the devices out of step; destroy the context") ;
+        return AMIE_B200_ERR_STATE ;
+    }
+    return AMIE_B200_OK ;
+}
+
+}
+
+int group_unsupported(amie_b200_ctx * ctx, const char * what)
+{
+    ctx->set_error(std::string(what)+": not available on a multi-device context") ;
+    return AMIE_B200_ERR_UNSUPPORTED ;
+}
+
+// ------------------------------------------------------------------ create / destroy
+
+amie_b200_ctx * group_create(const int * devices, int ndev, std::string & err)
+{
+    if(ndev < 2 || ndev > GROUP_MAX || !devices) { err = "amie_b200_create: 2 to 8 devices per context" ; return nullptr ; }
+    int count = 0 ;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { err = "amie_b200_create: no CUDA device" ; return nullptr ; }
+    for(int i = 0 ; i < ndev ; i++)
+        if(devices[i] < 0 || devices[i] >= count) { err = "amie_b200_create: no such CUDA device" ; return nullptr ; }
+    // every pair of distinct devices needs a peer path (NVLink / NVSwitch on the target box): the halo pushes and the
+    // reduction mailboxes are plain stores into the neighbour's memory
+    for(int i = 0 ; i < ndev ; i++)
+        for(int j = 0 ; j < ndev ; j++)
+        {
+            if(devices[i] == devices[j]) continue ;
+            int can = 0 ;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) ;
+            if(!can)
+            {
+                err = "amie_b200_create: devices "+std::to_string(devices[i])+" and "+std::to_string(devices[j])+" have no peer-to-peer path" ;
+                return nullptr ;
+            }
+            cudaSetDevice(devices[i]) ;
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0) ;
+            if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            {
+                err = std::string("cudaDeviceEnablePeerAccess: ")+cudaGetErrorString(e) ;
+                return nullptr ;
+            }
+            cudaGetLastError() ;
+        }
+    amie_b200_ctx * ctx = new amie_b200_ctx ;
+    LocalGroup * g = new LocalGroup ;
+    ctx->group = g ;
+    ctx->device = devices[0] ;
+    for(int i = 0 ; i < ndev ; i++)
+    {
+        amie_b200_ctx * c = amie_b200_create(devices+i, 1) ;
+        if(!c)
+        {
+            err = amie_b200_global_error() ;
+            for(auto * k : g->child) amie_b200_destroy(k) ;
+            delete g ; delete ctx ;
+            return nullptr ;
+        }
+        g->child.push_back(c) ;
+    }
+    ctx->num_sms = g->child[0]->num_sms ;
+    g->start(ndev) ;
+    return ctx ;
+}
+
+void group_destroy(amie_b200_ctx * ctx)
+{
+    LocalGroup * g = ctx->group ;
+    g->stop() ;
+    for(auto * c : g->child) amie_b200_destroy(c) ;
+    delete g ;
+    ctx->group = nullptr ;
+    delete ctx ;
+}
+
+// ------------------------------------------------------------------ matrix
+
+int group_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb)
+{
+    if(!row_size || (!column_index && nnzb)) return AMIE_B200_ERR_ARG ;
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(stride != 2 && stride != 3) { ctx->set_error("set_structure: a multi-device context takes stride 2 or 3") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    LocalGroup * g = ctx->group ;
+    const double t0 = wall_now() ;
+    g->bounds.assign(g->world+1, 0) ;
+    if((rc = amie_b200_partition_rows(nb, row_size, g->world, g->bounds.data()))) return rc ;
+    g->blk_off.assign(g->world+1, 0) ;
+    {
+        uint64_t acc = 0 ;
+        int p = 0 ;
+        for(uint64_t i = 0 ; i <= nb ; i++)
+        {
+            while(p <= g->world && g->bounds[p] == i) g->blk_off[p++] = acc ;
+            if(i < nb) acc += row_size[i] ;
+        }
+        if(acc != nnzb) { ctx->set_error("set_structure: sum(row_size) != nnzb") ; return AMIE_B200_ERR_ARG ; }
+    }
+    ctx->have_structure = ctx->have_values = ctx->have_rhs = false ;
+    rc = g->run([&](int r) -> int
+    {
+        amie_b200_ctx * c = g->child[r] ;
+        int e = dist_init_local(c, r, g) ;
+        if(e) return e ;
+        return dist_set_structure_local(c, stride, nb, row_size+g->bounds[r], column_index+g->blk_off[r], g->blk_off[r+1]-g->blk_off[r]) ;
+    }) ;
+    if(rc) return harvest(ctx, rc) ;
+    ctx->S = stride ; ctx->nb = ctx->nb_global = nb ; ctx->nnzb = nnzb ; ctx->N = nb*(uint64_t)stride ;
+    ctx->have_structure = true ;
+    ctx->stats.structure_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
+}
+
+int group_set_values(amie_b200_ctx * ctx, const double * array)
+{
+    if(!array && ctx->nnzb) return AMIE_B200_ERR_ARG ;
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("set_values before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    const double t0 = wall_now() ;
+    const uint64_t per_block = (uint64_t)ctx->S*(ctx->S+ctx->S%2) ;
+    rc = g->run([&](int r) -> int { return amie_b200_set_values(g->child[r], array+g->blk_off[r]*per_block) ; }) ;
+    if(rc) return harvest(ctx, rc) ;
+    ctx->have_values = true ;
+    ctx->stats.values_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
+}
+
+int group_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    int stride = 0 ;
+    uint64_t nb = 0, nnzb = 0 ;
+    if((rc = amie_b200_synth_sizes(s, &stride, &nb, &nnzb))) return rc ;
+    const double t0 = wall_now() ;
+    std::vector<uint32_t> rs(nb) ;
+    uint64_t counted = 0 ;
+    if((rc = amie_b200_synth_count(s, 0, nb, rs.data(), &counted))) return rc ;
+    g->bounds.assign(g->world+1, 0) ;
+    if((rc = amie_b200_partition_rows(nb, rs.data(), g->world, g->bounds.data()))) return rc ;
+    g->blk_off.assign(g->world+1, 0) ;
+    for(int p = 0 ; p < g->world ; p++)
+    {
+        uint64_t acc = 0 ;
+        for(uint64_t i = g->bounds[p] ; i < g->bounds[p+1] ; i++) acc += rs[i] ;
+        g->blk_off[p+1] = g->blk_off[p]+acc ;
+    }
+    rs.clear() ; rs.shrink_to_fit() ;
+    rc = g->run([&](int r) -> int
+    {
+        amie_b200_ctx * c = g->child[r] ;
+        int e = dist_init_local(c, r, g) ;
+        if(e) return e ;
+        return amie_b200_dist_synth_to_device(c, s) ;
+    }) ;
+    if(rc) return harvest(ctx, rc) ;
+    ctx->S = stride ; ctx->nb = ctx->nb_global = nb ; ctx->nnzb = nnzb ; ctx->N = nb*(uint64_t)stride ;
+    ctx->have_structure = ctx->have_values = ctx->have_rhs = true ;
+    ctx->stats.structure_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
+}
+
+// ------------------------------------------------------------------ per-slice calls
+
+int group_sliced(amie_b200_ctx * ctx, const std::function<int(amie_b200_ctx *, uint64_t, uint64_t)> & f)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("no matrix structure on the devices yet") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    const uint64_t S = (uint64_t)ctx->S ;
+    rc = g->run([&](int r) -> int { return f(g->child[r], g->bounds[r]*S, (g->bounds[r+1]-g->bounds[r])*S) ; }) ;
+    return harvest(ctx, rc) ;
+}
+
+// the four solver entry points.  resident: b / x0 already on the devices, x stays there.
+int group_solve(amie_b200_ctx * ctx, bool bicg, bool resident, const double * b, const double * x0, uint64_t nx0,
+                int precond_kind, double eps, int maxit, uint64_t nssor, uint64_t rowstart, uint64_t colstart,
+                double * x_out, uint64_t * nit_out, double * err_out, double * rho_out)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_values) { ctx->set_error("solve before set_values") ; return AMIE_B200_ERR_STATE ; }
+    if(resident && !ctx->have_rhs) { ctx->set_error("solve: rhs not on the devices") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    const uint64_t S = (uint64_t)ctx->S ;
+    // BiCGStab only takes x0 when the sizes agree (biconjugategradientstabilized.cpp:21-24): a GLOBAL decision
+    if(bicg && nx0 != ctx->N) nx0 = 0 ;
+    uint64_t nit[GROUP_MAX] = {} ;
+    double err[GROUP_MAX] = {}, rho[GROUP_MAX] = {} ;
+    rc = g->run([&](int r) -> int
+    {
+        amie_b200_ctx * c = g->child[r] ;
+        const uint64_t d0 = g->bounds[r]*S, nd = (g->bounds[r+1]-g->bounds[r])*S ;
+        int e ;
+        if(!resident)
+        {
+            if((e = amie_b200_upload_rhs(c, b+d0))) return e ;
+            const uint64_t n0 = nx0 > d0 ? std::min<uint64_t>(nx0-d0, nd) : 0 ;
+            if((e = amie_b200_upload_x0(c, n0 ? x0+d0 : nullptr, n0))) return e ;
+        }
+        int ret = bicg ? amie_b200_bicgstab_resident(c, precond_kind, eps, maxit, nit+r, err+r)
+                       : amie_b200_pcg_resident(c, precond_kind, eps, maxit, nssor, rowstart, colstart, nit+r, err+r, rho+r) ;
+        if(ret < 0) return ret ;
+        if(!resident && (e = amie_b200_download_x(c, x_out+d0))) return e ;
+        return ret ;
+    }) ;
+    if(rc < 0) return harvest(ctx, rc) ;
+    // every device took the same decisions: the answers of part 0 are everybody's
+    for(int r = 1 ; r < g->world ; r++)
+        if(g->results[r] != g->results[0] || nit[r] != nit[0])
+        {
+            ctx->set_error("group solve: the devices disagree on the outcome (internal error)") ;
+            g->broken = true ;
+            return AMIE_B200_ERR_STATE ;
+        }
+    if(!resident) ctx->have_rhs = true ;
+    if(nit_out) *nit_out = nit[0] ;
+    if(err_out) *err_out = err[0] ;
+    if(rho_out) *rho_out = rho[0] ;
+    return rc ;
+}
+
+// ------------------------------------------------------------------ stats / options
+
+int group_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
+{
+    const LocalGroup * g = ctx->group ;
+    amie_b200_stats a {} ;
+    for(int r = 0 ; r < g->world ; r++)
+    {
+        amie_b200_stats s ;
+        amie_b200_get_stats(g->child[r], &s) ;
+        if(r == 0) a = s ;
+        else
+        {
+            // sums: work and bytes; maxima: times (the devices run side by side)
+            a.kernel_launches += s.kernel_launches ;
+            a.h2d_bytes += s.h2d_bytes ; a.d2h_bytes += s.d2h_bytes ;
+            a.spmv_algorithmic_bytes += s.spmv_algorithmic_bytes ;
+            a.device_bytes += s.device_bytes ;
+            a.solve_ms = std::max(a.solve_ms, s.solve_ms) ;
+            a.h2d_ms = std::max(a.h2d_ms, s.h2d_ms) ; a.d2h_ms = std::max(a.d2h_ms, s.d2h_ms) ;
+            // per-launch SpMV time: keep the slowest device's average (spmv_ms_total / spmv_timed)
+            if(s.spmv_timed && a.spmv_timed && s.spmv_ms_total/s.spmv_timed > a.spmv_ms_total/a.spmv_timed)
+            { a.spmv_ms_total = s.spmv_ms_total ; a.spmv_timed = s.spmv_timed ; }
+        }
+    }
+    a.stride = ctx->S ; a.nb = ctx->nb ; a.nnzb = ctx->nnzb ; a.ndof = ctx->N ;
+    a.structure_ms = ctx->stats.structure_ms ; a.values_ms = ctx->stats.values_ms ;
+    *out = a ;
+    return AMIE_B200_OK ;
+}
+
+int group_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
+{
+    LocalGroup * g = ctx->group ;
+    for(auto * c : g->child)
+    {
+        int rc = amie_b200_set_option(c, key, value) ;
+        if(rc) { ctx->set_error(c->err) ; return rc ; }
+    }
+    return AMIE_B200_OK ;
+}

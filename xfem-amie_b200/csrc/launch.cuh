@@ -6,6 +6,7 @@
 #include "kernels_spmv_tma.cuh"
 #include "kernels_spmv_rt.cuh"
 #include "kernels_spmv_rt2.cuh"
+#include "kernels_spmv_rtm.cuh"
 #include "kernels_vec.cuh"
 #include "kernels_setup.cuh"
 
@@ -35,13 +36,33 @@ static inline int persistent_grid(const amie_b200_ctx * ctx, int per_sm, uint32_
     return (int)(g ? g : 1) ;
 }
 
-// the occupancy query is cached per kernel instantiation (one static per expansion site)
+// Occupancy and the opt-in to > 48 KB of dynamic shared memory are properties of (kernel, DEVICE): one cache slot per
+// device ordinal and kernel instantiation.  A process may hold contexts on several devices (group.cu does).
+#define AMIE_MAX_DEVICES 64
+static inline int device_slot(const amie_b200_ctx * ctx) { return ctx->device >= 0 && ctx->device < AMIE_MAX_DEVICES ? ctx->device : 0 ; }
+
 #define SPMV_LAUNCH(KERNEL, ROWS_PER_TILE) do { \
-        static int per_sm = 0 ; \
-        if(!per_sm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KERNEL, 256, 0) ; \
+        static int per_sm_of[AMIE_MAX_DEVICES] = {} ; \
+        int & per_sm = per_sm_of[device_slot(ctx)] ; \
+        if(!per_sm) { int q = 0 ; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, KERNEL, 256, 0) ; per_sm = q < 1 ? 1 : q ; } \
         uint32_t ntiles = (uint32_t)((args.nrows+(ROWS_PER_TILE)-1)/(ROWS_PER_TILE)) ; \
         int grid = persistent_grid(ctx, per_sm, ntiles) ; \
         KERNEL<<<grid, 256, 0, ctx->stream>>>(args) ; } while(0)
+
+// first use of a kernel instantiation on a device: raise its dynamic shared-memory limit there, query its occupancy
+template<typename K>
+static inline int smem_kernel_per_sm(const amie_b200_ctx * ctx, K kern, int threads, int smem, int * cache)
+{
+    int & per_sm = cache[device_slot(ctx)] ;
+    if(!per_sm)
+    {
+        int q = 0 ;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem) ;
+        per_sm = q < 1 ? 1 : q ;
+    }
+    return per_sm ;
+}
 
 // TMA-staged stride-3 kernel: R rows per tile, NST stages, CAP blocks of stage capacity
 template<int DOT, bool MINUS_B, int R, int NST, int CAP, bool PF = false>
@@ -50,13 +71,8 @@ static inline void launch_s3_tma(amie_b200_ctx * ctx, const SpmvArgs & args)
     auto kern = k_spmv_s3_tma<DOT, MINUS_B, R, NST, CAP, PF> ;
     constexpr int threads = PF ? 320 : 288 ;
     constexpr int smem = TmaStageLayout<R, NST, CAP>::TOTAL_BYTES ;
-    static int per_sm = 0 ;
-    if(!per_sm)
-    {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
-        if(per_sm < 1) per_sm = 1 ;
-    }
+    static int cache[AMIE_MAX_DEVICES] = {} ;
+    const int per_sm = smem_kernel_per_sm(ctx, kern, threads, smem, cache) ;
     const uint32_t ntiles = (args.nrows+R-1)/R ;
     const int grid = persistent_grid(ctx, per_sm, ntiles) ;
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
@@ -69,13 +85,22 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB, NP> ;
     constexpr int smem = RtLayout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+NP)*32 ;
-    static int per_sm = 0 ;
-    if(!per_sm)
-    {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
-        if(per_sm < 1) per_sm = 1 ;
-    }
+    static int cache[AMIE_MAX_DEVICES] = {} ;
+    const int per_sm = smem_kernel_per_sm(ctx, kern, threads, smem, cache) ;
+    const uint32_t ntiles = (args.nrows+RT_ROWS-1)/RT_ROWS ;
+    const int grid = persistent_grid(ctx, per_sm, ntiles) ;
+    kern<<<grid, threads, smem, ctx->stream>>>(args) ;
+}
+
+// row-thread pipeline with T teams of TM warps per tile (kernels_spmv_rtm.cuh)
+template<int DOT, bool MINUS_B, int T, int TM, int NST, int CAP, int G, int NP = 1>
+static inline void launch_s3_rtm(amie_b200_ctx * ctx, const SpmvArgs & args)
+{
+    auto kern = k_spmv_s3_rtm<DOT, MINUS_B, T, TM, NST, CAP, G, NP> ;
+    constexpr int smem = RtmLayout<NST, CAP, T, TM>::TOTAL_BYTES ;
+    constexpr int threads = (T*TM+NP)*32 ;
+    static int cache[AMIE_MAX_DEVICES] = {} ;
+    const int per_sm = smem_kernel_per_sm(ctx, kern, threads, smem, cache) ;
     const uint32_t ntiles = (args.nrows+RT_ROWS-1)/RT_ROWS ;
     const int grid = persistent_grid(ctx, per_sm, ntiles) ;
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
@@ -87,13 +112,8 @@ static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP> ;
     constexpr int smem = Rt2Layout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+NP)*32 ;
-    static int per_sm = 0 ;
-    if(!per_sm)
-    {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) ;
-        if(per_sm < 1) per_sm = 1 ;
-    }
+    static int cache[AMIE_MAX_DEVICES] = {} ;
+    const int per_sm = smem_kernel_per_sm(ctx, kern, threads, smem, cache) ;
     const uint32_t ntiles = (args.nrows+RT2_ROWS-1)/RT2_ROWS ;
     const int grid = persistent_grid(ctx, per_sm, ntiles) ;
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
@@ -131,7 +151,11 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
             // fills its stage (27 blocks/row for Q1 hexahedra, 12-15 for linear tetrahedra).  Short rows mean small
             // tiles, and ONE producer warp (~0.3 us per tile) then caps the CTA: three producers there.
             const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
-            if(avg > 15.5 || ctx->opt_variant == 3)
+            if(ctx->opt_variant == 4)      launch_s3_rtm<DOT, MINUS_B, 3, 3, 7, 270, 1>(ctx, args) ;
+            else if(ctx->opt_variant == 5) launch_s3_rtm<DOT, MINUS_B, 3, 2, 7, 270, 1>(ctx, args) ;
+            else if(ctx->opt_variant == 6) launch_s3_rtm<DOT, MINUS_B, 4, 3, 12, 160, 1, 3>(ctx, args) ;
+            else if(ctx->opt_variant == 7) launch_s3_rtm<DOT, MINUS_B, 5, 2, 12, 160, 1, 3>(ctx, args) ;
+            else if(avg > 15.5 || ctx->opt_variant == 3)
                 launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;   // 7 stages, not 8: leaves ~30 KB of L1 for the x gather
             else
                 launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3>(ctx, args) ;
@@ -178,6 +202,10 @@ static inline int launch_spmv_range(amie_b200_ctx * ctx, const SpmvCall & c, uin
     else if(c.dot == DOT_OMEGA && !c.minus_b) spmv_dispatch<DOT_OMEGA, false>(ctx, args) ;
     else { ctx->set_error("launch_spmv: unsupported combination") ; return AMIE_B200_ERR_ARG ; }
     ctx->stats.kernel_launches++ ;
+    // a refused launch (shared-memory opt-in missing on this device, bad configuration) must not go unnoticed: the
+    // solver would iterate on stale reduction scalars
+    const cudaError_t le = cudaPeekAtLastError() ;
+    if(le != cudaSuccess) { ctx->set_error(std::string("SpMV launch: ")+cudaGetErrorString(le)) ; return AMIE_B200_ERR_CUDA ; }
     return AMIE_B200_OK ;
 }
 

@@ -116,11 +116,14 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     }
     const int S = ctx->S ;
     const uint64_t N = ctx->N ;
-    if(rowstart%S || colstart%S || rowstart > N)
+    if(rowstart%S || colstart%S || rowstart > ctx->nb_global*(uint64_t)S)
     {
         ctx->set_error("pcg: rowstart/colstart must be multiples of the stride") ;
         return AMIE_B200_ERR_ARG ;
     }
+    // row-partitioned context: rows are addressed locally from here on, columns stay global (dist_spmv)
+    const uint64_t rowstart_global = rowstart ;
+    if(ctx->dist) rowstart = dist_local_rowstart(ctx, rowstart) ;
     ctx_reset_solve_stats(ctx) ;
     cudaEvent_t ev0 = ctx->ev_a, ev1 = ctx->ev_b ;
     cudaEventRecord(ev0, ctx->stream) ;
@@ -252,7 +255,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         }
 
         double err = 0. ;
-        if((rc = residual(R, 1., rowstart, true, &err))) return rc ;                // :266-267 (rowstart passed as colstart)
+        if((rc = residual(R, 1., rowstart_global, true, &err))) return rc ;         // :266-267 (rowstart passed as colstart)
         if(err < errmin)                                                            // :268-272
         {
             errmin = std::sqrt(std::fabs(rho)) ;

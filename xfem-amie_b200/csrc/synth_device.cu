@@ -4,6 +4,7 @@
 // bits equal the host generator's (tests/test_synth.py checks that on the GPU).
 #include "launch.cuh"
 #include "synth.h"
+#include "group.h"
 #include <cub/cub.cuh>
 
 namespace {
@@ -77,6 +78,7 @@ int synth_rows_to_device(amie_b200_ctx * ctx, const SynthRecipe & R, uint64_t ro
 extern "C" int amie_b200_synth_to_device(amie_b200_ctx * ctx, const amie_b200_synth * s)
 {
     if(!ctx || !s) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_synth_to_device(ctx, s) ;
     const SynthRecipe & R = *synth_recipe_of(s) ;
     double t0 = wall_now() ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;

@@ -6,6 +6,7 @@
 #include <vector>
 #include <iostream>
 #include <cstdlib>
+#include <algorithm>
 
 namespace
 {
@@ -17,18 +18,62 @@ struct Entry
     uint64_t colhash = 0 ;
     bool renumbered = false ;
     std::vector<uint32_t> perm ;            // perm[old node] = new node while renumbered
+    bool have_values = false ;
+    uint64_t valhash = 0 ;                  // of the array last uploaded
+    uint64_t last_use = 0 ;
 } ;
 std::map<Amie::Assembly *, Entry> registry ;
+uint64_t use_clock = 0 ;
 
-uint64_t hash_u32(const unsigned int * p, size_t n)
+// Order-dependent 64-bit hash of EVERY word (multiply-xorshift per word, four independent lanes per chunk, chunks
+// in parallel and then folded in order).  It decides whether an upload can be skipped, so nothing is sampled.
+uint64_t hash_words(const uint64_t * p, size_t n, uint64_t seed)
 {
-    // FNV-1a over a strided sample: cheap, and any re-numbering changes it
-    uint64_t h = 1469598103934665603ull ;
-    size_t step = n > 65536 ? n/65536 : 1 ;
-    for(size_t i = 0 ; i < n ; i += step) { h ^= p[i] ; h *= 1099511628211ull ; }
-    h ^= n ;
+    const size_t chunk = 1u << 16 ;
+    const size_t nchunks = (n+chunk-1)/chunk ;
+    std::vector<uint64_t> part(nchunks) ;
+    #pragma omp parallel for schedule(static)
+    for(long long c = 0 ; c < (long long)nchunks ; c++)
+    {
+        const size_t a = (size_t)c*chunk, b = std::min(n, a+chunk) ;
+        uint64_t h[4] = { seed^0x9e3779b97f4a7c15ull, seed^0xbf58476d1ce4e5b9ull, seed^0x94d049bb133111ebull, seed^0x2545f4914f6cdd1dull } ;
+        size_t i = a ;
+        for( ; i+4 <= b ; i += 4)
+            for(int l = 0 ; l < 4 ; l++) { h[l] = (h[l]^p[i+l])*0x100000001b3ull ; h[l] ^= h[l] >> 29 ; }
+        for( ; i < b ; i++) { h[0] = (h[0]^p[i])*0x100000001b3ull ; h[0] ^= h[0] >> 29 ; }
+        part[c] = ((h[0]*31+h[1])*31+h[2])*31+h[3] ;
+    }
+    uint64_t h = seed^n ;
+    for(uint64_t v : part) { h = (h^v)*0xff51afd7ed558ccdull ; h ^= h >> 33 ; }
     return h ;
 }
+
+uint64_t hash_u32(const unsigned int * p, size_t n, uint64_t seed)
+{
+    uint64_t h = hash_words(reinterpret_cast<const uint64_t *>(p), n/2, seed) ;      // valarray storage is 8-byte aligned
+    if(n & 1) h = (h^p[n-1])*0x100000001b3ull ;
+    return h^n ;
+}
+
+// Assembly::cgsolve builds a fresh solver per call and nothing tells this file when an Assembly dies, so the registry
+// is a small cache: beyond AMIE_B200_MAX_CONTEXTS (default 2) the least recently used context is destroyed and its HBM
+// released.  An evicted Assembly that solves again simply uploads again.
+void evict_beyond_capacity(Amie::Assembly * keep)
+{
+    size_t cap = 2 ;
+    if(const char * e = getenv("AMIE_B200_MAX_CONTEXTS")) cap = (size_t)std::max(1, atoi(e)) ;
+    while(registry.size() > cap)
+    {
+        auto victim = registry.end() ;
+        for(auto it = registry.begin() ; it != registry.end() ; ++it)
+            if(it->first != keep && (victim == registry.end() || it->second.last_use < victim->second.last_use)) victim = it ;
+        if(victim == registry.end()) break ;
+        amie_b200_destroy(victim->second.ctx) ;
+        registry.erase(victim) ;
+    }
+}
+
+struct AtExit { ~AtExit() { for(auto & kv : registry) amie_b200_destroy(kv.second.ctx) ; registry.clear() ; } } at_exit ;
 }
 
 namespace AmieB200Shim
@@ -38,8 +83,12 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
 {
     Amie::CoordinateIndexedSparseMatrix & A = a->getMatrix() ;
     Entry & e = registry[a] ;
+    e.last_use = ++use_clock ;
     if(!e.ctx)
     {
+        evict_beyond_capacity(a) ;
+        // one device (AMIE_B200_DEVICE) or several behind the same calls (AMIE_B200_DEVICES=0,1,...: the block rows are
+        // partitioned inside the library, csrc/group.cu)
         e.ctx = amie_b200_create(nullptr, 0) ;
         if(!e.ctx)
         {
@@ -50,7 +99,7 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
     }
     const size_t nb = A.row_size.size(), nnzb = A.column_index.size() ;
     const unsigned int * cp = nnzb ? &A.column_index[0] : nullptr ;
-    const uint64_t h = hash_u32(cp, nnzb) ;
+    const uint64_t h = hash_u32(cp, nnzb, 1)^hash_u32(nb ? &A.row_size[0] : nullptr, nb, 2) ;
     // rowstart / colstart address AMIE's numbering (space-time planes): such assemblies keep it
     const char * env = getenv("AMIE_B200_RENUMBER") ;
     const bool want_renumber = env && atoi(env) != 0 && a->rowstart == 0 && a->colstart == 0 && nb > 0 ;
@@ -81,13 +130,33 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
             return nullptr ;
         }
         e.stride = A.stride ; e.nb = nb ; e.nnzb = nnzb ; e.colptr = cp ; e.colhash = h ; e.renumbered = want_renumber ;
+        e.have_values = false ;
     }
-    // values change on every assembly (make_final zeroes and re-scatters them): upload each solve
-    if(amie_b200_set_values(e.ctx, &A.array[0]))
+    // Values change whenever make_final re-scatters them (every damage step) -- but not between the CG, CG, BiCGStab
+    // solves of one FeatureTree::step, nor between load steps of an elastic run.  A full hash of the array (host memory
+    // speed, all cores) costs far less than pushing it over PCIe again.  AMIE_B200_ALWAYS_UPLOAD=1 turns the check off.
+    const char * always = getenv("AMIE_B200_ALWAYS_UPLOAD") ;
+    const bool check = !(always && atoi(always) != 0) ;
+    const uint64_t vh = check ? hash_words(reinterpret_cast<const uint64_t *>(&A.array[0]), A.array.size(), 3) : 0 ;
+    if(!check || !e.have_values || vh != e.valhash)
     {
-        std::cerr << "amie_b200: set_values: " << amie_b200_last_error(e.ctx) << std::endl ;
-        return nullptr ;
+        e.have_values = false ;
+        if(amie_b200_set_values(e.ctx, &A.array[0]))
+        {
+            std::cerr << "amie_b200: set_values: " << amie_b200_last_error(e.ctx) << std::endl ;
+            return nullptr ;
+        }
+        e.have_values = check ;
+        e.valhash = vh ;
+        if(getenv("AMIE_B200_VERBOSE"))
+        {
+            amie_b200_stats st ;
+            if(amie_b200_get_stats(e.ctx, &st) == 0)
+                std::cerr << "amie_b200: matrix upload: structure " << st.structure_ms << " ms, values " << st.values_ms << " ms" << std::endl ;
+        }
     }
+    else if(getenv("AMIE_B200_VERBOSE"))
+        std::cerr << "amie_b200: matrix unchanged since the last solve: no upload" << std::endl ;
     return e.ctx ;
 }
 

@@ -3,6 +3,7 @@
 #include "solvers/biconjugategradientstabilized.h"
 #include "amie_b200_shim.h"
 #include <iostream>
+#include <algorithm>
 
 using namespace Amie ;
 
@@ -44,8 +45,12 @@ bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * pr
         return false ;
     }
     amie_b200_stats st ;
-    if(ret == 1 && amie_b200_get_stats(ctx, &st) == 0 && st.early_return)
+    const bool have_stats = amie_b200_get_stats(ctx, &st) == 0 ;
+    if(ret == 1 && have_stats && st.early_return)
         return true ;               // the reference returns from :43-44 / :57-63 without a cerr line
+    // biconjugategradientstabilized.cpp:131 (device time instead of the host's wall clock)
+    if(have_stats)
+        std::cerr << "mflops: " << n*2*(2.*assembly->getMatrix().array.size()+6.*x.size())/std::max(st.solve_ms*1e3, 1e-32) << std::endl ;
     if(verbose)
     {
         if(ret)

@@ -7,6 +7,7 @@
 #include "amie_b200_shim.h"
 #include <iostream>
 #include <cstdlib>
+#include <algorithm>
 
 namespace Amie {
 
@@ -63,12 +64,16 @@ bool ConjugateGradient::solve(const Vector &x0, Preconditionner * precond, const
         return false ;
     }
     amie_b200_stats st ;
-    if(ret == 1 && amie_b200_get_stats(ctx, &st) == 0 && st.early_return)
+    const bool have_stats = amie_b200_get_stats(ctx, &st) == 0 ;
+    if(ret == 1 && have_stats && st.early_return)
     {
         // conjugategradient.cpp:74-78
         std::cerr << "\n CG "<< x.size() << " homogeneous. " << std::abs(b).max() << std::endl ;
         return true ;
     }
+    // conjugategradient.cpp:259-264: flops of the iterations over the solve time in microseconds (here: device time)
+    if(have_stats && nit)
+        std::cerr << "mflops: " << nit*(2.*assembly->getMatrix().array.size()+4.*x.size())/std::max(st.solve_ms*1e3, 1e-32) << std::endl ;
     if(ret)
         std::cerr << "\n CG " << x.size() << " converged after " << nit << " iterations. Error : " << err << ", last rho = " << rho << ", max : "  << x.max() << ", min : "  << x.min() << std::endl ;
     else
