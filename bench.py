@@ -12,7 +12,13 @@ iterations, so `value` = iterations of all timed steps / device time of those st
              mean CUDA-event duration of the SpMV launches of the timed steps
   cpu_baseline : the reference's own CPU solver (oracle/_ref, OpenMP, all host cores) on a bounded sample
 
-`--impl reference` times only that CPU arm and prints its own line.
+`--impl reference` times only that CPU arm and prints its own line.  It runs in a process of its own that loads
+nothing but oracle/ libraries (the generator is oracle/libamie_synth.so), with OMP_PROC_BIND=close, OMP_PLACES=cores and
+one thread per PHYSICAL core of the affinity mask; the GPU arm's cpu_baseline leg calls it as a subprocess
+(`--cpu-leg`), so the thread pinning never touches the process that drives the GPUs.
+
+`--gpus N --single-process` (no torchrun): ONE context over N devices, amie_b200_create(devices, N) -- the shape
+Assembly::cgsolve has (one caller thread, global host arrays); same timed region and JSON line as N = 1.
 """
 import argparse
 import ctypes
@@ -25,8 +31,8 @@ import time
 
 import numpy as np
 
-# experiment switch read by the library at context creation (include/amie_b200.h, option "split_dot")
-SPLIT_DOT = os.environ.get("AMIE_B200_SPLIT_DOT", "0") not in ("", "0")
+# --single-process (one context over N devices) needs eager CUDA module loading, decided when CUDA initialises
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -103,65 +109,201 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU reference arm
 
-def cpu_reference_rate(pkg, n_cpu, threads=0):
-    """The reference's own ConjugateGradient::solve (oracle/_ref, OpenMP) on S3-hex-n_cpu.
+def physical_cores():
+    """Physical cores of this process's affinity mask (hyper-thread siblings counted once)."""
+    cpus = sorted(os.sched_getaffinity(0))
+    seen = set()
+    for c in cpus:
+        try:
+            seen.add(open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip())
+        except OSError:
+            seen.add(str(c))
+    return max(1, len(seen))
+
+
+CPU_ENV = {"OMP_PROC_BIND": "close", "OMP_PLACES": "cores"}
+
+
+def ensure_cpu_env():
+    """The reference arm's OpenMP placement has to be in the environment BEFORE libgomp
+    initialises: re-exec once with it.  Only ever called by the reference arm's own process."""
+    if all(os.environ.get(k) == v for k, v in CPU_ENV.items()):
+        return
+    env = dict(os.environ, **CPU_ENV)
+    env.pop("OMP_NUM_THREADS", None)          # torchrun exports OMP_NUM_THREADS=1
+    os.execve(sys.executable, [sys.executable] + sys.argv, env)
+
+
+def cpu_reference_rate(preset, n_cpu, threads=0, spmv=True):
+    """The reference's own ConjugateGradient::solve (oracle/_ref, OpenMP) on `preset`-n_cpu.
     Returns dict(dof_iter_per_s, it_per_s, nit, wall, cores, kind, n)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
-    syn = pkg.Synth("S3-hex", n_cpu)
-    rs, ci, arr, b = syn.rows()
-    S = ol.Sys(syn.stride, syn.nb, rs, ci, arr, b)
+    S = ol.synth_system(preset, n_cpu)
     if ol.ref() is not None:
-        # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on
-        cores = threads or len(os.sched_getaffinity(0)) or ol.ref_max_threads()
+        cores = threads or physical_cores()
         ok, x, nit, wall, _ = ol.ref_cg(S, nssor=32, nthreads=cores)
         kind = "reference"
         # the reference's own SpMV, assign(y, A*x), 20 launches (SURVEY.md section 8(d)): GB/s by the algorithmic bytes
         # every roofline here uses, and by the bytes of the reference's padded layout
-        _, spmv_s = ol.ref_spmv(S, b, mode=0, nthreads=cores, reps=20)
-        st, cl = S.stride, S.stride + S.stride % 2
-        spmv = {"ms": 1e3 * spmv_s,
-                "gbs_algorithmic": (S.nnzb * (8 * st * st + 4) + 4 * (S.nb + 1) + 16 * S.n) / spmv_s / 1e9,
-                "gbs_padded_layout": (S.nnzb * (8 * st * cl + 4) + 8 * S.nb + 16 * S.n) / spmv_s / 1e9}
+        spmv_info = None
+        if spmv:
+            _, spmv_s = ol.ref_spmv(S, S.b, mode=0, nthreads=cores, reps=20)
+            spmv_info = spmv_rates(S.stride, S.nb, S.nnzb, spmv_s)
     else:
         cores = 1
         t0 = time.time()
         ok, x, info = ol.oracle_cg(S, nssor=32)
         wall, nit = time.time() - t0, info.nit
         kind = "port"
-        spmv = None
+        spmv_info = None
     return dict(dof_iter_per_s=S.n * nit / wall, it_per_s=nit / wall, nit=int(nit), wall=wall, cores=int(cores),
-                kind=kind, n=n_cpu, ndof=S.n, converged=bool(ok), spmv=spmv)
+                kind=kind, n=n_cpu, ndof=S.n, converged=bool(ok), spmv=spmv_info)
 
 
-def run_reference_arm(args, pkg, rank):
+def spmv_rates(st, nb, nnzb, spmv_s):
+    """The reference's assign(y, A*x): GB/s by the algorithmic bytes every roofline here uses
+    and by the bytes of the reference's padded layout."""
+    cl, n = st + st % 2, nb * st
+    return {"ms": 1e3 * spmv_s,
+            "gbs_algorithmic": (nnzb * (8 * st * st + 4) + 4 * (nb + 1) + 16 * n) / spmv_s / 1e9,
+            "gbs_padded_layout": (nnzb * (8 * st * cl + 4) + 8 * nb + 16 * n) / spmv_s / 1e9}
+
+
+def mesh_ndof(preset, n):
+    return (2 * n * n) if preset.startswith("S2") else (3 * n ** 3)
+
+
+def host_bytes_needed(preset, n):
+    """Host memory of ONE copy of the system in the reference layout + the solver's vectors (generous)."""
+    per_row = {"S3-hex": 27, "ASR-hex": 27, "S3-tet": 15, "S2-tri": 7}.get(preset, 27)
+    st = 2 if preset.startswith("S2") else 3
+    nb = mesh_ndof(preset, n) // st
+    return nb * per_row * (8 * st * (st + st % 2) + 8) + 16 * 8 * nb * st
+
+
+def same_size_sample(preset, n, eps, cores, want_x_path=None, spmv_reps=3):
+    """The reference's solve of the WORKLOAD-size system, truncated by a looser eps (maxit bounds only the restarts of
+    ConjugateGradient::solve, conjugategradient.cpp:93,121, never the inner loop, so a tolerance is the one way to get
+    a bounded sample of the same system).  The matrix is generated straight into the reference's storage."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if ol.ref() is None:
+        return None
+    t0 = time.time()
+    ret, x, nit, wall, spmv_s, dims = ol.ref_cg_synth(preset, n, eps=eps, nssor=32, nthreads=cores, spmv_reps=spmv_reps,
+                                                      want_x=want_x_path is not None)
+    out = {"workload": f"{preset}-{n}", "ndof": dims["nb"] * dims["stride"], "eps": eps, "nit": int(nit), "solve_s": wall,
+           "it_per_s": nit / wall if wall > 0 else None, "converged": bool(ret), "total_s": time.time() - t0,
+           "spmv": spmv_rates(dims["stride"], dims["nb"], dims["nnzb"], spmv_s) if spmv_s else None}
+    if want_x_path is not None:
+        np.save(want_x_path, x)
+        out["x_checksum"] = float(np.abs(x).sum())
+    return out
+
+
+def pick_same_size_n(preset, n):
+    """The workload size if one copy of it fits comfortably in host memory, else the largest smaller mesh that does."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    for cand in [n] + [c for c in (200, 175, 128, 96, 64) if c < n]:
+        if host_bytes_needed(preset, cand) * 1.25 < avail:
+            return cand
+    return min(n, 48)
+
+
+def run_reference_arm(args, rank):
+    """`--impl reference`: the unmodified reference (oracle/_ref) on the host cores; nothing of the product is loaded."""
     if rank != 0:
         return
-    N_work = 3 * args.n ** 3
+    ensure_cpu_env()
+    cores = physical_cores()
+    N_work = mesh_ndof(args.preset, args.n)
+    env = {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")}
+    if args.cpu_leg:
+        # called by the GPU arm: one small full solve (+ the reference's SpMV) and the same-size truncated solve
+        out = {"cores": cores, "env": env, "small": cpu_reference_rate(args.preset, args.cpu_n, cores)}
+        if args.pair_n:
+            out["same_size"] = same_size_sample(args.preset, args.pair_n, args.pair_eps, cores, want_x_path=args.pair_x)
+        print(json.dumps(out), flush=True)
+        return
+    # driver-launched: K bounded steps.  One full solve costs ~3e-7 n^4 s on 16 cores: size the mesh to the step budget.
+    budget = 200.0 / max(1, args.steps + args.warmup)
+    n_cpu = args.cpu_n
+    if not args.cpu_n_given:
+        n_cpu = 64 if not args.preset.startswith("S2") else 1024
+        for cand in ((96, 128) if not args.preset.startswith("S2") else (2048,)):
+            if 3e-7 * cand ** 4 * (16.0 / cores) < budget and cand <= args.n:
+                n_cpu = cand
+        n_cpu = min(n_cpu, args.n)
     rates = []
     for _ in range(args.warmup):
-        cpu_reference_rate(pkg, max(8, args.cpu_n // 2))
+        cpu_reference_rate(args.preset, max(8, n_cpu // 2), cores, spmv=False)
     t_all = time.time()
-    for _ in range(args.steps):
-        rates.append(cpu_reference_rate(pkg, args.cpu_n))
+    for k in range(args.steps):
+        rates.append(cpu_reference_rate(args.preset, n_cpu, cores, spmv=(k == args.steps - 1)))
     wall = time.time() - t_all
     r = rates[-1]
     dof_it = float(np.mean([q["dof_iter_per_s"] for q in rates]))
     value = dof_it / N_work
-    sample = (f"each step = one full ConjugateGradient::solve of S3-hex-{r['n']} ({r['ndof']} DOF, {r['nit']} it) by the "
-              f"{'compiled reference (oracle/_ref, OpenMP)' if r['kind'] == 'reference' else 'C oracle port'}; DOF*iter/s scaled by the DOF ratio "
-              f"to the S3-hex-{args.n} workload ({N_work} DOF)")
+    # once, outside the K steps: the same-size sample, so that the scaled figure can be checked against a direct one
+    same = None
+    if not args.no_same_size:
+        n_same = pick_same_size_n(args.preset, args.n)
+        same = same_size_sample(args.preset, n_same, args.pair_eps, cores)
+    sample = (f"each step = one full ConjugateGradient::solve of {args.preset}-{r['n']} ({r['ndof']} DOF, {r['nit']} it) by the "
+              f"{'compiled reference (oracle/_ref, OpenMP)' if r['kind'] == 'reference' else 'C oracle port'} on {cores} physical cores "
+              f"(OMP_PROC_BIND=close, OMP_PLACES=cores); DOF*iter/s scaled by the DOF ratio to the {args.preset}-{args.n} workload "
+              f"({N_work} DOF); `same_size` = one solve of the workload-size system itself, truncated at eps {args.pair_eps:g}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"S3-hex-{args.n}", "ndof": N_work, "eps": 1e-10, "nssor": 32, "maxit": -1},
+            "config": {"workload": f"{args.preset}-{args.n}", "ndof": N_work, "eps": 1e-10, "nssor": 32, "maxit": -1},
             "dof_iter_per_s": dof_it,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample, "spmv": r["spmv"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample, "spmv": r["spmv"],
+                             "env": env, "same_size": same},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+
+PAIR_EPS_DEFAULT = 1e-3      # --impl reference has no GPU to search with; the GPU arm searches (same_size_pair)
+
+
+def cpu_leg(args, pair_n, pair_eps, pair_x):
+    """cpu_baseline of the GPU arm: the reference arm in a process of its own (oracle/ libraries only, pinned threads)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-leg", "--preset", args.preset,
+           "--mesh-n", str(args.n), "--cpu-n", str(args.cpu_n)]
+    if pair_n:
+        cmd += ["--pair-n", str(pair_n), "--pair-eps", repr(pair_eps), "--pair-x", pair_x]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS")}
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1800)
+    if p.returncode != 0:
+        return {"error": p.stderr[-500:]}
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def upload_sample(pkg, preset, n, devices):
+    """What the drop-in pays per topology / per matrix: set_structure and set_values from HOST arrays in the
+    reference's padded layout (pageable memory, as a valarray is), on a mesh whose host copy is practical."""
+    syn = pkg.Synth(preset, n)
+    rs, ci, arr, b = syn.rows()
+    A = pkg.CoordinateIndexedSparseMatrix(rs, ci, syn.stride, arr)
+    asm = pkg.Assembly(A, b, devices=devices) if devices else pkg.Assembly(A, b, device=0)
+    asm.sync_matrix()
+    asm.values_changed()
+    asm.sync_matrix()              # second upload: allocations and first-touch costs are behind
+    st = asm.stats()
+    out = {"workload": f"{preset}-{n}", "ndof": int(st.ndof), "structure_ms": st.structure_ms, "values_ms": st.values_ms,
+           "values_host_bytes": int(arr.nbytes), "values_GBs": arr.nbytes / (st.values_ms * 1e-3) / 1e9,
+           "note": "host arrays in the reference's padded layout, pageable memory; K-Repack to the compact device layout inside"}
+    asm.close()
+    return out
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -169,24 +311,37 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mesh-n", dest="n", type=int, default=int(os.environ.get("AMIE_BENCH_N", 256)), help="nodes per side of S3-hex-n (256 -> 50.3 M DOF)")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=None, help="nodes per side (default: 256 for the 3D presets -> 50.3 M DOF hexahedra, 4096 for S2-tri)")
     ap.add_argument("--preset", default="S3-hex")
-    ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("AMIE_BENCH_CPU_N", 64)), help="size of the CPU baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=None, help="size of the CPU arm's full-solve sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-same-size", action="store_true", help="skip the workload-size truncated reference solve")
+    ap.add_argument("--no-upload", action="store_true", help="skip the set_structure / set_values timing sample")
     ap.add_argument("--spmv-variant", type=int, default=0, help="kernel selection for A/B runs (option spmv_variant; 0 = the shipped default)")
+    ap.add_argument("--single-process", action="store_true", help="--gpus N without torchrun: ONE context over N devices")
+    # internal: the GPU arm's cpu_baseline leg
+    ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--pair-n", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--pair-eps", type=float, default=PAIR_EPS_DEFAULT, help=argparse.SUPPRESS)
+    ap.add_argument("--pair-x", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.n is None:
+        args.n = int(os.environ.get("AMIE_BENCH_N", 4096 if args.preset.startswith("S2") else 256))
+    args.cpu_n_given = args.cpu_n is not None
+    if args.cpu_n is None:
+        args.cpu_n = int(os.environ.get("AMIE_BENCH_CPU_N", 1024 if args.preset.startswith("S2") else 64))
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
 
+    if args.impl == "reference":
+        run_reference_arm(args, rank)       # never loads the product library
+        return 0
+
     import __graft_entry__ as g
     pkg = g.load_package()
-
-    if args.impl == "reference":
-        run_reference_arm(args, pkg, rank)
-        return 0
 
     import torch
     if not torch.cuda.is_available():
@@ -199,12 +354,18 @@ def main():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if world > 1:
-        from bench_dist import run_distributed          # row-partitioned path
+        from bench_dist import run_distributed          # row-partitioned path, one process per GPU
         return run_distributed(args, pkg, dist, rank, world, local_rank)
+
+    devices = None
+    if args.gpus > 1:
+        if not args.single_process:
+            raise SystemExit("bench.py --gpus N: launch with torch.distributed.run (one process per GPU) or pass --single-process")
+        devices = list(range(args.gpus))
 
     # ---- build the system directly in HBM
     syn = pkg.Synth(args.preset, args.n)
-    asm = pkg.Assembly(device=local_rank)
+    asm = pkg.Assembly(devices=devices) if devices else pkg.Assembly(device=local_rank)
     t0 = time.time()
     syn.to_device(asm)
     gen_s = time.time() - t0
@@ -214,10 +375,11 @@ def main():
     st = asm.stats()
     N, nb, nnzb, s = st.ndof, st.nb, st.nnzb, st.stride
     algo_bytes = st.spmv_algorithmic_bytes
+    ngpu = max(1, args.gpus)
 
-    def resident_step():
+    def resident_step(eps=1e-10):
         asm.upload_x0(None)
-        ok, nit, err, rho = asm.pcg_resident(nssor=32)
+        ok, nit, err, rho = asm.pcg_resident(nssor=32, eps=eps)
         return ok, nit, asm.stats()
 
     for _ in range(args.warmup):
@@ -247,8 +409,10 @@ def main():
     value = its / (dev_ms * 1e-3)
     spmv_avg_ms = spmv_ms / max(1, spmv_n)
     peak, peak_src = measured_peak()
-    achieved = algo_bytes / (spmv_avg_ms * 1e-3) / 1e9
+    # per-GPU figure: on a multi-device context every device moves its share of the bytes in the (slowest device's) launch time
+    achieved = algo_bytes / ngpu / (spmv_avg_ms * 1e-3) / 1e9
     iter_bytes = algo_bytes + 120 * N           # + K-Update (7R+4W) + K-Dir (3R+1W), Kahan compensators kept
+    x_checksum = float(np.abs(asm.download_x()).sum())
 
     # ---- e2e: host (pinned) buffers through the C-ABI call
     e2e = None
@@ -275,38 +439,97 @@ def main():
         e2e = {"value": e_its / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(2 * N * 8), "d2h_bytes_per_step": int(N * 8),
                "x_checksum": float(np.abs(x_host).sum())}
 
-    # ---- CPU baseline (rank 0, bounded sample)
+    # ---- CPU baseline (rank 0, bounded samples, in a process of its own)
     cpu = None
     if not args.no_cpu:
-        r = cpu_reference_rate(pkg, args.cpu_n)
-        cpu = {"value": r["dof_iter_per_s"] / N, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-               "dof_iter_per_s": r["dof_iter_per_s"], "spmv": r["spmv"],
-               "sample": f"one full ConjugateGradient::solve of S3-hex-{r['n']} ({r['ndof']} DOF, {r['nit']} it, {r['wall']:.1f} s); "
-                         f"DOF*iter/s scaled by the DOF ratio to this workload ({N} DOF)"}
+        pair_n, pair = 0, None
+        pair_x = os.path.join("/tmp", f"amie_bench_pair_x_{os.getpid()}.npy")
+        if not args.no_same_size:
+            # the same system on both sides, the solve truncated by a looser eps.  The GPU searches the tolerance that
+            # gives a bounded number of iterations; the reference then solves with exactly that eps.
+            pair_n = pick_same_size_n(args.preset, args.n)
+            pasm, psyn = asm, syn
+            if pair_n != args.n:
+                psyn = pkg.Synth(args.preset, pair_n)
+                pasm = pkg.Assembly(device=local_rank)
+                psyn.to_device(pasm)
+            pair_eps, g_nit, g_ms = None, 0, 0.0
+            for eps in (1e-1, 3e-2, 1e-2, 3e-3, 1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 1e-6, 1e-7):
+                pasm.upload_x0(None)
+                ok, g_nit, _, _ = pasm.pcg_resident(nssor=32, eps=eps)
+                g_ms = pasm.stats().solve_ms
+                pair_eps = eps
+                if g_nit >= 60:
+                    break
+            x_gpu = pasm.download_x()
+            pair = {"workload": f"{args.preset}-{pair_n}", "eps": pair_eps, "gpu_nit": int(g_nit), "gpu_solve_ms": g_ms,
+                    "gpu_it_per_s": g_nit / (g_ms * 1e-3) if g_ms else None, "gpus": ngpu if pasm is asm else 1}
+            if pasm is not asm:
+                pasm.close()
+        r = cpu_leg(args, pair_n, pair["eps"] if pair else PAIR_EPS_DEFAULT, pair_x)
+        if "error" in r:
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "reference", "sample": "cpu leg failed: " + r["error"]}
+        else:
+            small, same = r["small"], r.get("same_size")
+            if same and pair:
+                x_ref = np.load(pair_x)
+                os.remove(pair_x)
+                pair.update({"ref_nit": same["nit"], "ref_solve_s": same["solve_s"], "ref_it_per_s": same["it_per_s"],
+                             "rel_l2_x_gpu_vs_ref": float(np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref)),
+                             "ref_spmv": same["spmv"], "ref_total_s": same["total_s"]})
+                del x_ref
+            same_config = bool(same and pair and pair_n == args.n)
+            if same and pair:
+                # iterations/s of the truncated solve of the workload-size system (pre- and post-smoothing included, as in
+                # every reference solve), scaled by the DOF ratio only when host memory forced a smaller mesh
+                value_cpu = same["it_per_s"] * (same["ndof"] / N)
+                sample = (f"the reference's ConjugateGradient::solve of {same['workload']} ({same['ndof']} DOF) truncated at eps {pair['eps']:g}: "
+                          f"{same['nit']} it in {same['solve_s']:.1f} s on {r['cores']} physical cores (OMP_PROC_BIND=close, OMP_PLACES=cores)"
+                          + ("" if same_config else f"; scaled by the DOF ratio to this workload ({N} DOF): host memory did not hold the full-size matrix"))
+            else:
+                value_cpu = small["dof_iter_per_s"] / N
+                sample = (f"one full ConjugateGradient::solve of {args.preset}-{small['n']} ({small['ndof']} DOF, {small['nit']} it, {small['wall']:.1f} s); "
+                          f"DOF*iter/s scaled by the DOF ratio to this workload ({N} DOF)")
+            cpu = {"value": value_cpu, "unit": UNIT, "cores": r["cores"], "kind": small["kind"], "sample": sample,
+                   "same_config": same_config, "same_size_pair": pair, "env": r["env"],
+                   "full_solve_small_mesh": {"workload": f"{args.preset}-{small['n']}", "nit": small["nit"], "wall_s": small["wall"],
+                                             "dof_iter_per_s": small["dof_iter_per_s"], "scaled_it_per_s": small["dof_iter_per_s"] / N,
+                                             "spmv": small["spmv"]}}
+
+    upload = None
+    if not args.no_upload:
+        up_n = {"S3-hex": 128, "ASR-hex": 128, "S3-tet": 160, "S2-tri": 2048}.get(args.preset, 128)
+        upload = upload_sample(pkg, args.preset, min(up_n, args.n), devices)
 
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.preset}-{args.n}/1", {}).get("bytes")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.preset}-{args.n}/{ngpu}", {}).get("bytes")
     except Exception:
         pass
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    if s == 3:
+        kernel = "k_spmv_s3_rt" + ("m" if args.spmv_variant in (4, 5, 6, 7) else "") + "<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)"
+    else:
+        kernel = "k_spmv_s2_rt<DOT_YX> (row-thread TMA pipeline, 2x2 blocks)"
+    par = None
+    if devices:
+        par = f"row-partition x{ngpu} inside ONE context (one caller thread, one worker thread per device); halo + 2-double reductions over NVLink peer memory"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.preset}-{args.n}", "ndof": int(N), "block_rows": int(nb), "blocks": int(nnzb), "stride": int(s),
                        "eps": 1e-10, "nssor": 32, "maxit": -1, "precond": "InverseDiagonal",
                        "step": "one full PCG solve (reference control flow)", "iterations_per_step": its / max(1, args.steps),
                        "l2": "matrix (%.1f GB) is far larger than L2; no flush needed" % (nnzb * (8 * s * s + 4) / 1e9),
-                       "generate_s": gen_s},
+                       "generate_s": gen_s, **({"parallelism": par} if par else {})},
             "converged": bool(conv), "wall_ms_per_step": wall_ms / max(1, args.steps),
             "dof_iter_per_s": value * N, "smoothing_spmv_per_step": smoothing / max(1, args.steps),
-            "pcg_iteration_gbs": iter_bytes * value / 1e9,
+            "pcg_iteration_gbs": iter_bytes * value / 1e9, "x_checksum": x_checksum,
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": (("k_spmv_s3_rt<DOT_NONE> (q = A p; p.q as a separate pass: AMIE_B200_SPLIT_DOT)" if SPLIT_DOT else
-                                                          "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)") if s == 3 else "k_spmv_s2_rt<DOT_YX> (row-thread TMA pipeline, 2x2 blocks)"),
-                         "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
+                         "traffic": traffic, "kernel": kernel,
+                         "algorithmic_bytes_per_launch": int(algo_bytes // ngpu), "launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "peak_source": peak_src},
-            "e2e": e2e, "cpu_baseline": cpu}
+            "e2e": e2e, "cpu_baseline": cpu, "upload": upload}
     print(json.dumps(line), flush=True)
     asm.close()
     return 0

@@ -1,15 +1,23 @@
 """Row-partitioned leg of bench.py (N > 1): one process per GPU, launched by torch.distributed.run.
 
 STRONG scaling: the same S3-hex-n system is split into N contiguous block-row ranges balanced by
-stored blocks; each rank generates its own rows directly in HBM.  The p-halo travels by NCCL
-send/recv overlapped with the interior SpMV and the two dot products per iteration are 2-double
-all-reduces (xfem-amie_b200/csrc/dist.cu).  Time = max over ranks of the CUDA-event solve time.
+stored blocks; each rank generates its own rows directly in HBM.  The p-halo is pushed straight into
+the neighbours' memory over NVLink (cudaIpc-mapped peer stores + device-side flags), overlapped with
+the interior SpMV; the two dot products per iteration are combined through peer mailboxes, every rank
+adding the partial sums in rank order (xfem-amie_b200/csrc/dist.cu; AMIE_B200_TRANSPORT=nccl selects
+the NCCL send/recv + allreduce path).  Time = max over ranks of the CUDA-event solve time.
+The line carries `x_checksum` (sum of |x| over all ranks) and the iteration count, to be compared with
+the N = 1 line of bench.py: the partitioned solve must reproduce the single-device answer.
 """
 import ctypes
 import json
 import time
 
 import numpy as np
+
+
+# sum |x| of the single-device solve (bench.py, N = 1, profiles/): the partitioned solve must land on the same field
+X_CHECKSUM_1GPU = {("S3-hex", 256): 6789467.724700802}
 
 
 def run_distributed(args, pkg, dist, rank, world, local_rank):
@@ -77,6 +85,7 @@ def run_distributed(args, pkg, dist, rank, world, local_rank):
     wall_ms = 1e3 * (time.time() - t_wall)
     clocks = sampler.stop()
 
+    x_checksum = sumf(float(np.abs(asm.download_x()).sum()))
     dev_ms_max = maxf(dev_ms)
     spmv_avg_ms = maxf(spmv_ms / max(1, spmv_n))
     algo_bytes_total = sumf(st.spmv_algorithmic_bytes)
@@ -122,6 +131,9 @@ def run_distributed(args, pkg, dist, rank, world, local_rank):
                            "halo_block_columns_max": int(halo_max), "l2": "per-rank matrix is far larger than L2; no flush needed",
                            "generate_s": gen_s},
                 "converged": bool(conv), "wall_ms_per_step": wall_ms / max(1, args.steps), "dof_iter_per_s": value * N_glob,
+                "x_checksum": x_checksum, "nit": int(its // max(1, args.steps)),
+                "x_checksum_rel_to_1gpu": (abs(x_checksum / X_CHECKSUM_1GPU[(args.preset, args.n)] - 1.0)
+                                           if (args.preset, args.n) in X_CHECKSUM_1GPU else None),
                 "clocks": clocks, "gpu_launches": launches_total,
                 "roofline": {"bound": "hbm", "achieved": achieved_per_gpu, "peak": peak, "unit": "GB/s", "frac": achieved_per_gpu / peak,
                              "traffic": None, "kernel": "k_spmv_s3_rt (per GPU, interior + boundary launches incl. halo wait)",

@@ -11,6 +11,13 @@
 //   amie_e2e_* 2dst <sampling> <out.bin>            examples/main_tension_benchmark.cpp --space-time (:96-157) with its default
 //                                                   parameters: notched space-time damage sample, first step + 3 load steps;
 //                                                   the solver sees rowstart = colstart > 0 (space-time planes)
+//   amie_e2e_* tripoint <sampling> <out.bin> [nsteps [max_iterations_per_step]]
+//                                                   examples/main_tripoint.cpp:274-559 with its usual arguments `<sampling> 0 3.9 1.2`
+//                                                   (no stirrups): the reinforced-concrete half beam in three-point bending,
+//                                                   ConcreteBehaviour + VonMises rebars in layers; nsteps load steps of the
+//                                                   driver's loop (:115-130), every step re-solving on ONE topology while damage
+//                                                   changes the values (BASELINE.json config 4).  out.bin then holds one record
+//                                                   per load step.
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -34,6 +41,10 @@
 #include "features/inclusion3d.h"
 #include "physics/stiffness.h"
 #include "physics/stiffness_with_imposed_deformation.h"
+#include "physics/stiffness_and_fracture.h"
+#include "physics/void_form.h"
+#include "physics/fracturecriteria/vonmises.h"
+#include "physics/materials/concrete_behaviour.h"
 #include "physics/viscoelasticity_and_fracture.h"
 #include "physics/damagemodels/spacetimeisotropiclineardamage.h"
 #include "physics/fracturecriteria/maxstrain.h"
@@ -45,9 +56,9 @@
 
 using namespace Amie ;
 
-static void write_vec(const char * path, const Vector & v)
+static void write_vec(const char * path, const Vector & v, const char * how = "wb")
 {
-    FILE * f = fopen(path, "wb") ;
+    FILE * f = fopen(path, how) ;
     uint64_t n = v.size() ;
     fwrite(&n, 8, 1, f) ;
     fwrite(&v[0], 8, n, f) ;
@@ -236,6 +247,108 @@ int main(int argc, char ** argv)
         write_vec(argv[3], F.getDisplacements()) ;
         if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
         fprintf(stderr, "2dst: rowstart %zu colstart %zu\n", (size_t)F.getAssembly()->rowstart, (size_t)F.getAssembly()->colstart) ;
+    }
+    else if(mode == "tripoint")
+    {
+        // the set-up of examples/main_tripoint.cpp:274-556 for `tripoint <sampling> 0 3.9 1.2`, call by call
+        const size_t nsteps = argc > 4 ? (size_t)atoi(argv[4]) : 3 ;
+        const int maxiter = argc > 5 ? atoi(argv[5]) : 900 ;
+        const double softeningFactor = M_PI*.24 ;
+        const double sampleLength = 3.9, sampleHeight = 1.2, supportLever = sampleLength*.5-.250 ;
+        const double supportMidPointToEndClearance = 0.25, platewidth = 0.15, plateHeight = 0.051 ;
+        const double rebarDiametre = 0.025, rebarEndCover = 0.047, phi = 3.*rebarDiametre ;
+        const double compressionCrit = -34.2e6 ;
+        const double E_steel = 200e9, nu_steel = 0.01, nu = 0.3, E_paste = 37e9 ;
+        const double E_steel_effective = M_PI*0.5*rebarDiametre*rebarDiametre*E_steel/(rebarDiametre*rebarDiametre)*.75 ;
+        const double halfSampleOffset = sampleLength*.25 ;
+        Matrix m0_steel = Tensor::cauchyGreen(E_steel, nu_steel, SPACE_TWO_DIMENSIONAL, PLANE_STRAIN, YOUNG_POISSON) ;
+        Matrix m0_steel_effective = Tensor::cauchyGreen(E_steel_effective, nu_steel, SPACE_TWO_DIMENSIONAL, PLANE_STRAIN, YOUNG_POISSON) ;
+
+        RectangularFeature sample(nullptr, sampleLength*.5, sampleHeight+2.*plateHeight, halfSampleOffset, 0) ;
+        RectangularFeature samplebulk(nullptr, sampleLength*.5, sampleHeight+2.*plateHeight, halfSampleOffset, 0) ;
+        RectangularFeature topsupport(nullptr, platewidth, plateHeight, platewidth*.5, sampleHeight*.5+plateHeight*.5) ;
+        topsupport.setBehaviour(new Stiffness(m0_steel)) ;
+        RectangularFeature topsupportbulk(nullptr, platewidth, plateHeight, platewidth*.5, sampleHeight*.5+plateHeight*.5) ;
+        topsupportbulk.setBehaviour(new Stiffness(m0_steel)) ;
+        RectangularFeature toprightvoid(nullptr, sampleLength*.5-platewidth, plateHeight, (sampleLength*.5-platewidth)*.5+platewidth, sampleHeight*.5+plateHeight*.5) ;
+        toprightvoid.setBehaviour(new VoidForm()) ;
+        RectangularFeature toprightvoidbulk(nullptr, sampleLength*.5-platewidth, plateHeight, (sampleLength*.5-platewidth)*.5+platewidth, sampleHeight*.5+plateHeight*.5) ;
+        toprightvoidbulk.setBehaviour(new VoidForm()) ;
+        RectangularFeature baseright(platewidth, plateHeight, supportLever, -sampleHeight*.5-plateHeight*.5) ;
+        baseright.setBehaviour(new Stiffness(m0_steel)) ;
+        RectangularFeature baserightbulk(platewidth, plateHeight, supportLever, -sampleHeight*.5-plateHeight*.5) ;
+        baserightbulk.setBehaviour(new Stiffness(m0_steel)) ;
+        RectangularFeature bottomcentervoid(supportLever-platewidth*.5, plateHeight, (supportLever-platewidth*.5)*.5, -sampleHeight*.5-plateHeight*.5) ;
+        bottomcentervoid.setBehaviour(new VoidForm()) ;
+        bottomcentervoid.isVirtualFeature = true ;
+        RectangularFeature rightbottomvoid(supportMidPointToEndClearance-platewidth*.5, plateHeight, sampleLength*.5-(supportMidPointToEndClearance-platewidth*.5)*.5, -sampleHeight*.5-plateHeight*.5) ;
+        rightbottomvoid.setBehaviour(new VoidForm()) ;
+        rightbottomvoid.isVirtualFeature = true ;
+        RectangularFeature bottomcentervoidbulk(supportLever-platewidth*.5, plateHeight, (supportLever-platewidth*.5)*.5, -sampleHeight*.5-plateHeight*.5) ;
+        bottomcentervoidbulk.setBehaviour(new VoidForm()) ;
+        RectangularFeature rightbottomvoidbulk(supportMidPointToEndClearance-platewidth*.5, plateHeight, sampleLength*.5-(supportMidPointToEndClearance-platewidth*.5)*.5, -sampleHeight*.5-plateHeight*.5) ;
+        rightbottomvoidbulk.setBehaviour(new VoidForm()) ;
+
+        const double rebarcenter = (sampleLength*.5-rebarEndCover)*.5, rebarlength = (sampleLength-rebarEndCover*2.)*.5 ;
+        const double rebary[4] = { -sampleHeight*.5+0.064, -sampleHeight*.5+0.064+0.085, sampleHeight*.5-0.064, sampleHeight*.5-0.064-0.085 } ;
+        std::vector<RectangularFeature *> rebar ;
+        for(int i = 0 ; i < 4 ; i++)
+        {
+            rebar.push_back(new RectangularFeature(&sample, rebarlength, rebarDiametre, rebarcenter, rebary[i])) ;
+            rebar.back()->setBehaviour(new StiffnessAndFracture(m0_steel_effective*softeningFactor, new VonMises(490e6))) ;
+        }
+
+        FeatureTree F(&samplebulk, .4-3.*rebarDiametre) ;
+        for(RectangularFeature * conc : { &samplebulk, &sample })
+        {
+            conc->setBehaviour(new ConcreteBehaviour(E_paste, nu, compressionCrit, PLANE_STRAIN, UPPER_BOUND, SPACE_TWO_DIMENSIONAL)) ;
+            ConcreteBehaviour * cb = dynamic_cast<ConcreteBehaviour *>(conc->getBehaviour()) ;
+            cb->variability = 0.00 ;
+            cb->rebarLocationsAndDiameters.push_back(std::make_pair(rebar[0]->getCenter().getY(), rebarDiametre)) ;
+            cb->rebarLocationsAndDiameters.push_back(std::make_pair(rebar[1]->getCenter().getY(), rebarDiametre)) ;
+        }
+        samplebulk.getBehaviour()->setSource(sample.getPrimitive()) ;
+        sample.isVirtualFeature = true ;
+
+        const int rebarlayer = -1 ;
+        F.addFeature(nullptr, &sample, rebarlayer, phi) ;
+        F.addFeature(&samplebulk, &baserightbulk) ;
+        F.addFeature(&sample, &baseright, rebarlayer, phi) ;
+        F.addFeature(&baseright, &bottomcentervoid, rebarlayer, phi) ;
+        F.addFeature(&baseright, &rightbottomvoid, rebarlayer, phi) ;
+        F.addFeature(&samplebulk, &topsupportbulk) ;
+        F.addFeature(&sample, &topsupport, rebarlayer, phi) ;
+        F.addFeature(&topsupportbulk, &toprightvoidbulk) ;
+        F.addFeature(&topsupport, &toprightvoid, rebarlayer, phi) ;
+        F.addFeature(&baserightbulk, &bottomcentervoidbulk) ;
+        F.addFeature(&baserightbulk, &rightbottomvoidbulk) ;
+        for(int i = 0 ; i < 4 ; i++) F.addFeature(&samplebulk, rebar[i], rebarlayer, phi) ;
+        F.setSamplingFactor(rebar[2], 1./20) ;
+        F.setSamplingFactor(rebar[3], 1./20) ;
+        F.setSamplingFactor(&baseright, 2) ;
+        F.setSamplingFactor(&topsupport, 2) ;
+        F.setSamplingNumber(sampling) ;
+        F.setSamplingRestriction(0) ;
+        F.setMaxIterationsPerStep(maxiter) ;
+        F.thresholdScoreMet = 0.001 ;
+        F.addPoint(new Point(supportLever, -sampleHeight*.5-plateHeight)) ;
+        F.addPoint(new Point(platewidth, sampleHeight*.5)) ;
+        BoundingBoxAndRestrictionDefinedBoundaryCondition * load = new BoundingBoxAndRestrictionDefinedBoundaryCondition(SET_ALONG_ETA, TOP, -platewidth, platewidth, -10, 10, 0.) ;
+        F.addBoundaryCondition(load) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, LEFT)) ;
+        F.addBoundaryCondition(new BoundingBoxNearestNodeDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM, Point(supportLever, -sampleHeight*.5-plateHeight))) ;
+        F.setOrder(LINEAR) ;
+
+        // the driver's loop (:115-130): a load step, and the next displacement increment once it converged
+        const double delta_d = argc > 6 ? atof(argv[6]) : 5.*0.0175e-3 ;
+        for(size_t v = 0 ; v < nsteps ; v++)
+        {
+            const bool go_on = F.step() ;
+            if(go_on) load->setData(load->getData()-delta_d) ;
+            write_vec(argv[3], F.getDisplacements(-1, false), v ? "ab" : "wb") ;
+            fprintf(stderr, "tripoint: load step %zu converged %d unknowns %zu average damage %g\n", v, (int)go_on,
+                    (size_t)F.getDisplacements(-1, false).size(), F.averageDamage) ;
+        }
     }
     else if(mode == "2d")
     {

@@ -180,6 +180,52 @@ int amie_ref_cg(int stride, uint64_t nb, const uint32_t * row_size, const uint32
     return ok ? 1 : 0 ;
 }
 
+// The same solve on a system the caller generates IN PLACE: `fill(user, column_index, array_padded, forces)` writes
+// straight into the reference's own storage, so a benchmark-size matrix (43 GB of padded values at 50 M DOF) exists
+// once in host memory, not twice.  spmv_reps > 0 additionally times assign(y, A*b) on that matrix (seconds per call).
+typedef int (*amie_ref_fill_fn)(void * user, uint32_t * column_index, double * array_padded, double * forces) ;
+int amie_ref_cg_fill(int stride, uint64_t nb, const uint32_t * row_size, uint64_t nnzb, amie_ref_fill_fn fill, void * user,
+                     double eps, int maxit, uint64_t nssor, int nthreads, int spmv_reps,
+                     double * x_out, uint64_t * nit_out, double * wall_s_out, double * spmv_s_out, char * log, uint64_t logcap)
+{
+#ifdef HAVE_OPENMP
+    if(nthreads > 0) omp_set_num_threads(nthreads) ;
+#endif
+    Amie::Assembly a ;
+    {
+        std::valarray<unsigned int> rs(row_size, nb) ;
+        std::valarray<unsigned int> ci(0u, nnzb) ;
+        a.coordinateIndexedMatrix = new Amie::CoordinateIndexedSparseMatrix(rs, ci, (size_t)stride) ;
+    }
+    a.externalForces.resize(nb*stride) ;
+    a.externalForces = 0. ;
+    a.displacements.resize(nb*stride) ;
+    a.displacements = 0. ;
+    static_assert(sizeof(unsigned int) == sizeof(uint32_t), "column_index element type") ;
+    if(fill(user, reinterpret_cast<uint32_t *>(&a.coordinateIndexedMatrix->column_index[0]), &a.coordinateIndexedMatrix->array[0], &a.externalForces[0]))
+        return -1 ;
+    CerrCapture cap ;
+    if(spmv_reps > 0 && spmv_s_out)
+    {
+        Vector y(0., nb*stride) ;
+        Amie::assign(y, (*a.coordinateIndexedMatrix)*a.externalForces, 0, 0) ;          // first touch
+        double t0 = now() ;
+        for(int r = 0 ; r < spmv_reps ; r++) Amie::assign(y, (*a.coordinateIndexedMatrix)*a.externalForces, 0, 0) ;
+        *spmv_s_out = (now()-t0)/spmv_reps ;
+    }
+    Amie::ConjugateGradient cg(&a) ;
+    cg.nssor = nssor ;
+    Vector vx0(0., 0) ;
+    double t0 = now() ;
+    bool ok = cg.solve(vx0, nullptr, eps, maxit, false) ;
+    double t1 = now() ;
+    if(x_out) std::memcpy(x_out, &cg.x[0], cg.x.size()*sizeof(double)) ;
+    if(nit_out) *nit_out = cg.nit ;
+    if(wall_s_out) *wall_s_out = t1-t0 ;
+    copy_log(cap.sink.str(), log, logcap) ;
+    return ok ? 1 : 0 ;
+}
+
 int amie_ref_bicgstab(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
                       const double * array_padded, const double * b, const double * x0, uint64_t nx0,
                       int precond_kind, double eps, int maxit, int nthreads,

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# multi-device contexts (tests/test_gpu_group.py) need eager CUDA module loading, decided when CUDA initialises:
+# before torch or the library touch the driver (xfem-amie_b200/csrc/group.cu)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np
 import pytest
 

@@ -59,6 +59,49 @@ def ref():
     return _ref
 
 
+_synth = None
+
+
+def synth_lib():
+    """oracle/libamie_synth.so: the synthetic-mesh generator as a host-only library (no CUDA library in the process)."""
+    global _synth
+    if _synth is None:
+        so = os.path.join(ORACLE_DIR, "libamie_synth.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "libamie_synth.so"], stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(so)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.amie_b200_synth_create.restype = vp
+        L.amie_b200_synth_create.argtypes = [ctypes.c_char_p, ci, u64]
+        L.amie_b200_synth_destroy.argtypes = [vp]
+        L.amie_b200_synth_sizes.argtypes = [vp, vp, vp, vp]
+        L.amie_b200_synth_count.argtypes = [vp, u64, u64, vp, vp]
+        L.amie_b200_synth_fill.argtypes = [vp, u64, u64, vp, vp, vp]
+        _synth = L
+    return _synth
+
+
+def synth_system(preset, n, seed=1):
+    """The S3-hex-n / S3-tet-n / S2-tri-n / ASR-hex-n system of SURVEY.md section 8(d) as a Sys, generated on the host."""
+    L = synth_lib()
+    h = L.amie_b200_synth_create(preset.encode(), int(n), int(seed))
+    if not h:
+        raise ValueError(f"unknown synthetic preset {preset!r}")
+    h = ctypes.c_void_p(h)
+    st, nb, tot = ctypes.c_int(), u64(), u64()
+    L.amie_b200_synth_sizes(h, ctypes.byref(st), ctypes.byref(nb), None)
+    rs = np.zeros(nb.value, np.uint32)
+    L.amie_b200_synth_count(h, 0, nb.value, _vp(rs), ctypes.byref(tot))
+    s = st.value
+    ci = np.zeros(tot.value, np.uint32)
+    arr = np.zeros(tot.value * s * (s + s % 2))
+    b = np.zeros(nb.value * s)
+    rc = L.amie_b200_synth_fill(h, 0, nb.value, _vp(ci), _vp(arr), _vp(b))
+    L.amie_b200_synth_destroy(h)
+    assert rc == 0
+    return Sys(s, nb.value, rs, ci, arr, b)
+
+
 class Sys:
     """A block-sparse system in the reference layout (numpy arrays)."""
 
@@ -177,6 +220,40 @@ def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, col
                         int(maxit), u64(nssor), u64(rowstart), u64(colstart), int(nthreads), _vp(x),
                         ctypes.byref(nit), ctypes.byref(wall), log, u64(8192))
     return ret, x, nit.value, wall.value, log.value.decode(errors="replace")
+
+
+def ref_cg_synth(preset, n, eps=1e-10, maxit=-1, nssor=32, nthreads=1, spmv_reps=0, seed=1, want_x=True):
+    """The reference's ConjugateGradient::solve on the synthetic system `preset`-n, generated straight into the
+    reference's own storage (one copy of the matrix in host memory: benchmark sizes).  Returns
+    (ret, x or None, nit, solve seconds, seconds per assign(y, A*b) or None, dict(stride, nb, nnzb))."""
+    R, L = ref(), synth_lib()
+    h = L.amie_b200_synth_create(preset.encode(), int(n), int(seed))
+    if not h:
+        raise ValueError(f"unknown synthetic preset {preset!r}")
+    h = ctypes.c_void_p(h)
+    st, nb, tot = ctypes.c_int(), u64(), u64()
+    L.amie_b200_synth_sizes(h, ctypes.byref(st), ctypes.byref(nb), None)
+    rs = np.zeros(nb.value, np.uint32)
+    L.amie_b200_synth_count(h, 0, nb.value, _vp(rs), ctypes.byref(tot))
+    FILL = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+    def fill(user, ci, arr, forces):
+        return L.amie_b200_synth_fill(h, 0, nb.value, ci, arr, forces)
+    cb = FILL(fill)
+    x = np.zeros(nb.value * st.value) if want_x else None
+    nit, wall, spmv_s = u64(), f64(), f64(-1.0)
+    log = ctypes.create_string_buffer(8192)
+    R.amie_ref_cg_fill.argtypes = [ctypes.c_int, u64, ctypes.c_void_p, u64, FILL, ctypes.c_void_p, f64, ctypes.c_int, u64,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_char_p, u64]
+    ret = R.amie_ref_cg_fill(st.value, nb.value, _vp(rs), tot.value, cb, None, eps, int(maxit), int(nssor), int(nthreads),
+                             int(spmv_reps), _vp(x), ctypes.cast(ctypes.byref(nit), ctypes.c_void_p),
+                             ctypes.cast(ctypes.byref(wall), ctypes.c_void_p), ctypes.cast(ctypes.byref(spmv_s), ctypes.c_void_p),
+                             log, 8192)
+    L.amie_b200_synth_destroy(h)
+    if ret < 0:
+        raise RuntimeError("amie_ref_cg_fill: the generator failed")
+    return ret, x, nit.value, wall.value, (spmv_s.value if spmv_reps > 0 else None), dict(stride=st.value, nb=nb.value, nnzb=tot.value)
 
 
 def ref_bicgstab(S, x0=None, precond=0, eps=1e-10, maxit=-1, nthreads=1, b=None, diag=None):

@@ -217,7 +217,6 @@ amie_b200_ctx * amie_b200_create(const int * devices, int ndev)
     amie_b200_ctx * ctx = new amie_b200_ctx ;
     ctx->device = dev ;
     ctx->num_sms = prop.multiProcessorCount ;
-    if(const char * e = getenv("AMIE_B200_SPLIT_DOT")) ctx->opt_split_dot = atoi(e) ;
     G_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) ;
     G_TRY(cudaMalloc(&ctx->st, sizeof(KrylovState))) ;
     G_TRY(cudaMemset(ctx->st, 0, sizeof(KrylovState))) ;
@@ -274,7 +273,6 @@ int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
     else if(k == "verbose") ctx->opt_verbose = (int)value ;
     else if(k == "iters_per_batch") ctx->opt_batch = (int)value ;
     else if(k == "graph") ctx->opt_graph = (int)value ;
-    else if(k == "split_dot") ctx->opt_split_dot = (int)value ;
     else if(k == "assemble_variant") ctx->opt_assemble_variant = (int)value ;
     else if(k == "dirichlet_variant") ctx->opt_dirichlet_variant = (int)value ;
     else if(k == "fields_variant") ctx->opt_fields_variant = (int)value ;

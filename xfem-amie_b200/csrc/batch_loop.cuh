@@ -8,9 +8,8 @@
 #pragma once
 #include "launch.cuh"
 
-// what a captured batch depends on besides the arguments checked below: the SpMV kernel selection and the shape of
-// an iteration (split_dot adds a kernel)
-static inline int graph_variant_key(const amie_b200_ctx * ctx) { return ctx->opt_variant+(ctx->opt_split_dot ? 1000 : 0) ; }
+// what a captured batch depends on besides the arguments checked below: the SpMV kernel selection
+static inline int graph_variant_key(const amie_b200_ctx * ctx) { return ctx->opt_variant ; }
 
 template<typename QueueOne>
 static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot & slot, bool use_graph, int batch,
@@ -29,8 +28,10 @@ static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot &
             ctx->opt_time_spmv = 0 ;                       // event pairs are not graph material
             cudaGraph_t graph = nullptr ;
             CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal)) ;
-            for(int i = 0 ; i < batch ; i++) queue_one() ;
+            int qrc = AMIE_B200_OK ;
+            for(int i = 0 ; i < batch && !qrc ; i++) qrc = queue_one() ;
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph) ;
+            if(qrc) { if(graph) cudaGraphDestroy(graph) ; ctx->opt_time_spmv = saved_t ; return qrc ; }
             ctx->opt_time_spmv = saved_t ;
             ctx->stats.kernel_launches = kl ; ctx->stats.spmv_launches = sl ;     // counted per replay below
             CUDA_TRY(ctx, e) ;
@@ -43,8 +44,12 @@ static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot &
     }
     int pslot = 0, pending = 0 ;
     bool stopped = false ;
+    // safety net: the device-side test ends the loop after at most n_limit iterations (krylov_scalars.cuh)
+    const uint64_t batches_cap = (ctx->nb_global*(uint64_t)ctx->S*4+16)/(uint64_t)batch+4 ;
+    uint64_t batches = 0 ;
     while(!stopped)
     {
+        if(++batches > batches_cap) { ctx->set_error("iteration loop: the device never reported the end of the loop") ; return AMIE_B200_ERR_CUDA ; }
         if(use_graph)
         {
             CUDA_TRY(ctx, cudaGraphLaunch(slot.exec, ctx->stream)) ;
@@ -52,7 +57,13 @@ static int run_iteration_batches(amie_b200_ctx * ctx, amie_b200_ctx::GraphSlot &
             ctx->stats.spmv_launches += (uint64_t)spmv_per_iter*batch ;
         }
         else
-            for(int i = 0 ; i < batch ; i++) queue_one() ;
+            for(int i = 0 ; i < batch ; i++)
+            {
+                // a failed launch or exchange must end the loop here: nothing would ever set `stop`
+                const int qrc = queue_one() ;
+                if(qrc) return qrc ;
+            }
+        CUDA_TRY(ctx, cudaPeekAtLastError()) ;
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_host+pslot, ctx->st, sizeof(KrylovState), cudaMemcpyDeviceToHost, ctx->stream)) ;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_poll[pslot], ctx->stream)) ;
         pending++ ;

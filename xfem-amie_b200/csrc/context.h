@@ -59,7 +59,6 @@ struct amie_b200_ctx
     int opt_verbose = 0 ;
     int opt_batch = 0 ;         // iterations per speculative batch (0 = auto)
     int opt_graph = -1 ;        // -1 auto, 0 off, 1 on
-    int opt_split_dot = 0 ;     // 1: PCG's p.q as its own pass after a plain SpMV (single device; env AMIE_B200_SPLIT_DOT)
     int opt_assemble_variant = 0 ;  // 0: one stored entry per thread; 2: entry-group blocks; 3: + stored blocks visited by list length (kernels_assemble.cuh)
     int opt_fields_variant = 0 ;    // 1: slot loop of k_element_fields unrolled and phase-split for linear triangles / tetrahedra
     int opt_dirichlet_variant = 0 ; // 0: binary search of the id list per fixed dof; 1: per-node offsets (kernels_assemble.cuh)

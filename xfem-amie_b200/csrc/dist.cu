@@ -343,6 +343,10 @@ struct DistState
     uint64_t cs_save_len = 0 ;
 } ;
 
+// AMIE_B200_TRACE=1: stage markers of the partitioned paths on stderr (debugging hangs between parts)
+static bool trace_on() { static int v = -1 ; if(v < 0) { const char * e = getenv("AMIE_B200_TRACE") ; v = (e && atoi(e)) ? 1 : 0 ; } return v == 1 ; }
+#define TRACE(ctx, ...) do { if(trace_on()) { fprintf(stderr, "[amie_b200 part %d dev %d] ", (ctx)->dist ? (ctx)->dist->rank : -1, (ctx)->device) ; fprintf(stderr, __VA_ARGS__) ; fprintf(stderr, "\n") ; fflush(stderr) ; } } while(0)
+
 // ---- collectives used at set-up time, on either plumbing -------------------------------------------------------
 #define GROUP_TRY(ctx, ok) do { if(!(ok)) { (ctx)->set_error("group: a collective step was abandoned (another device failed)") ; return AMIE_B200_ERR_STATE ; } } while(0)
 
@@ -509,6 +513,7 @@ static int peer_setup(amie_b200_ctx * ctx)
     if(d->local)
     {
         // the only transport of an in-process group (group_create refused devices without a peer path)
+        TRACE(ctx, "peer_setup") ;
         int rc = peer_setup_local(ctx) ;
         double ok = rc == AMIE_B200_OK ? 1. : 0. ;
         CUDA_TRY(ctx, cudaDeviceSynchronize()) ;           // the memsets above are done before anybody signals
@@ -557,8 +562,10 @@ static int peer_vector(amie_b200_ctx * ctx, const double * base, const std::vect
     for(auto & m : d->vec_maps)
         if(m.base == base && m.gen == ctx->alloc_gen) { *out = &m.of_peer ; return AMIE_B200_OK ; }
     std::vector<void *> all ;
+    TRACE(ctx, "peer_vector: first use of %p as a SpMV input", (const void *)base) ;
     int rc = ipc_exchange(ctx, const_cast<double *>(base), true, all) ;
     if(rc) return rc ;
+    TRACE(ctx, "peer_vector: exchanged") ;
     DistState::VecMap m ;
     m.base = base ; m.gen = ctx->alloc_gen ;
     for(const DistPeer & p : d->peers) m.of_peer.push_back(static_cast<double *>(all[p.rank])) ;
@@ -603,6 +610,9 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
         cudaEventRecord(e0, ctx->stream) ;
     }
     const bool peer = d->peer_on && !d->peers.empty() ;
+    static int traced = 0 ;
+    const bool tr = trace_on() && traced < 12 ;
+    if(tr) { traced++ ; TRACE(ctx, "dist_spmv: x %p dot %d rowstart %llu colstart %llu peer %d", (const void *)c.x, c.dot, (unsigned long long)c.rowstart, (unsigned long long)c.colstart, (int)peer) ; }
     if(peer)
     {
         // stores straight into the neighbours' halo tails over NVLink, then a flag; no NCCL call
@@ -682,6 +692,7 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
     // tail with its NEXT push while the boundary rows above still read it
     if(!dot && peer) launch_finalize_peer(ctx, FIN_DEFER_SET) ;
     if(cs_local) CUDA_TRY(ctx, cudaMemcpyAsync(xv, d->cs_save, cs_local*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
+    if(tr) TRACE(ctx, "dist_spmv: queued") ;
     if(e1) cudaEventRecord(e1, ctx->stream) ;
     ctx->stats.spmv_launches++ ;
     if(c.smoothing) ctx->stats.smoothing_spmv++ ;
@@ -698,6 +709,7 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     cudaStream_t st = ctx->stream ;
     auto pol = thrust::cuda::par.on(st) ;
 
+    TRACE(ctx, "finish_structure: rows [%u, %u), %llu blocks", r0, r1, (unsigned long long)ctx->nnzb) ;
     // ---- halo = sorted distinct off-range columns
     uint32_t * tmp = nullptr ;
     CUDA_TRY(ctx, cudaMalloc(&tmp, std::max<uint64_t>(ctx->nnzb, 1)*sizeof(uint32_t))) ;
@@ -823,6 +835,7 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     }
     d->int_a = best_a ; d->int_b = best_b ;
 
+    TRACE(ctx, "finish_structure: halo %llu, send %llu, peers %zu, interior [%u, %u)", (unsigned long long)d->nhalo, (unsigned long long)d->nsend, d->peers.size(), d->int_a, d->int_b) ;
     ctx->ncols_local = (uint64_t)nbl+d->nhalo ;
     int arc = ctx_alloc_vectors(ctx) ;
     if(arc) return arc ;

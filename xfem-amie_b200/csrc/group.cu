@@ -11,6 +11,35 @@
 #include "synth.h"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
+#include <dlfcn.h>
+
+// ------------------------------------------------------------------ CUDA module loading
+// The parts of a group wait for one another ON THE DEVICES (halo flags, reduction mailboxes: dist.cu).  With lazy
+// module loading (the CUDA 12 default) the first launch of a kernel loads it, and that load can wait for the context
+// to go idle -- which never happens while a kernel of another part spins for the very kernel being launched
+// (CUDA programming guide, "Lazy Loading": concurrent execution).  One process per GPU never meets this; one process
+// driving several parts does, measured: S3-hex-14 on devices {0,0} hangs in the first PCG iterations under LAZY and
+// solves under EAGER (profiles/r02_notes.md).  So: a host that announces a multi-device context through
+// AMIE_B200_DEVICES gets eager loading before CUDA initialises (this constructor runs when the library is loaded);
+// any other host sets CUDA_MODULE_LOADING=EAGER itself, and group_create refuses to build a group under LAZY.
+__attribute__((constructor)) static void amie_b200_pick_module_loading()
+{
+    const char * e = getenv("AMIE_B200_DEVICES") ;
+    if(e && strchr(e, ',')) setenv("CUDA_MODULE_LOADING", "EAGER", 0) ;
+}
+
+// 1 eager, 2 lazy, 0 unknown (driver older than cuModuleGetLoadingMode)
+static int module_loading_mode()
+{
+    void * h = dlopen("libcuda.so.1", RTLD_NOW) ;
+    if(!h) return 0 ;
+    typedef int (*fn_t)(int *) ;
+    fn_t f = reinterpret_cast<fn_t>(dlsym(h, "cuModuleGetLoadingMode")) ;
+    int mode = 0 ;
+    if(!f || f(&mode) != 0) return 0 ;
+    return mode ;
+}
 
 // ------------------------------------------------------------------ barrier + worker pool
 
@@ -51,7 +80,9 @@ void LocalGroup::worker(int rank)
             seen = job_gen ;
             f = job ;
         }
+        if(getenv("AMIE_B200_TRACE")) { fprintf(stderr, "[amie_b200 worker %d] job %llu starts\n", rank, (unsigned long long)seen) ; fflush(stderr) ; }
         int rc = (*f)(rank) ;
+        if(getenv("AMIE_B200_TRACE")) { fprintf(stderr, "[amie_b200 worker %d] job %llu returned %d\n", rank, (unsigned long long)seen, rc) ; fflush(stderr) ; }
         // a rank that failed may have left the others inside a collective: release them, the group is unusable afterwards
         if(rc < 0 && world > 1) abort() ;
         {
@@ -140,6 +171,13 @@ amie_b200_ctx * group_create(const int * devices, int ndev, std::string & err)
     if(cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { err = "amie_b200_create: no CUDA device" ; return nullptr ; }
     for(int i = 0 ; i < ndev ; i++)
         if(devices[i] < 0 || devices[i] >= count) { err = "amie_b200_create: no such CUDA device" ; return nullptr ; }
+    if(module_loading_mode() == 2)
+    {
+        err = "amie_b200_create: a multi-device context needs CUDA_MODULE_LOADING=EAGER in the environment before CUDA "
+              "initialises (its parts wait for one another on the devices; lazy kernel loading deadlocks there). "
+              "Set it, or list the devices in AMIE_B200_DEVICES before the process starts." ;
+        return nullptr ;
+    }
     // every pair of distinct devices needs a peer path (NVLink / NVSwitch on the target box): the halo pushes and the
     // reduction mailboxes are plain stores into the neighbour's memory
     for(int i = 0 ; i < ndev ; i++)

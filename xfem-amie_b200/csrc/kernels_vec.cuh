@@ -182,20 +182,6 @@ static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_dot2(const double *
         krylov_finalize(st, finalize, tot[0], tot[1]) ;
 }
 
-// u.v over [begin,end) as its own pass inside the speculative iteration loop (option "split_dot": the SpMV before it
-// then runs in its plain form, which is measurably faster than the fused-dot form -- profiles/r01_notes.md).  Like the
-// fused kernels it returns at once when the loop has stopped, and it owns the SpMV's ticket and partials.
-static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_dot_checked(const double * u, const double * v, uint64_t begin, uint64_t end,
-                                                                 KrylovState * st, double * partials, int finalize)
-{
-    if(st->stop) return ;
-    double sum[2] = {0., 0.} ;
-    for(uint64_t i = begin+(uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < end ; i += (uint64_t)gridDim.x*blockDim.x)
-        sum[0] = fma(u[i], v[i], sum[0]) ;
-    double tot[2] ;
-    if(grid_sum<2, AMIE_VEC_THREADS>(sum, partials, st->ticket+TICKET_SPMV, tot) && threadIdx.x == 0)
-        krylov_finalize(st, finalize, tot[0], tot[1]) ;
-}
 
 // out = D^-1 in  (InverseDiagonal::precondition, solvers/inversediagonal.cpp:62-67)
 static __global__ void __launch_bounds__(AMIE_VEC_THREADS) k_precond(const double * in, const double * d, double * out, uint64_t n)

@@ -6,7 +6,6 @@
 #include "kernels_spmv_tma.cuh"
 #include "kernels_spmv_rt.cuh"
 #include "kernels_spmv_rt2.cuh"
-#include "kernels_spmv_rtm.cuh"
 #include "kernels_vec.cuh"
 #include "kernels_setup.cuh"
 
@@ -92,20 +91,6 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
 }
 
-// row-thread pipeline with T teams of TM warps per tile (kernels_spmv_rtm.cuh)
-template<int DOT, bool MINUS_B, int T, int TM, int NST, int CAP, int G, int NP = 1>
-static inline void launch_s3_rtm(amie_b200_ctx * ctx, const SpmvArgs & args)
-{
-    auto kern = k_spmv_s3_rtm<DOT, MINUS_B, T, TM, NST, CAP, G, NP> ;
-    constexpr int smem = RtmLayout<NST, CAP, T, TM>::TOTAL_BYTES ;
-    constexpr int threads = (T*TM+NP)*32 ;
-    static int cache[AMIE_MAX_DEVICES] = {} ;
-    const int per_sm = smem_kernel_per_sm(ctx, kern, threads, smem, cache) ;
-    const uint32_t ntiles = (args.nrows+RT_ROWS-1)/RT_ROWS ;
-    const int grid = persistent_grid(ctx, per_sm, ntiles) ;
-    kern<<<grid, threads, smem, ctx->stream>>>(args) ;
-}
-
 template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
 static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
@@ -151,11 +136,7 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
             // fills its stage (27 blocks/row for Q1 hexahedra, 12-15 for linear tetrahedra).  Short rows mean small
             // tiles, and ONE producer warp (~0.3 us per tile) then caps the CTA: three producers there.
             const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
-            if(ctx->opt_variant == 4)      launch_s3_rtm<DOT, MINUS_B, 3, 3, 7, 270, 1>(ctx, args) ;
-            else if(ctx->opt_variant == 5) launch_s3_rtm<DOT, MINUS_B, 3, 2, 7, 270, 1>(ctx, args) ;
-            else if(ctx->opt_variant == 6) launch_s3_rtm<DOT, MINUS_B, 4, 3, 12, 160, 1, 3>(ctx, args) ;
-            else if(ctx->opt_variant == 7) launch_s3_rtm<DOT, MINUS_B, 5, 2, 12, 160, 1, 3>(ctx, args) ;
-            else if(avg > 15.5 || ctx->opt_variant == 3)
+            if(avg > 15.5 || ctx->opt_variant == 3)
                 launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;   // 7 stages, not 8: leaves ~30 KB of L1 for the x gather
             else
                 launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3>(ctx, args) ;

@@ -19,8 +19,9 @@ void launch_vec(amie_b200_ctx * ctx, F f)
     ctx->stats.kernel_launches++ ;
 }
 
-void queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
+int queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
 {
+    int rc ;
     const int grid = vec_grid(ctx, ctx->N) ;
     VecArgs a = vec_args(ctx, 0, FIN_STORE, 1) ;
     if(precond == PRECOND_JACOBI) k_bicg_p<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
@@ -28,18 +29,18 @@ void queue_bicg_iteration(amie_b200_ctx * ctx, int precond, int fin_xr)
     ctx->stats.kernel_launches++ ;
     SpmvCall c ;
     c.x = a.p_ ; c.y = a.v ; c.dot = DOT_YW ; c.w = a.r_ ; c.finalize = FIN_BICG_RV ; c.check_stop = 1 ;
-    launch_spmv(ctx, c) ;                                                           // :99-100
+    if((rc = launch_spmv(ctx, c))) return rc ;                                      // :99-100
     if(precond == PRECOND_JACOBI) k_bicg_s<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     else                          k_bicg_s<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     ctx->stats.kernel_launches++ ;
     SpmvCall c2 ;
     c2.x = a.s_ ; c2.y = a.t ; c2.dot = DOT_OMEGA ; c2.w = a.s ; c2.d = precond == PRECOND_JACOBI ? ctx->dinv : nullptr ;
     c2.finalize = FIN_BICG_OMEGA ; c2.check_stop = 1 ;
-    launch_spmv(ctx, c2) ;                                                          // :105-115
+    if((rc = launch_spmv(ctx, c2))) return rc ;                                     // :105-115
     VecArgs a3 = vec_args(ctx, 0, fin_kind(ctx, fin_xr), 1) ;
     k_bicg_xr<<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a3) ;                     // :118-120, :92-94
     ctx->stats.kernel_launches++ ;
-    after_reduce(ctx, fin_xr) ;
+    return after_reduce(ctx, fin_xr) ;
 }
 
 }
@@ -185,7 +186,7 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
         const bool graph = want_graph(ctx, iter_bytes) ;
         const int nb_iter = graph ? (ctx->opt_batch > 0 ? ctx->opt_batch : 16) : batch ;
         if((rc = run_iteration_batches(ctx, ctx->graph_bicg, graph, nb_iter, precond, 0, 0, 5, 2,
-                                       [&]() { queue_bicg_iteration(ctx, precond, FIN_BICG_RHO) ; }))) return rc ;
+                                       [&]() { return queue_bicg_iteration(ctx, precond, FIN_BICG_RHO) ; }))) return rc ;
     }
     if((rc = ctx_sync_state(ctx, 2))) return rc ;
     CUDA_TRY(ctx, cudaGetLastError()) ;

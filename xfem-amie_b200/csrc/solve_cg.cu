@@ -83,25 +83,16 @@ int residual(const CgRun & R, double sign, uint64_t colstart, bool smoothing, do
 }
 
 // one PCG iteration (:220-256), all decisions on the device
-void queue_iteration(const CgRun & R)
+int queue_iteration(const CgRun & R)
 {
     amie_b200_ctx * ctx = R.ctx ;
-    launch_dir(R, false) ;
+    int rc ;
+    if((rc = launch_dir(R, false))) return rc ;
     SpmvCall c ;
     c.x = ctx->p ; c.y = ctx->q ; c.dot = DOT_YX ; c.finalize = FIN_CG_PQ ; c.check_stop = 1 ;
     c.rowstart = R.rowstart ; c.colstart = R.colstart ;
-    if(ctx->opt_split_dot && !ctx->dist)
-    {
-        // q = A p in the plain form, then p.q over the rows >= rowstart as a streaming pass of its own
-        c.dot = DOT_NONE ; c.finalize = FIN_STORE ;
-        launch_spmv(ctx, c) ;
-        k_dot_checked<<<vec_grid(ctx, ctx->N-R.rowstart), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->p, ctx->q, R.rowstart, ctx->N,
-                                                                                             ctx->st, ctx->partials, FIN_CG_PQ) ;
-        ctx->stats.kernel_launches++ ;
-    }
-    else
-        launch_spmv(ctx, c) ;
-    launch_update(R, false) ;
+    if((rc = launch_spmv(ctx, c))) return rc ;
+    return launch_update(R, false) ;
 }
 
 }
@@ -130,7 +121,6 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     CgRun R { ctx, precond_kind == AMIE_B200_PRECOND_NULL ? PRECOND_NULL : PRECOND_JACOBI, rowstart, colstart } ;
     const size_t vbytes = N*sizeof(double) ;
     int rc ;
-    int ret = 0 ;
     uint64_t nit = 0 ;
     double err_final = 0., rho_final = 0. ;
 
@@ -154,6 +144,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     // :74-78  homogeneous right-hand side: the solver's x stays zero-initialised
     double bmax = 0. ;
     if((rc = ctx_max(ctx, ctx->b, N, 0, &bmax))) return rc ;
+    if(getenv("AMIE_B200_TRACE")) { fprintf(stderr, "[amie_b200 dev %d] pcg: |b|max %g, N %llu (global %llu)\n", ctx->device, bmax, (unsigned long long)N, (unsigned long long)(ctx->nb_global*S)) ; fflush(stderr) ; }
     if(bmax < eps*eps)
     {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->x, 0, vbytes, ctx->stream)) ;
@@ -196,7 +187,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
                 perr = err ;
                 if((rc = residual(R, 1., colstart, true, &err))) return rc ;        // :136-138
                 if(err > perr) break ;                                              // :139 (NaN compares false, like the reference)
-                launch_smooth(R) ;                                                  // :141-149
+                if((rc = launch_smooth(R))) return rc ;                             // :141-149
             }
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->xc, 0, vbytes, ctx->stream)) ;       // :151
         }
@@ -208,6 +199,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
             finish(0) ;
             return AMIE_B200_ERR_NAN ;
         }
+        if(getenv("AMIE_B200_TRACE")) { fprintf(stderr, "[amie_b200 dev %d] pcg: restart at nit %llu, err0 %g\n", ctx->device, (unsigned long long)nit, err0) ; fflush(stderr) ; }
         if(nit == 0) errmin = err0 ;                                                // :167
         if(err0 < realeps)                                                          // :170-175
         {
@@ -225,7 +217,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
         s0.n_limit = Nglob ;                                                        // localnit < getForces().size()  (:218)
         if((rc = ctx_push_state(ctx, s0))) return rc ;
 
-        launch_dir(R, true) ;                                                       // :183-186, :189
+        if((rc = launch_dir(R, true))) return rc ;                                  // :183-186, :189
         {
             // :187  q = A*p through operator Vector(): every column (no colstart)
             SpmvCall c ;
@@ -233,14 +225,14 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
             c.rowstart = rowstart ; c.colstart = 0 ;
             if((rc = launch_spmv(ctx, c))) return rc ;                              // :190-197
         }
-        launch_update(R, true) ;                                                    // :199-210 (not counted in nit)
+        if((rc = launch_update(R, true))) return rc ;                               // :199-210 (not counted in nit)
 
         // :218-257, queued speculatively (batch_loop.cuh)
         {
             const bool graph = want_graph(ctx, iter_bytes) ;
             const int nb_iter = graph ? (ctx->opt_batch > 0 ? ctx->opt_batch : 32) : batch ;
-            if((rc = run_iteration_batches(ctx, ctx->graph_cg, graph, nb_iter, R.precond, rowstart, colstart, (ctx->opt_split_dot && !ctx->dist) ? 4 : 3, 1,
-                                           [&]() { queue_iteration(R) ; }))) return rc ;
+            if((rc = run_iteration_batches(ctx, ctx->graph_cg, graph, nb_iter, R.precond, rowstart, colstart, 3, 1,
+                                           [&]() { return queue_iteration(R) ; }))) return rc ;
         }
         if((rc = ctx_sync_state(ctx, 2))) return rc ;
         CUDA_TRY(ctx, cudaGetLastError()) ;
@@ -268,7 +260,7 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
             {
                 double dummy ;
                 if((rc = residual(R, 1., colstart, true, &dummy))) return rc ;      // :279
-                launch_smooth(R) ;                                                  // :280-288
+                if((rc = launch_smooth(R))) return rc ;                             // :280-288
                 if((rc = ctx_sync_state(ctx, 2))) return rc ;
                 const double perr = err ;
                 err = std::sqrt(ctx->st_host[2].dot[0]) ;                           // :291  |D^-1 r|
@@ -284,7 +276,6 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
             if(ctx->opt_verbose) fprintf(stderr, "\n CG %llu converged after %llu iterations. Error : %g, last rho = %g\n", (unsigned long long)N, (unsigned long long)nit, err, last_rho) ;
             return finish(1) ;
         }
-        (void)ret ;
     }
     // :314-317
     {
