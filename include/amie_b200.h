@@ -42,13 +42,28 @@ extern "C" {
 #define AMIE_B200_PRECOND_LUMPED 3    /* InverseLumpedDiagonal: d = 1/(row sum), +-1 if tiny    (:19-48)             */
 #define AMIE_B200_PRECOND_DIAGONAL 4  /* any Preconditionner of that form: the caller supplies d with                */
                                       /* amie_b200_set_preconditioner_diagonal                                       */
+/* block preconditioners, PCG only (built on the device from the resident values):     */
+#define AMIE_B200_PRECOND_BLOCK2X2 5  /* Inverse2x2Diagonal (solvers/inversediagonal.cpp:84-133) on a stride-2 matrix: */
+                                      /* the inverse of every node's 2x2 diagonal block; same bits as the class      */
+#define AMIE_B200_PRECOND_BLOCK3X3 6  /* the same construction on the 3x3 node blocks of a stride-3 matrix, with the */
+                                      /* reference's det() / invert3x3Matrix (utilities/matrixops.cpp:838-847,       */
+                                      /* :681-702).  No reference class: opt-in block-Jacobi, other iteration counts */
 
 typedef struct amie_b200_ctx amie_b200_ctx ;
 
 /* ------------------------------------------------------------------ context */
 
-/* devices: CUDA ordinals; ndev == 1: one context drives one device (NULL/0 -> device 0 or env
- * AMIE_B200_DEVICE).  Several GPUs = one context per device + amie_b200_dist_init (below).
+/* devices: CUDA ordinals.
+ *   ndev == 1 (or NULL/0 -> device 0, env AMIE_B200_DEVICE): one context drives one device.
+ *   ndev  > 1 (or NULL/0 with env AMIE_B200_DEVICES="0,1,..."): ONE context over several GPUs of a box, still driven
+ *     by one caller thread with GLOBAL host arrays -- the shape Assembly::cgsolve has (solvers/assembly.cpp:1841-1850).
+ *     The block rows are partitioned inside the library (amie_b200_partition_rows), one worker thread and one child
+ *     context per device, halo and reductions over NVLink peer memory (csrc/group.cu, csrc/dist.cu).  Needs a
+ *     peer-to-peer path between the devices and CUDA_MODULE_LOADING=EAGER (set automatically when AMIE_B200_DEVICES
+ *     lists several devices at load time).  Strides 2 and 3.  An ordinal may be listed more than once (several parts on
+ *     one GPU: how the path is tested on a one-GPU box).  Not on a multi-device context: set_block_map,
+ *     download_matrix, the value-assembly and field-recovery rows (AMIE_B200_ERR_UNSUPPORTED).
+ *   One process per GPU (torchrun, MPI) uses amie_b200_dist_init (below) instead.
  * Returns NULL on failure (see amie_b200_global_error). */
 amie_b200_ctx * amie_b200_create(const int * devices, int ndev) ;
 void            amie_b200_destroy(amie_b200_ctx * ctx) ;
@@ -109,6 +124,8 @@ int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out) ;
 /* The diagonal of preconditioner `precond_kind` (0, 2, 3: built on the device from the resident values; 4: the one
  * set below), as the corresponding reference class holds it in its `diagonal` member.                              */
 int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, double * d_out) ;
+/* The s x s blocks of precond_kind 5 | 6, row-major per node (blocks_out[nb*s*s]): Inverse2x2Diagonal::blocks.     */
+int amie_b200_preconditioner_blocks(amie_b200_ctx * ctx, int precond_kind, double * blocks_out) ;
 /* d[N] for AMIE_B200_PRECOND_DIAGONAL: what a user-written Preconditionner with precondition(v, t) { t = v*d } holds.
  * Kept until replaced or until the structure changes.                                                              */
 int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d) ;
@@ -251,14 +268,14 @@ typedef struct amie_b200_stats
 } amie_b200_stats ;
 int amie_b200_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 
-/* option keys: "time_spmv" (0/1: record an event pair around every SpMV launch),
- * "spmv_variant" (kernel selection), "compensated" (0/1),
- * "split_dot" (0/1: PCG's p.q as a separate streaming pass after a plain SpMV instead of the fused form; single
- * device; same algorithm, another summation order; default from env AMIE_B200_SPLIT_DOT),
- * "iters_per_graph" (iterations captured per CUDA-graph launch), "verbose" (0/1:
- * print the reference's cerr lines), "assemble_variant" (0 | 2 | 3), "dirichlet_variant" (0 | 1) and "fields_variant" (0 | 1):
- * kernel selection of amie_b200_assemble / amie_b200_set_boundary_conditions / amie_b200_element_fields (same bits, see
- * csrc/kernels_assemble.cuh, csrc/kernels_fields.cuh).                                                     */
+/* option keys (anything else: AMIE_B200_ERR_ARG):
+ *   "time_spmv"       0/1: record a CUDA-event pair around every SpMV launch (stats spmv_ms_total / spmv_timed);
+ *   "spmv_variant"    kernel selection of the block-row SpMV, 0 = the shipped choice;
+ *   "verbose"         0/1: print the reference's cerr lines from inside the library;
+ *   "iters_per_batch" iterations queued per poll of the device-side loop state (0 = automatic);
+ *   "graph"           -1 automatic, 0 / 1: replay the iteration batches as a CUDA graph (small, launch-bound systems);
+ *   "fields_variant"  1 (default) the unrolled field-recovery kernel for linear triangles / tetrahedra, 0 the generic
+ *                     slot loop (same bits, csrc/kernels_fields.cuh).                                          */
 int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value) ;
 
 /* ------------------------------------------------------------------ synthetic problems
@@ -292,8 +309,8 @@ int amie_b200_partition_halo(uint64_t r0, uint64_t r1, const uint32_t * row_size
 
 /* ------------------------------------------------------------------ node renumbering (host-only)
  * The mesher's numbering has no locality; these are the host half of a renumbering applied once per topology
- * (csrc/reorder.cpp; the device half -- values gathered through block_from, vectors through perm -- is not wired
- * into the context yet).  perm_out[old node] = new node: reverse Cuthill-McKee on the block graph.               */
+ * (csrc/reorder.cpp; the device half is amie_b200_set_block_map: values scattered through block_to inside K-Repack,
+ * the host permutes the vectors).  perm_out[old node] = new node: reverse Cuthill-McKee on the block graph.      */
 int amie_b200_rcm_order(uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint32_t * perm_out) ;
 /* The structure in the new numbering (columns ascending inside each row) and, for every stored block of it, the
  * stored block of the old structure it is (block_from_out[new k] = old k): array_new block k = array_old block

@@ -29,6 +29,7 @@
 #include "solvers/inversediagonal.h"
 #include "solvers/preconditionners.h"
 #include "sparse/sparse_matrix.h"
+#include "utilities/matrixops.h"
 
 namespace {
 
@@ -86,6 +87,7 @@ Amie::Preconditionner * make_precond(int kind, Amie::Assembly & a)
         case 2: return new Amie::InverseDiagonalSquared(a.getMatrix()) ;
         case 3: return new Amie::InverseLumpedDiagonal(a.getMatrix()) ;
         case 4: return new UserDiagonal(g_user_diag, g_user_diag_n) ;
+        case 5: return new Amie::Inverse2x2Diagonal(a.getMatrix()) ;
         default: return nullptr ;
     }
 }
@@ -119,6 +121,33 @@ int amie_ref_precond_diagonal(int stride, uint64_t nb, const uint32_t * row_size
     else if(kind == 3) { Amie::InverseLumpedDiagonal P(a.getMatrix()) ; std::memcpy(d_out, &P.diagonal[0], n*sizeof(double)) ; }
     else return -1 ;
     return 0 ;
+}
+
+// the 2x2 blocks Inverse2x2Diagonal holds (solvers/inversediagonal.cpp:84-119), row-major, one per dof pair
+int amie_ref_precond_blocks2(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint64_t nnzb,
+                             const double * array_padded, double * blocks_out)
+{
+    Amie::Assembly a ;
+    fill_assembly(a, stride, nb, row_size, column_index, nnzb, array_padded, nullptr) ;
+    Amie::Inverse2x2Diagonal P(a.getMatrix()) ;
+    for(size_t i = 0 ; i < P.blocks.size() ; i++)
+        for(int r = 0 ; r < 2 ; r++)
+            for(int c = 0 ; c < 2 ; c++)
+                blocks_out[i*4+r*2+c] = P.blocks[i][r][c] ;
+    return (int)P.blocks.size() ;
+}
+
+// Amie::det and Amie::invert3x3Matrix (utilities/matrixops.cpp:826-847, :681-702) on n row-major 3x3 matrices
+void amie_ref_det_invert3x3(const double * m_in, uint64_t n, double * det_out, double * inv_out)
+{
+    for(uint64_t k = 0 ; k < n ; k++)
+    {
+        Amie::Matrix M(3, 3) ;
+        for(int r = 0 ; r < 3 ; r++) for(int c = 0 ; c < 3 ; c++) M[r][c] = m_in[k*9+r*3+c] ;
+        det_out[k] = Amie::det(M) ;
+        Amie::invert3x3Matrix(M) ;
+        for(int r = 0 ; r < 3 ; r++) for(int c = 0 ; c < 3 ; c++) inv_out[k*9+r*3+c] = M[r][c] ;
+    }
 }
 
 // Assembly::extrapolate(factor) (solvers/assembly.cpp:1772-1814) on a hand-filled displacementHistory {prev, back}

@@ -55,7 +55,7 @@ int emu_precond_diagonal(int kind, int stride, uint64_t nb, const uint32_t * row
 // incremental damage step.  Returns 0, 1 (node id out of range), 2 (pair outside the pattern).
 int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
                  uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
-                 int all, uint64_t mark_first, uint64_t mark_count, int variant, double * vals)
+                 int all, uint64_t mark_first, uint64_t mark_count, double * vals)
 {
     std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
     const uint64_t nsrc = n_elem*(uint64_t)npe*npe ;
@@ -76,29 +76,27 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
             k_map_fill(dest.data(), nsrc, cptr.data(), count.data(), csrc.data()) ;
         }
     emu_launch(GRID, BLOCK, [&]() { k_map_sort(cptr.data(), csrc.data(), nnzb) ; }) ;
+    // update_elements: the stream numbering (k_map_positions), then the elementary matrices placed in two uneven chunks
+    // of whole elements (the device streams the host array through a staging buffer)
+    const uint64_t total = cptr[nnzb] ;
+    const uint64_t SSu = (uint64_t)stride*stride ;
+    std::vector<uint32_t> pos(nsrc ? nsrc : 1, NO_DEST) ;
+    emu_launch(GRID, BLOCK, [&]() { k_map_positions(csrc.data(), total, pos.data()) ; }) ;
+    std::vector<double> placed(total*SSu ? total*SSu : 1, 0.) ;
+    const uint64_t cut = n_elem/3 ;
+    for(int part = 0 ; part < 2 ; part++)
+    {
+        const uint64_t e0 = part ? cut : 0, ne = part ? n_elem-cut : cut ;
+        if(!ne) continue ;
+        const double * stage = ke+e0*pp*SSu ;
+        const double * sc = scales ? scales+e0 : nullptr ;
+        BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_place_elements<N*N>(stage, sc, e0, pos.data(), e0*pp, ne*pp, pp, placed.data()) ; }))
+    }
     std::vector<unsigned char> dirty(nnzb ? nnzb : 1, 0) ;
     if(!all)
         emu_launch(GRID, BLOCK, [&]() { k_mark_dirty(dest.data(), mark_first*pp, (mark_first+mark_count)*pp, dirty.data()) ; }) ;
     const uint64_t nent = nnzb*(uint64_t)stride*stride ;
-    if(variant == 2 || variant == 3)
-    {
-        std::vector<uint32_t> order ;
-        if(variant == 3)
-        {
-            // ensure_order (assemble.cu): k_list_lengths, then a stable sort of the block ids by list length, longest first
-            std::vector<uint32_t> len(nnzb ? nnzb : 1), id(nnzb ? nnzb : 1) ;
-            emu_launch(GRID, BLOCK, [&]() { k_list_lengths(cptr.data(), nnzb, len.data(), id.data()) ; }) ;
-            order.assign(id.begin(), id.begin()+nnzb) ;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len[x] > len[y] ; }) ;
-        }
-        const uint32_t * ord = variant == 3 ? order.data() : nullptr ;
-        const unsigned G = 5 ;       // groups per block: a few, so that the group-stride loop wraps many times
-        BY_STRIDE(stride, emu_launch(GRID, N*N*G, [&]() { k_assemble_gather_v2<N*N>(cptr.data(), csrc.data(), ke, scales, pp, ord, dirty.data(), all, vals, (uint32_t)nnzb) ; }))
-    }
-    else
-    {
-        BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_assemble_gather<N*N>(cptr.data(), csrc.data(), ke, scales, pp, dirty.data(), all, vals, nent) ; }))
-    }
+    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_assemble_gather<N*N>(cptr.data(), placed.data(), dirty.data(), all, vals, nent) ; }))
     emu_launch(GRID, BLOCK, [&]() { k_clear_dirty(dirty.data(), nnzb) ; }) ;
     for(uint64_t k = 0 ; k < nnzb ; k++) if(dirty[k]) return -1 ;
     return 0 ;
@@ -109,21 +107,11 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
 int emu_dirichlet(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
                   double * vals, double * forces, double * natural, const double * add_to_forces,
                   uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
-                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, int variant, unsigned char * dirty_out)
+                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
 {
     std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
     std::vector<unsigned char> fixmask(nb ? nb : 1, 0), forcemask(nb ? nb : 1, 0) ;
     (void)nnzb ;
-    if(variant == 1)
-    {
-        std::vector<uint32_t> fixoff(nb ? nb : 1, 0xDEADBEEFu), forceoff(nb ? nb : 1, 0xDEADBEEFu) ;
-        if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask_offsets(fix_ids, nfix, stride, fixmask.data(), fixoff.data()) ; }) ;
-        if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask_offsets(force_ids, nforce, stride, forcemask.data(), forceoff.data()) ; }) ;
-        BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N, true>(rp.data(), col, nb, vals, forces, natural, add_to_forces,
-                                                                             fixmask.data(), fixoff.data(), fix_values, (uint32_t)nfix,
-                                                                             forcemask.data(), forceoff.data(), force_values, (uint32_t)nforce, dirty_out) ; }))
-        return 0 ;
-    }
     if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask(fix_ids, nfix, stride, fixmask.data()) ; }) ;
     if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask(force_ids, nforce, stride, forcemask.data()) ; }) ;
     BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N>(rp.data(), col, nb, vals, forces, natural, add_to_forces,

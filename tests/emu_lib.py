@@ -74,7 +74,7 @@ def precond_diagonal(kind, stride, row_size, column_index, vals_compact):
     return d
 
 
-def assemble(stride, row_size, column_index, ids, ke, scales, vals=None, mark=None, variant=0):
+def assemble(stride, row_size, column_index, ids, ke, scales, vals=None, mark=None):
     """Full assembly (vals None) or the incremental re-accumulation of the blocks touched by elements
     [mark[0], mark[0]+mark[1]) on top of `vals`.  Returns (rc, vals_compact)."""
     rs = np.ascontiguousarray(row_size, np.uint32)
@@ -86,12 +86,12 @@ def assemble(stride, row_size, column_index, ids, ke, scales, vals=None, mark=No
     out = np.zeros(ci.size * s * s) if vals is None else np.array(vals, np.float64)
     first, count = (0, 0) if mark is None else mark
     rc = emu().emu_assemble(s, u64(rs.size), _vp(rs), _vp(ci), u64(ci.size), u64(ids.shape[0]), int(ids.shape[1]), _vp(ids),
-                            _vp(ke), _vp(scales), 1 if mark is None else 0, u64(first), u64(count), int(variant), _vp(out))
+                            _vp(ke), _vp(scales), 1 if mark is None else 0, u64(first), u64(count), _vp(out))
     return rc, out
 
 
 def dirichlet(stride, row_size, column_index, vals_compact, forces, fix_ids, fix_values, force_ids=None, force_values=None,
-              natural=None, add_to_forces=None, variant=0):
+              natural=None, add_to_forces=None):
     rs = np.ascontiguousarray(row_size, np.uint32)
     ci = np.ascontiguousarray(column_index, np.uint32)
     vals, forces = np.array(vals_compact, np.float64), np.array(forces, np.float64)
@@ -102,7 +102,7 @@ def dirichlet(stride, row_size, column_index, vals_compact, forces, fix_ids, fix
     gv = np.ascontiguousarray([] if force_values is None else force_values, np.float64)
     dirty = np.zeros(max(1, ci.size), np.uint8)
     rc = emu().emu_dirichlet(int(stride), u64(rs.size), _vp(rs), _vp(ci), u64(ci.size), _vp(vals), _vp(forces), _vp(nat), _vp(add),
-                             u64(fi.size), _vp(fi), _vp(fv), u64(gi.size), _vp(gi), _vp(gv), int(variant), _vp(dirty))
+                             u64(fi.size), _vp(fi), _vp(fv), u64(gi.size), _vp(gi), _vp(gv), _vp(dirty))
     assert rc == 0, rc
     return vals, forces, nat, dirty[:ci.size]
 

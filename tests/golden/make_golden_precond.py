@@ -7,6 +7,9 @@ reference (oracle/_ref; run in the build container, the .npz files are committed
       of ConjugateGradient::solve / BiConjugateGradientStabilized::solve (x, nit, return value) with an object of
       kind 2 / 3 passed as `precond`, and with a user-written Preconditionner (kind 4: precondition(v, t) is
       t = v * user_diagonal, oracle/ref_harness.cpp:UserDiagonal).
+  blockprecond.npz : Inverse2x2Diagonal (solvers/inversediagonal.cpp:84-133) on two stride-2 systems (its `blocks`
+      and ConjugateGradient::solve with it), and Amie::det / Amie::invert3x3Matrix on the 3x3 node blocks of a
+      stride-3 system and on random 3x3 matrices (utilities/matrixops.cpp:826-847, :681-702).
 """
 import os
 import sys
@@ -44,5 +47,29 @@ def main():
         print("wrote", path, os.path.getsize(path), "bytes;", {k: int(out[k]) for k in out if k.endswith(("_ok", "_nit"))})
 
 
+def blocks():
+    pkg = g.load_package()
+    out = {}
+    rs, ci, arr, b = random_spd_blocks(2, 60, 5)
+    for name, S in (("tri", make_sys(pkg, ol, "S2-tri", 10)), ("rand", ol.Sys(2, 60, rs, ci, arr, b))):
+        for k, v in dict(nb=S.nb, row_size=S.row_size, column_index=S.column_index, array=S.array, b=S.b).items():
+            out[f"{name}_{k}"] = v
+        out[f"{name}_blocks"] = ol.ref_precond_blocks2(S)
+        ret, x, nit, _, _ = ol.ref_cg(S, precond=5, nssor=32)
+        out[f"{name}_cg_ok"], out[f"{name}_cg_x"], out[f"{name}_cg_nit"] = ret, x, nit
+    S3 = make_sys(pkg, ol, "ASR-hex", 5)
+    A = S3.to_scipy()
+    m = np.stack([A[3 * k:3 * k + 3, 3 * k:3 * k + 3].toarray().ravel() for k in range(S3.nb)])
+    m = np.concatenate([m, np.random.default_rng(9).standard_normal((50, 9))])
+    det, inv = ol.ref_det_invert3x3(m)
+    for k, v in dict(nb=S3.nb, row_size=S3.row_size, column_index=S3.column_index, array=S3.array).items():
+        out[f"hex_{k}"] = v
+    out["m3"], out["det3"], out["inv3"] = m, det, inv
+    path = os.path.join(HERE, "blockprecond.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    blocks()

@@ -168,6 +168,28 @@ def oracle_precond_diagonal(S, kind):
     return d
 
 
+def oracle_precond_blocks(S):
+    """The s x s blocks of the block preconditioners (kind 5 on stride 2, kind 6 on stride 3), row-major per node."""
+    B = np.zeros(S.nb * S.stride * S.stride)
+    oracle().amie_oracle_precond_blocks(*S.head(), _vp(B))
+    return B
+
+
+def ref_precond_blocks2(S):
+    """The 2x2 blocks the reference's Inverse2x2Diagonal builds (stride-2 systems: one per node)."""
+    B = np.zeros(S.n // 2 * 4)
+    n = ref().amie_ref_precond_blocks2(*S.head(), _vp(B))
+    assert n == S.n // 2
+    return B
+
+
+def ref_det_invert3x3(m):
+    m = np.ascontiguousarray(m, np.float64).reshape(-1, 9)
+    det, inv = np.zeros(m.shape[0]), np.zeros_like(m)
+    ref().amie_ref_det_invert3x3(_vp(m), u64(m.shape[0]), _vp(det), _vp(inv))
+    return det, inv
+
+
 def oracle_assign(S, v, b=None, rowstart=0, colstart=0):
     y = np.zeros(S.n)
     v = np.ascontiguousarray(v, np.float64)

@@ -53,20 +53,19 @@ def test_preconditioner_diagonals_against_reference_fixtures(name):
         assert same_bits(em.precond_diagonal(kind, s, g["row_size"], g["column_index"], vals), g[f"diag{kind}"]), kind
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
 @pytest.mark.parametrize("dims,stride,ragged", [((9, 8), 2, False), ((6, 5, 7), 3, False), ((7, 6, 5), 3, True),
                                                 ((12, 11), 1, False), ((5, 4, 4), 4, False), ((4, 4, 3), 6, True)])
-def test_assemble_kernels_match_oracle(ol, dims, stride, ragged, variant):
+def test_assemble_kernels_match_oracle(ol, dims, stride, ragged):
     nb, el = grid_elements(ol, dims, stride, seed=sum(dims) + stride, ragged=ragged)
     rs, ci = el.pattern(nb)
-    rc, vals = em.assemble(stride, rs, ci, el.ids, el.ke, el.scales, variant=variant)
+    rc, vals = em.assemble(stride, rs, ci, el.ids, el.ke, el.scales)
     assert rc == 0
     assert same_bits(em.padded(vals, stride), ol.oracle_assemble(stride, nb, rs, ci, el))
     # a damage-like step: some elements change, only their stored blocks are re-accumulated
     rng = np.random.default_rng(1)
     first, count = el.n_elem // 3, max(1, el.n_elem // 5)
     el.ke[first:first + count] *= rng.uniform(0.1, 0.9, (count, 1, 1, 1))
-    rc, vals2 = em.assemble(stride, rs, ci, el.ids, el.ke, el.scales, vals=vals, mark=(first, count), variant=variant)
+    rc, vals2 = em.assemble(stride, rs, ci, el.ids, el.ke, el.scales, vals=vals, mark=(first, count))
     assert rc == 0
     assert same_bits(em.padded(vals2, stride), ol.oracle_assemble(stride, nb, rs, ci, el))
     # error paths of the map build
@@ -80,25 +79,22 @@ def test_assemble_kernels_match_oracle(ol, dims, stride, ragged, variant):
         assert rc in (0, 2)          # 2 when that pair is not in the pattern
 
 
-@pytest.mark.parametrize("variants", [(0, 0), (2, 1), (3, 1)])
 @pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
-def test_assemble_and_eliminate_reproduce_the_featuretree_matrix(ol, name, variants):
+def test_assemble_and_eliminate_reproduce_the_featuretree_matrix(ol, name):
     G = np.load(os.path.join(GOLDEN, name))
     s, nb = int(G["stride"]), int(G["nb"])
     el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
-    rc, vals = em.assemble(s, G["row_size"], G["column_index"], el.ids, el.ke, el.scales, variant=variants[0])
+    rc, vals = em.assemble(s, G["row_size"], G["column_index"], el.ids, el.ke, el.scales)
     assert rc == 0
-    vals, forces, _, dirty = em.dirichlet(s, G["row_size"], G["column_index"], vals, np.zeros(nb * s), G["fix_ids"], G["fix_values"],
-                                          variant=variants[1])
+    vals, forces, _, dirty = em.dirichlet(s, G["row_size"], G["column_index"], vals, np.zeros(nb * s), G["fix_ids"], G["fix_values"])
     assert same_bits(em.padded(vals, s), G["array_post"])
     if bool(G["forces_comparable"]):
         assert same_bits(forces, G["forces_post"])
     assert dirty.any()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("stride", [1, 2, 3, 4, 6])
-def test_dirichlet_kernel_matches_oracle(ol, stride, variant):
+def test_dirichlet_kernel_matches_oracle(ol, stride):
     nb = 70
     rs, ci, arr, b = random_spd_blocks(stride, nb, 500 + stride)
     n = nb * stride
@@ -112,17 +108,16 @@ def test_dirichlet_kernel_matches_oracle(ol, stride, variant):
         frv = rng.standard_normal(frc.size)
         nat, add = rng.standard_normal(n), rng.standard_normal(n)
         a0, f0, n0, _ = ol.oracle_set_bcs(stride, nb, rs, ci, arr, b, fix, fv, frc, frv, nat, add)
-        v1, f1, n1, _ = em.dirichlet(stride, rs, ci, vals, b, fix, fv, frc, frv, nat, add, variant=variant)
+        v1, f1, n1, _ = em.dirichlet(stride, rs, ci, vals, b, fix, fv, frc, frv, nat, add)
         assert same_bits(em.padded(v1, stride), a0) and same_bits(f1, f0) and same_bits(n1, n0), nfix
 
 
-@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("stride", [2, 3])
-def test_dirichlet_kernel_against_reference_fixture(stride, variant):
+def test_dirichlet_kernel_against_reference_fixture(stride):
     G = np.load(os.path.join(GOLDEN, f"bc-rand-s{stride}.npz"))
     vals = em.compact(G["array"], stride)
     v1, f1, n1, _ = em.dirichlet(stride, G["row_size"], G["column_index"], vals, G["forces"], G["fix_ids"], G["fix_values"],
-                                 G["force_ids"], G["force_values"], G["natural"], G["add_to_forces"], variant=variant)
+                                 G["force_ids"], G["force_values"], G["natural"], G["add_to_forces"])
     assert same_bits(em.padded(v1, stride), G["array_post"])
     assert same_bits(f1, G["forces_post"]) and same_bits(n1, G["natural_post"])
 

@@ -26,7 +26,7 @@ CASES = [("S3-hex", 12), ("S3-hex", 20), ("S3-tet", 14), ("S2-tri", 40), ("ASR-h
 LARGE = [("S3-hex", 44), ("S3-tet", 44), ("S2-tri", 256)]
 # solver fixtures only: *-assembly.npz / bc-rand-*.npz / *-fields.npz / precond-*.npz belong to the assembly, field-recovery and preconditioner tests
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith(("bc-rand-", "precond-")))]
+          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith(("bc-rand-", "precond-", "blockprecond")))]
 
 
 def assembly_of(pkg, S):

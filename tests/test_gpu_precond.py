@@ -145,3 +145,71 @@ def test_precond_error_paths(pkg, systems):
         pkg.ConjugateGradient(asm).solve(None, Foreign(), 1e-10, -1)
     assert e.value.code == pkg.ERR_UNSUPPORTED
     asm.close()
+
+
+# ---------------------------------------------------------------------------------------------------- block preconditioners
+# Inverse2x2Diagonal (solvers/inversediagonal.cpp:84-133) on stride-2 systems, and the
+# same construction on the 3x3 node blocks of stride-3 systems (opt-in; the reference has no 3x3 class).
+
+@pytest.mark.parametrize("preset,n", [("S2-tri", 40), ("S2-tri", 12)])
+def test_inverse2x2diagonal_blocks_and_solve(pkg, ol, systems, preset, n):
+    S = systems(preset, n)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+    B = asm.preconditioner_blocks(pkg.PRECOND_BLOCK2X2)
+    assert np.array_equal(B.reshape(-1), ol.oracle_precond_blocks(S))
+    if ol.ref() is not None:
+        assert np.array_equal(B.reshape(-1), ol.ref_precond_blocks2(S))      # the class itself
+    ret, x_ref, info = ol.oracle_cg(S, precond=5, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, pkg.Inverse2x2Diagonal(), 1e-10, -1)
+    assert ok == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= 2, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= 1e-8
+    if ol.ref() is not None:
+        rret, rx, rnit, _, _ = ol.ref_cg(S, precond=5, nssor=32, nthreads=1)
+        assert abs(int(cg.nit) - int(rnit)) <= 2 and rel_l2(cg.x, rx) <= 1e-8
+    # back to the default on the same context: the block buffer must not leak into the Jacobi kernels
+    ret0, x0_ref, info0 = ol.oracle_cg(S, nssor=32)
+    assert cg.solve(None, None, 1e-10, -1) == bool(ret0) and abs(int(cg.nit) - int(info0.nit)) <= 2
+    assert rel_l2(cg.x, x0_ref) <= 1e-8
+    # a stride-2 kind on a stride-2 matrix only; BiCGStab has no block path
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    with pytest.raises(pkg.AmieB200Error) as e:
+        bi.solve(None, pkg.Inverse2x2Diagonal(), 1e-10, -1)
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    asm.close()
+
+
+@pytest.mark.parametrize("preset,n", [("S3-hex", 12), ("ASR-hex", 12), ("S3-tet", 14)])
+def test_block_jacobi_3x3(pkg, ol, systems, preset, n):
+    S = systems(preset, n)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
+    B = asm.preconditioner_blocks(pkg.PRECOND_BLOCK3X3)
+    assert np.array_equal(B.reshape(-1), ol.oracle_precond_blocks(S))
+    ret, x_ref, info = ol.oracle_cg(S, precond=6, nssor=32)
+    ret0, _, info0 = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, pkg.BlockJacobi3x3(), 1e-10, -1)
+    print(f"{preset}-{n}: Jacobi {info0.nit} it, 3x3 block-Jacobi {info.nit} it (oracle) / {cg.nit} it (GPU)")
+    assert ok == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= 2, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= 1e-8
+    with pytest.raises(pkg.AmieB200Error) as e:
+        asm.preconditioner_blocks(pkg.PRECOND_BLOCK2X2)          # stride mismatch
+    assert e.value.code == pkg.ERR_UNSUPPORTED
+    asm.close()
+
+
+def test_block_preconditioner_with_rowstart_and_on_a_group(pkg, ol, systems):
+    S = systems("S2-tri", 40)
+    rs = S.stride * (S.nb // 3)
+    ret, x_ref, info = ol.oracle_cg(S, precond=5, nssor=32, rowstart=rs, colstart=rs)
+    for devices in (None, [0, 0]):
+        A = pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array)
+        asm = pkg.Assembly(A, S.b, devices=devices) if devices else pkg.Assembly(A, S.b, device=0)
+        cg = pkg.ConjugateGradient(asm)
+        cg.nssor, cg.rowstart, cg.colstart = 32, rs, rs
+        ok = cg.solve(None, pkg.Inverse2x2Diagonal(), 1e-10, -1)
+        assert ok == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= 2, (devices, cg.nit, info.nit)
+        assert rel_l2(cg.x, x_ref) <= 1e-8
+        asm.close()

@@ -12,7 +12,7 @@ import pytest
 
 # solver fixtures only: *-assembly.npz / bc-rand-*.npz / *-fields.npz / precond-*.npz belong to the assembly, field-recovery and preconditioner tests
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith(("bc-rand-", "precond-")))]
+          if not (p.endswith(("-assembly.npz", "-fields.npz")) or os.path.basename(p).startswith(("bc-rand-", "precond-", "blockprecond")))]
 
 
 def _sys(ol, g):

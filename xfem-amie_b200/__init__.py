@@ -27,6 +27,7 @@ f64 = ctypes.c_double
 
 ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NAN, ERR_UNSUPPORTED, ERR_NCCL = -1, -2, -3, -4, -5, -6
 PRECOND_JACOBI, PRECOND_NULL, PRECOND_DIAGONAL_SQUARED, PRECOND_LUMPED, PRECOND_DIAGONAL = 0, 1, 2, 3, 4
+PRECOND_BLOCK2X2, PRECOND_BLOCK3X3 = 5, 6
 default_solver_precision = 1e-10          # polynomial/variable.h:14
 
 
@@ -77,6 +78,7 @@ def lib():
         L.amie_b200_spmv.argtypes = [vp, vp, vp, u64, u64, vp]
         L.amie_b200_inverse_diagonal.argtypes = [vp, vp]
         L.amie_b200_preconditioner_diagonal.argtypes = [vp, ci, vp]
+        L.amie_b200_preconditioner_blocks.argtypes = [vp, ci, vp]
         L.amie_b200_set_preconditioner_diagonal.argtypes = [vp, vp]
         L.amie_b200_residual.argtypes = [vp, vp, vp, vp, vp]
         L.amie_b200_upload_rhs.argtypes = [vp, vp]
@@ -501,6 +503,14 @@ class Assembly:
         self.check(lib().amie_b200_preconditioner_diagonal(self.ctx, int(kind), _ptr(d)))
         return self.from_device_order(d)
 
+    def preconditioner_blocks(self, kind):
+        """The s x s blocks of PRECOND_BLOCK2X2 / PRECOND_BLOCK3X3 ([nb, s, s], row-major: Inverse2x2Diagonal::blocks)."""
+        self.sync_matrix()
+        st = self.stats()
+        B = np.zeros((st.nb, st.stride, st.stride))
+        self.check(lib().amie_b200_preconditioner_blocks(self.ctx, int(kind), _ptr(B)))
+        return B
+
     def cgsolve(self, maxit=-1, verbose=False):
         """Assembly::cgsolve for an assembled symmetric system (solvers/assembly.cpp:1841-1858)."""
         cg = ConjugateGradient(self)
@@ -534,6 +544,24 @@ class InverseDiagonalSquared(Preconditionner):
 class InverseLumpedDiagonal(Preconditionner):
     """solvers/inversediagonal.h:32-38; built on the device from the assembly's matrix."""
     kind = PRECOND_LUMPED
+
+    def __init__(self, A=None):
+        pass
+
+
+class Inverse2x2Diagonal(Preconditionner):
+    """solvers/inversediagonal.h:49-55 on a stride-2 system: the inverse of every node's 2x2 diagonal block, built on
+    the device from the assembly's matrix with the reference's arithmetic (PCG only)."""
+    kind = PRECOND_BLOCK2X2
+
+    def __init__(self, A=None):
+        pass
+
+
+class BlockJacobi3x3(Preconditionner):
+    """The 3x3 counterpart for stride-3 systems (det / invert3x3Matrix of utilities/matrixops.cpp).  The reference has
+    no such class: opt-in, iteration counts differ from the Jacobi default (PCG only)."""
+    kind = PRECOND_BLOCK3X3
 
     def __init__(self, A=None):
         pass

@@ -2,6 +2,7 @@
 // The solvers are in solve_cg.cu and solve_bicg.cu.  No CPU fallback anywhere: every compute
 // entry point needs a CUDA device and reports AMIE_B200_ERR_CUDA without one.
 #include "launch.cuh"
+#include "kernels_vec_block.cuh"
 #include "group.h"
 #include <cstring>
 #include <cmath>
@@ -22,6 +23,7 @@ void ctx_free_matrix(amie_b200_ctx * ctx)
     assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
     field_map_destroy(ctx) ;             // element data belongs to the topology too
     dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ; dfree(ctx->block_to) ;
+    ctx->dinv_len = 0 ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }
 
@@ -83,12 +85,26 @@ int ctx_ensure_dinv(amie_b200_ctx * ctx, int kind)
         if(!ctx->user_diag) { ctx->set_error("diagonal preconditioner: amie_b200_set_preconditioner_diagonal was not called") ; return AMIE_B200_ERR_STATE ; }
     }
     else if(!ctx->have_values) { ctx->set_error("inverse diagonal: no values") ; return AMIE_B200_ERR_STATE ; }
-    if(kind != AMIE_B200_PRECOND_JACOBI && kind != AMIE_B200_PRECOND_DIAGONAL && ctx->dist)
+    const bool block = kind == AMIE_B200_PRECOND_BLOCK2X2 || kind == AMIE_B200_PRECOND_BLOCK3X3 ;
+    if(block && ctx->S != (kind == AMIE_B200_PRECOND_BLOCK2X2 ? 2 : 3))
+    {
+        ctx->set_error("block preconditioner: kind 5 (Inverse2x2Diagonal) takes stride 2, kind 6 stride 3") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    if(!block && kind != AMIE_B200_PRECOND_JACOBI && kind != AMIE_B200_PRECOND_DIAGONAL && ctx->dist)
     {
         ctx->set_error("InverseDiagonalSquared / InverseLumpedDiagonal: not available on a row-partitioned context (pass the diagonal)") ;
         return AMIE_B200_ERR_UNSUPPORTED ;
     }
-    if(!ctx->dinv) CUDA_TRY(ctx, cudaMalloc(&ctx->dinv, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;
+    const uint64_t need = std::max<uint64_t>(block ? ctx->N*(uint64_t)ctx->S : ctx->N, 1) ;
+    if(ctx->dinv_len < need)
+    {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+        dfree(ctx->dinv) ;
+        ctx->dinv_len = 0 ;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dinv, need*sizeof(double))) ;
+        ctx->dinv_len = need ;
+    }
     ctx->dinv_valid = false ;
     int grid = vec_grid(ctx, ctx->N) ;
 #define DIAG_BY_STRIDE(KERNEL, ...) do { \
@@ -103,6 +119,12 @@ int ctx_ensure_dinv(amie_b200_ctx * ctx, int kind)
         DIAG_BY_STRIDE(k_inverse_diagonal_squared, ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
     else if(kind == AMIE_B200_PRECOND_LUMPED)
         DIAG_BY_STRIDE(k_inverse_lumped_diagonal, ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    else if(block)
+    {
+        const int g = vec_grid(ctx, ctx->nb) ;
+        if(ctx->S == 2) k_block_inverse<2><<<g, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+        else            k_block_inverse<3><<<g, 256, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->vals, ctx->nb, ctx->dinv) ;
+    }
     else if(kind != AMIE_B200_PRECOND_JACOBI) { ctx->set_error("unknown diagonal preconditioner kind") ; return AMIE_B200_ERR_ARG ; }
     else if(ctx->dist)
     {
@@ -273,8 +295,6 @@ int amie_b200_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
     else if(k == "verbose") ctx->opt_verbose = (int)value ;
     else if(k == "iters_per_batch") ctx->opt_batch = (int)value ;
     else if(k == "graph") ctx->opt_graph = (int)value ;
-    else if(k == "assemble_variant") ctx->opt_assemble_variant = (int)value ;
-    else if(k == "dirichlet_variant") ctx->opt_dirichlet_variant = (int)value ;
     else if(k == "fields_variant") ctx->opt_fields_variant = (int)value ;
     else { ctx->set_error("unknown option "+k) ; return AMIE_B200_ERR_ARG ; }
     return AMIE_B200_OK ;
@@ -800,9 +820,22 @@ int amie_b200_set_preconditioner_diagonal(amie_b200_ctx * ctx, const double * d)
     return AMIE_B200_OK ;
 }
 
+int amie_b200_preconditioner_blocks(amie_b200_ctx * ctx, int precond_kind, double * blocks_out)
+{
+    if(!ctx || !blocks_out || (precond_kind != AMIE_B200_PRECOND_BLOCK2X2 && precond_kind != AMIE_B200_PRECOND_BLOCK3X3)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group)
+        return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_preconditioner_blocks(c, precond_kind, blocks_out+d0*(uint64_t)c->S) ; }) ;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    int rc = ctx_ensure_dinv(ctx, precond_kind) ;
+    if(rc) return rc ;
+    CUDA_TRY(ctx, cudaMemcpyAsync(blocks_out, ctx->dinv, ctx->N*(uint64_t)ctx->S*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) ;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+    return AMIE_B200_OK ;
+}
+
 int amie_b200_preconditioner_diagonal(amie_b200_ctx * ctx, int precond_kind, double * d_out)
 {
-    if(!ctx || !d_out || precond_kind == AMIE_B200_PRECOND_NULL) return AMIE_B200_ERR_ARG ;
+    if(!ctx || !d_out || precond_kind == AMIE_B200_PRECOND_NULL || precond_kind > AMIE_B200_PRECOND_DIAGONAL) return AMIE_B200_ERR_ARG ;
     if(ctx->group) return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) { return amie_b200_preconditioner_diagonal(c, precond_kind, d_out+d0) ; }) ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     int rc = ctx_ensure_dinv(ctx, precond_kind) ;

@@ -13,14 +13,18 @@
 // run-to-run deterministic.  The elimination runs one thread per scalar row, which owns every entry and the
 // right-hand-side component the reference touches while it walks that row.
 //
-// Traffic: gather = element blocks once (8 s^2 B each) + their 4 B list entries + the stored blocks written once;
-// elimination = column indices + a per-node mask byte, values only where a fixed dof is involved.
+// Layout.  update_elements does not keep the elementary matrices in upload order: a placing kernel writes every
+// block, multiplied by its element's scale, to ITS position in a stream where the contributions of one stored block
+// are contiguous and in element order (the permutation is built once per topology by set_elements).  The gather then
+// reads that stream front to back -- no index list, no scale lookup, whole sectors.
+//
+// Traffic: gather = element blocks once (8 s^2 B each) + 4 B of list offsets per stored block + the stored blocks
+// written once; elimination = column indices + a per-node mask byte, values only where a fixed dof is involved.
 #include "context.h"
 #include "kernels_assemble.cuh"
 #include <algorithm>
 #include <vector>
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_radix_sort.cuh>
 
 
 struct AssemblyMap
@@ -29,11 +33,12 @@ struct AssemblyMap
     int npe = 0 ;
     uint64_t nsrc = 0 ;                 // n_elem*npe*npe element blocks
     uint32_t * dest_of_src = nullptr ;  // [nsrc] stored block each element block lands on (NO_DEST: unused node slot)
-    uint32_t * cptr = nullptr ;         // [nnzb+1] contribution lists per stored block
-    uint32_t * csrc = nullptr ;         // [ncontrib] element-block indices, ascending within a list
-    uint32_t * order = nullptr ;        // [nnzb] stored blocks by list length, longest first (variant 3; built on first use)
-    double * ke = nullptr ;             // [nsrc*S*S] elementary matrices (blocks column-major)
-    double * scales = nullptr ;         // [n_elem]
+    uint32_t * cptr = nullptr ;         // [nnzb+1] contribution runs per stored block (positions in `placed`)
+    uint32_t * pos_of_src = nullptr ;   // [nsrc] position of every element block in `placed` (NO_DEST: unused node slot)
+    uint64_t total = 0 ;                // contributions in all
+    double * placed = nullptr ;         // [total*S*S] scale*Ke, the contributions of a stored block contiguous and in element order
+    double * stage = nullptr ;          // upload staging (STAGE_DOUBLES doubles) + one scale per staged element
+    double * stage_scales = nullptr ;
     unsigned char * dirty = nullptr ;   // [nnzb] stored blocks to re-accumulate at the next assemble
     bool built = false ;                // set_elements done (the struct also carries the BC scratch alone)
     bool all_dirty = true ;
@@ -41,10 +46,11 @@ struct AssemblyMap
     // boundary-condition scratch (sized on demand)
     unsigned char * fixmask = nullptr ; // [nb] bit n: dof n of the node is eliminated
     unsigned char * forcemask = nullptr ;
-    uint32_t * fixoff = nullptr ;       // [nb] variant 1 of the elimination: position of the node's first id in the list
-    uint32_t * forceoff = nullptr ;
     uint64_t mask_nb = 0 ;
 } ;
+
+// doubles staged per upload chunk (64 MB): update_elements streams the host array through it
+static const uint64_t STAGE_DOUBLES = 8ull << 20 ;
 
 template<typename T> static void afree(T *& p) { if(p) cudaFree(p) ; p = nullptr ; }
 
@@ -52,8 +58,8 @@ void assembly_map_destroy(amie_b200_ctx * ctx)
 {
     AssemblyMap * m = ctx->amap ;
     if(!m) return ;
-    afree(m->dest_of_src) ; afree(m->cptr) ; afree(m->csrc) ; afree(m->order) ; afree(m->ke) ; afree(m->scales) ; afree(m->dirty) ;
-    afree(m->fixmask) ; afree(m->forcemask) ; afree(m->fixoff) ; afree(m->forceoff) ;
+    afree(m->dest_of_src) ; afree(m->cptr) ; afree(m->pos_of_src) ; afree(m->placed) ; afree(m->stage) ; afree(m->stage_scales) ; afree(m->dirty) ;
+    afree(m->fixmask) ; afree(m->forcemask) ;
     delete m ;
     ctx->amap = nullptr ;
 }
@@ -66,11 +72,11 @@ uint64_t assembly_map_bytes(const amie_b200_ctx * ctx)
     if(m->built)
     {
         const uint64_t SS = (uint64_t)ctx->S*ctx->S ;
-        b += m->nsrc*4+(ctx->nnzb+1)*4+ctx->nnzb+m->nsrc*SS*8+m->n_elem*8 ;     // dest_of_src, cptr, dirty, ke, scales
-        b += m->nsrc*4 ;                                                         // csrc: at most one entry per element block
-        if(m->order) b += ctx->nnzb*4 ;
+        b += m->nsrc*4+(ctx->nnzb+1)*4+ctx->nnzb+m->total*SS*8 ;                // dest_of_src, cptr, dirty, placed
+        b += m->nsrc*4 ;                                                         // pos_of_src
+        if(m->stage) b += STAGE_DOUBLES*8+STAGE_DOUBLES/SS*8 ;
     }
-    if(m->fixmask) b += 2*m->mask_nb+2*m->mask_nb*4 ;
+    if(m->fixmask) b += 2*m->mask_nb ;
     return b ;
 }
 
@@ -90,33 +96,6 @@ static bool ascending_unique(const uint32_t * ids, uint64_t n, uint64_t limit)
     return true ;
 }
 
-// variant 3: the visiting order of the stored blocks, by contribution-list length (descending, stable)
-static int ensure_order(amie_b200_ctx * ctx, AssemblyMap * m)
-{
-    if(m->order || !ctx->nnzb) return AMIE_B200_OK ;
-    const uint64_t n = ctx->nnzb ;
-    uint32_t * len = nullptr, * len_sorted = nullptr, * id = nullptr ;
-    void * tmp = nullptr ;
-    size_t tmp_bytes = 0 ;
-    auto cleanup = [&]() { afree(len) ; afree(len_sorted) ; afree(id) ; if(tmp) cudaFree(tmp) ; tmp = nullptr ; } ;
-#define ORD_TRY(expr) do { cudaError_t _e = (expr) ; if(_e != cudaSuccess) { cleanup() ; afree(m->order) ; \
-        ctx->set_error(std::string(#expr)+": "+cudaGetErrorString(_e)) ; return AMIE_B200_ERR_CUDA ; } } while(0)
-    ORD_TRY(cudaMalloc(&len, n*sizeof(uint32_t))) ;
-    ORD_TRY(cudaMalloc(&len_sorted, n*sizeof(uint32_t))) ;
-    ORD_TRY(cudaMalloc(&id, n*sizeof(uint32_t))) ;
-    ORD_TRY(cudaMalloc(&m->order, n*sizeof(uint32_t))) ;
-    k_list_lengths<<<vec_grid(ctx, n), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, n, len, id) ;
-    ORD_TRY(cudaGetLastError()) ;
-    // lists are a handful of entries long: 16 key bits are plenty, but a list may in principle be longer -> all 32
-    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len, len_sorted, id, m->order, n, 0, 32, ctx->stream)) ;
-    ORD_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16))) ;
-    ORD_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len, len_sorted, id, m->order, n, 0, 32, ctx->stream)) ;
-    ORD_TRY(cudaStreamSynchronize(ctx->stream)) ;
-#undef ORD_TRY
-    cleanup() ;
-    return AMIE_B200_OK ;
-}
-
 extern "C" {
 
 int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const uint32_t * elem_ids)
@@ -134,11 +113,11 @@ int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const 
     m->n_elem = n_elem ; m->npe = npe ; m->nsrc = nsrc ;
     const int SS = ctx->S*ctx->S ;
     const uint64_t nnzb = ctx->nnzb ;
-    uint32_t * ids = nullptr, * count = nullptr ;
+    uint32_t * ids = nullptr, * count = nullptr, * csrc = nullptr ;
     void * tmp = nullptr ;
     size_t tmp_bytes = 0 ;
     int bad = 0 ;
-    auto cleanup = [&]() { afree(ids) ; afree(count) ; if(tmp) cudaFree(tmp) ; tmp = nullptr ; } ;
+    auto cleanup = [&]() { afree(ids) ; afree(count) ; afree(csrc) ; if(tmp) cudaFree(tmp) ; tmp = nullptr ; } ;
 #define MAP_TRY(expr) do { cudaError_t _e = (expr) ; if(_e != cudaSuccess) { cleanup() ; assembly_map_destroy(ctx) ; \
         ctx->set_error(std::string(#expr)+": "+cudaGetErrorString(_e)) ; return AMIE_B200_ERR_CUDA ; } } while(0)
     MAP_TRY(cudaMalloc(&ids, std::max<uint64_t>(n_elem*npe, 1)*sizeof(uint32_t))) ;
@@ -146,8 +125,7 @@ int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const 
     MAP_TRY(cudaMalloc(&m->dest_of_src, std::max<uint64_t>(nsrc, 1)*sizeof(uint32_t))) ;
     MAP_TRY(cudaMalloc(&m->cptr, (nnzb+1)*sizeof(uint32_t))) ;
     MAP_TRY(cudaMalloc(&m->dirty, std::max<uint64_t>(nnzb, 1))) ;
-    MAP_TRY(cudaMalloc(&m->ke, std::max<uint64_t>(nsrc*SS, 1)*sizeof(double))) ;
-    MAP_TRY(cudaMalloc(&m->scales, std::max<uint64_t>(n_elem, 1)*sizeof(double))) ;
+    MAP_TRY(cudaMalloc(&m->pos_of_src, std::max<uint64_t>(nsrc, 1)*sizeof(uint32_t))) ;
     MAP_TRY(cudaMemcpyAsync(ids, elem_ids, n_elem*npe*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
     MAP_TRY(cudaMemsetAsync(count, 0, (nnzb+1)*sizeof(uint32_t), ctx->stream)) ;
     MAP_TRY(cudaMemsetAsync(ctx->flag, 0, sizeof(int), ctx->stream)) ;
@@ -169,12 +147,17 @@ int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const 
     uint32_t total = 0 ;
     MAP_TRY(cudaMemcpyAsync(&total, m->cptr+nnzb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) ;
     MAP_TRY(cudaStreamSynchronize(ctx->stream)) ;
-    MAP_TRY(cudaMalloc(&m->csrc, std::max<uint64_t>(total, 1)*sizeof(uint32_t))) ;
+    m->total = total ;
+    MAP_TRY(cudaMalloc(&csrc, std::max<uint64_t>(total, 1)*sizeof(uint32_t))) ;
+    MAP_TRY(cudaMalloc(&m->placed, std::max<uint64_t>((uint64_t)total*SS, 1)*sizeof(double))) ;
     MAP_TRY(cudaMemsetAsync(count, 0, (nnzb+1)*sizeof(uint32_t), ctx->stream)) ;       // reused as the fill cursor
+    MAP_TRY(cudaMemsetAsync(m->pos_of_src, 0xFF, std::max<uint64_t>(nsrc, 1)*sizeof(uint32_t), ctx->stream)) ;   // NO_DEST
     if(nsrc)
     {
-        k_map_fill<<<vec_grid(ctx, nsrc), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->dest_of_src, nsrc, m->cptr, count, m->csrc) ;
-        k_map_sort<<<vec_grid(ctx, nnzb), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, nnzb) ;
+        // the lists (element blocks per stored block, ascending = element order) exist only to number the stream
+        k_map_fill<<<vec_grid(ctx, nsrc), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->dest_of_src, nsrc, m->cptr, count, csrc) ;
+        k_map_sort<<<vec_grid(ctx, nnzb), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, csrc, nnzb) ;
+        if(total) k_map_positions<<<vec_grid(ctx, total), AMIE_VEC_THREADS, 0, ctx->stream>>>(csrc, total, m->pos_of_src) ;
     }
     MAP_TRY(cudaGetLastError()) ;
     MAP_TRY(cudaStreamSynchronize(ctx->stream)) ;
@@ -198,22 +181,39 @@ int amie_b200_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t coun
     const uint64_t pp = (uint64_t)m->npe*m->npe, SS = (uint64_t)ctx->S*ctx->S ;
     if(!m->have_ke)
     {
-        // elements never uploaded contribute nothing until they are (scale 1, Ke 0)
-        CUDA_TRY(ctx, cudaMemsetAsync(m->ke, 0, std::max<uint64_t>(m->nsrc*SS, 1)*sizeof(double), ctx->stream)) ;
-        std::vector<double> ones(m->n_elem, 1.) ;
-        CUDA_TRY(ctx, cudaMemcpyAsync(m->scales, ones.data(), m->n_elem*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+        // elements never uploaded contribute nothing until they are
+        CUDA_TRY(ctx, cudaMemsetAsync(m->placed, 0, std::max<uint64_t>(m->total*SS, 1)*sizeof(double), ctx->stream)) ;
         m->have_ke = true ;
     }
     if(!count) return AMIE_B200_OK ;
-    CUDA_TRY(ctx, cudaMemcpyAsync(m->ke+first*pp*SS, ke, count*pp*SS*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-    if(scales)
-        CUDA_TRY(ctx, cudaMemcpyAsync(m->scales+first, scales, count*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-    else
+    if(!m->stage)
     {
-        std::vector<double> ones(count, 1.) ;
-        CUDA_TRY(ctx, cudaMemcpyAsync(m->scales+first, ones.data(), count*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->stage, STAGE_DOUBLES*sizeof(double))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->stage_scales, (STAGE_DOUBLES/SS+1)*sizeof(double))) ;
+    }
+    // host array -> staging -> its places in the stream, one chunk of whole elements at a time
+    const uint64_t per_elem = pp*SS ;
+    const uint64_t chunk = std::max<uint64_t>(1, STAGE_DOUBLES/per_elem) ;
+    if(per_elem > STAGE_DOUBLES) { ctx->set_error("update_elements: one elementary matrix exceeds the staging buffer") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    for(uint64_t e0 = 0 ; e0 < count ; e0 += chunk)
+    {
+        const uint64_t ne = std::min(chunk, count-e0) ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(m->stage, ke+e0*per_elem, ne*per_elem*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        if(scales) CUDA_TRY(ctx, cudaMemcpyAsync(m->stage_scales, scales+e0, ne*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        const double * sc = scales ? m->stage_scales : nullptr ;
+        const int g = vec_grid(ctx, ne*per_elem) ;
+        const uint64_t src0 = (first+e0)*pp, ns = ne*pp ;
+#define PLACE(N) k_place_elements<N><<<g, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->stage, sc, first+e0, m->pos_of_src, src0, ns, (uint32_t)pp, m->placed)
+        switch(ctx->S)
+        {
+            case 1: PLACE(1) ; break ;
+            case 2: PLACE(4) ; break ;
+            case 3: PLACE(9) ; break ;
+            case 4: PLACE(16) ; break ;
+            case 6: PLACE(36) ; break ;
+            default: ctx->set_error("update_elements: unsupported stride") ; return AMIE_B200_ERR_UNSUPPORTED ;
+        }
+#undef PLACE
     }
     if(!m->all_dirty)
         k_mark_dirty<<<vec_grid(ctx, count*pp), AMIE_VEC_THREADS, 0, ctx->stream>>>(m->dest_of_src, first*pp, (first+count)*pp, m->dirty) ;
@@ -230,22 +230,12 @@ int amie_b200_assemble(amie_b200_ctx * ctx)
     if(!m || !m->built || !m->have_ke) { ctx->set_error("assemble before set_elements + update_elements") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     const uint64_t SS = (uint64_t)ctx->S*ctx->S, nent = ctx->nnzb*SS ;
-    const uint32_t pp = (uint32_t)(m->npe*m->npe) ;
     const int all = m->all_dirty ? 1 : 0 ;
     const int grid = vec_grid(ctx, nent) ;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     if(nent)
     {
-        // variants 2 / 3: SS-thread groups, G stored blocks per block and step; 3 visits them by list length (kernels_assemble.cuh)
-        const int variant = ctx->opt_assemble_variant ;
-        const uint32_t G2 = (uint32_t)(AMIE_VEC_THREADS/SS) ;
-        const int grid2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((ctx->nnzb+G2-1)/G2, (uint64_t)ctx->num_sms*8)) ;
-        if(variant == 3) { int rc = ensure_order(ctx, m) ; if(rc) return rc ; }
-        const uint32_t * order = variant == 3 ? m->order : nullptr ;
-#define GATHER(N) do { if(variant == 2 || variant == 3) \
-            k_assemble_gather_v2<N><<<grid2, N*G2, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, order, m->dirty, all, ctx->vals, (uint32_t)ctx->nnzb) ; \
-        else \
-            k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->csrc, m->ke, m->scales, pp, m->dirty, all, ctx->vals, nent) ; } while(0)
+#define GATHER(N) k_assemble_gather<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(m->cptr, m->placed, m->dirty, all, ctx->vals, nent)
         switch(ctx->S)
         {
             case 1: GATHER(1) ; break ;
@@ -287,15 +277,12 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     AssemblyMap * m = ctx->amap ;
     if(m->mask_nb != ctx->nb)
     {
-        afree(m->fixmask) ; afree(m->forcemask) ; afree(m->fixoff) ; afree(m->forceoff) ;
+        afree(m->fixmask) ; afree(m->forcemask) ;
         m->mask_nb = 0 ;
         CUDA_TRY(ctx, cudaMalloc(&m->fixmask, std::max<uint64_t>(ctx->nb, 1))) ;
         CUDA_TRY(ctx, cudaMalloc(&m->forcemask, std::max<uint64_t>(ctx->nb, 1))) ;
-        CUDA_TRY(ctx, cudaMalloc(&m->fixoff, std::max<uint64_t>(ctx->nb, 1)*sizeof(uint32_t))) ;
-        CUDA_TRY(ctx, cudaMalloc(&m->forceoff, std::max<uint64_t>(ctx->nb, 1)*sizeof(uint32_t))) ;
         m->mask_nb = ctx->nb ;
     }
-    const bool offs = ctx->opt_dirichlet_variant == 1 ;
     uint32_t * d_ids = nullptr ;
     double * d_vals = nullptr, * d_add = nullptr, * d_nat = nullptr ;
     const uint64_t nm = nfix+nforce ;
@@ -309,16 +296,14 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
         BC_TRY(cudaMemcpyAsync(d_ids, fix_ids, nfix*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals, fix_values, nfix*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemsetAsync(m->fixmask, 0, ctx->nb, ctx->stream)) ;
-        if(offs) k_bc_mask_offsets<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask, m->fixoff) ;
-        else     k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask) ;
+        k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask) ;
     }
     if(nforce)
     {
         BC_TRY(cudaMemcpyAsync(d_ids+nfix, force_ids, nforce*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals+nfix, force_values, nforce*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemsetAsync(m->forcemask, 0, ctx->nb, ctx->stream)) ;
-        if(offs) k_bc_mask_offsets<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask, m->forceoff) ;
-        else     k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask) ;
+        k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask) ;
     }
     if(add_to_forces)
     {
@@ -333,10 +318,8 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     unsigned char * dirty = (m->built && !m->all_dirty) ? m->dirty : nullptr ;
     BC_TRY(cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     const int grid = vec_grid(ctx, ctx->N) ;
-#define DIRICHLET(N) do { if(offs) k_dirichlet<N, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
-        m->fixmask, m->fixoff, d_vals, (uint32_t)nfix, m->forcemask, m->forceoff, d_vals+nfix, (uint32_t)nforce, dirty) ; \
-    else k_dirichlet<N, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
-        m->fixmask, d_ids, d_vals, (uint32_t)nfix, m->forcemask, d_ids+nfix, d_vals+nfix, (uint32_t)nforce, dirty) ; } while(0)
+#define DIRICHLET(N) k_dirichlet<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
+        m->fixmask, d_ids, d_vals, (uint32_t)nfix, m->forcemask, d_ids+nfix, d_vals+nfix, (uint32_t)nforce, dirty)
     if(ctx->N)
         switch(ctx->S)
         {

@@ -31,7 +31,8 @@ struct amie_b200_ctx
     double * vals = nullptr ;
     double * dinv = nullptr ;
     bool have_structure = false, have_values = false, dinv_valid = false ;
-    int dinv_kind = AMIE_B200_PRECOND_JACOBI ;   // which diagonal preconditioner `dinv` holds while dinv_valid
+    int dinv_kind = AMIE_B200_PRECOND_JACOBI ;   // which preconditioner `dinv` holds while dinv_valid (a diagonal, or s x s blocks for kinds 5 / 6)
+    uint64_t dinv_len = 0 ;                      // doubles allocated for it
     double * user_diag = nullptr ;               // AMIE_B200_PRECOND_DIAGONAL: the caller's diagonal (N doubles)
     uint32_t * block_to = nullptr ;              // amie_b200_set_block_map: block k of the host array -> stored block (nnzb)
     bool have_rhs = false ;
@@ -59,9 +60,7 @@ struct amie_b200_ctx
     int opt_verbose = 0 ;
     int opt_batch = 0 ;         // iterations per speculative batch (0 = auto)
     int opt_graph = -1 ;        // -1 auto, 0 off, 1 on
-    int opt_assemble_variant = 0 ;  // 0: one stored entry per thread; 2: entry-group blocks; 3: + stored blocks visited by list length (kernels_assemble.cuh)
-    int opt_fields_variant = 0 ;    // 1: slot loop of k_element_fields unrolled and phase-split for linear triangles / tetrahedra
-    int opt_dirichlet_variant = 0 ; // 0: binary search of the id list per fixed dof; 1: per-node offsets (kernels_assemble.cuh)
+    int opt_fields_variant = 1 ;    // 1: slot loop of k_element_fields unrolled and phase-split for linear triangles / tetrahedra; 0: generic loop
 
     // ---- stats
     amie_b200_stats stats {} ;

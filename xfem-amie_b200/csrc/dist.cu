@@ -436,6 +436,16 @@ int dist_allreduce_max(amie_b200_ctx * ctx, double * value)
     return comm_allreduce_scalar(ctx, value, 1) ;
 }
 
+// In-process groups: every part has finished what it was doing on the HOST side (allocations above all) before any
+// part goes on to queue kernels that wait for the others on the device.  Nothing to do between processes.
+int dist_host_barrier(amie_b200_ctx * ctx)
+{
+    DistState * d = ctx->dist ;
+    if(!d || !d->local) return AMIE_B200_OK ;
+    GROUP_TRY(ctx, d->local->barrier()) ;
+    return AMIE_B200_OK ;
+}
+
 int dist_inverse_diagonal(amie_b200_ctx * ctx)
 {
     int grid = vec_grid(ctx, ctx->N) ;
@@ -590,14 +600,10 @@ int dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c)
         cs_local = std::min<uint64_t>(c.colstart-d->bounds[d->rank]*S, ctx->N) ;
     if(cs_local)
     {
-        if(d->cs_save_len < cs_local)
-        {
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)) ;
-            if(d->cs_save) cudaFree(d->cs_save) ;
-            d->cs_save = nullptr ; d->cs_save_len = 0 ;
-            CUDA_TRY(ctx, cudaMalloc(&d->cs_save, ctx->N*sizeof(double))) ;
-            d->cs_save_len = ctx->N ;
-        }
+        // (the parking buffer is allocated with the structure: no allocation may happen here, where another part of
+        // an in-process group can already be waiting on this one ON THE DEVICE -- cudaMalloc / cudaFree may synchronise
+        // the device, and two parts may share one)
+        if(d->cs_save_len < cs_local) { ctx->set_error("distributed SpMV: colstart buffer missing") ; return AMIE_B200_ERR_STATE ; }
         CUDA_TRY(ctx, cudaMemcpyAsync(d->cs_save, xv, cs_local*sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)) ;
         CUDA_TRY(ctx, cudaMemsetAsync(xv, 0, cs_local*sizeof(double), ctx->stream)) ;
     }
@@ -839,6 +845,9 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     ctx->ncols_local = (uint64_t)nbl+d->nhalo ;
     int arc = ctx_alloc_vectors(ctx) ;
     if(arc) return arc ;
+    if(d->cs_save) { cudaFree(d->cs_save) ; d->cs_save = nullptr ; d->cs_save_len = 0 ; }
+    CUDA_TRY(ctx, cudaMalloc(&d->cs_save, std::max<uint64_t>(ctx->N, 1)*sizeof(double))) ;     // colstart > 0: see dist_spmv
+    d->cs_save_len = ctx->N ;
     // vectors may have been re-allocated: earlier mappings of them are stale
     d->vec_maps.clear() ;
     return peer_setup(ctx) ;

@@ -12,6 +12,7 @@ int  dist_spmv(amie_b200_ctx * ctx, const SpmvCall & c) ;
 int  dist_finalize(amie_b200_ctx * ctx, int kind) ;              // allreduce of st->red_local + scalar step on every rank
 int  dist_allreduce_max(amie_b200_ctx * ctx, double * value) ;
 int  dist_inverse_diagonal(amie_b200_ctx * ctx) ;
+int  dist_host_barrier(amie_b200_ctx * ctx) ;                    // in-process groups: all parts past their host-side allocations
 // a GLOBAL rowstart (DOF units) in the local row numbering of this rank: 0 .. N_local
 uint64_t dist_local_rowstart(const amie_b200_ctx * ctx, uint64_t rowstart_global) ;
 

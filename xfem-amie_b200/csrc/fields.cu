@@ -204,8 +204,10 @@ int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u
         const int grid = field_grid(ctx, m->n_elem) ;
 #define FIELDS(D, P) k_element_fields<D, P><<<grid, FIELD_THREADS, 0, ctx->stream>>>(m->ids, m->dshape, m->jinv, m->tensors, m->istrain, m->istress, \
                     m->tensor_of_elem, du, len, m->n_elem, m->npe, m->out[0], m->out[1], m->out[2])
-        // "fields_variant" = 1: the unrolled, phase-split form for linear triangles / tetrahedra (kernels_fields.cuh)
-        const bool unrolled = ctx->opt_fields_variant == 1 ;
+        // linear triangles / tetrahedra take the unrolled, phase-split instantiations (kernels_fields.cuh: 18 loads in
+        // flight before the first multiply; 71 -> 77 % and 78 -> 80 % of the measured peak, same bits,
+        // profiles/r02_notes.md); option "fields_variant" = 0 forces the generic slot loop (tests)
+        const bool unrolled = ctx->opt_fields_variant != 0 ;
         if(m->dim == 2) { if(unrolled && m->npe == 3) FIELDS(2, 3) ; else FIELDS(2, 0) ; }
         else            { if(unrolled && m->npe == 4) FIELDS(3, 4) ; else FIELDS(3, 0) ; }
 #undef FIELDS

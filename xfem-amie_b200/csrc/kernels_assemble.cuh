@@ -79,12 +79,44 @@ static __global__ void k_mark_dirty(const uint32_t * __restrict__ dest_of_src, u
     }
 }
 
+// position of every element block in the PLACED stream: the contributions of stored block d occupy positions
+// [cptr[d], cptr[d+1]) in list order (ascending element-block index = element order)
+static __global__ void k_map_positions(const uint32_t * __restrict__ csrc, uint64_t total, uint32_t * __restrict__ pos_of_src)
+{
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    for(uint64_t p = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; p < total ; p += stride)
+        pos_of_src[csrc[p]] = (uint32_t)p ;
+}
+
+// update_elements: the uploaded elementary matrices go to their places in the stream, already multiplied by the
+// element's scale -- `scale*Ke` rounds the same whenever it is formed, so the sums below keep the reference's bits.
+// stage holds the blocks [src0, src0+nsrc) in upload order; scales (NULL = 1) one value per element from elem0 on.
+template<int SS>
+static __global__ void k_place_elements(const double * __restrict__ stage, const double * __restrict__ scales, uint64_t elem0,
+                                        const uint32_t * __restrict__ pos_of_src, uint64_t src0, uint64_t nsrc, uint32_t pp,
+                                        double * __restrict__ placed)
+{
+    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
+    for(uint64_t idx = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; idx < nsrc*SS ; idx += stride)
+    {
+        const uint64_t s = idx/SS ;
+        const uint32_t ent = (uint32_t)(idx-s*SS) ;
+        const uint64_t src = src0+s ;
+        const uint32_t pos = __ldg(pos_of_src+src) ;
+        if(pos == NO_DEST) continue ;
+        const double sc = scales ? __ldg(scales+(src/pp-elem0)) : 1. ;
+        placed[(uint64_t)pos*SS+ent] = __dmul_rn(sc, ld_stream(stage+idx)) ;
+    }
+}
+
 // one thread per stored entry: replay `y = scale*Ke - c ; t = a + y ; c = (t - a) - y ; a = t` over the block's
 // contributions in element order (solvers/assembly.cpp:685-690).  Explicit _rn intrinsics: no FMA contraction.
+// The contributions are one contiguous run of the placed stream: no index list, no scale load, and the 9 threads of a
+// stored block (and the blocks next to it in the warp) walk neighbouring 72-byte pieces -- every sector that is
+// fetched is used whole (the list-indexed version fetched 1.26x its bytes: profiles/r01c_ncu_assembly.txt).
 template<int SS>
-static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
-                                         const double * __restrict__ ke, const double * __restrict__ scales,
-                                         uint32_t pp, unsigned char * __restrict__ dirty, int all,
+static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, const double * __restrict__ placed,
+                                         unsigned char * __restrict__ dirty, int all,
                                          double * __restrict__ vals, uint64_t nent)
 {
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
@@ -94,76 +126,16 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
         const uint32_t ent = (uint32_t)(idx-d*SS) ;
         if(!all && !dirty[d]) continue ;
         const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
+        const double * v = placed+(uint64_t)p0*SS+ent ;
         double a = 0., c = 0. ;
-        for(uint32_t p = p0 ; p < p1 ; p++)
+        for(uint32_t p = p0 ; p < p1 ; p++, v += SS)
         {
-            const uint32_t src = __ldg(csrc+p) ;
-            const double sc = __ldg(scales+src/pp) ;
-            const double y = __dsub_rn(__dmul_rn(sc, ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
+            const double y = __dsub_rn(ld_stream(v), c) ;
             const double t = __dadd_rn(a, y) ;
             c = __dsub_rn(__dsub_rn(t, a), y) ;
             a = t ;
         }
         vals[idx] = a ;
-    }
-}
-
-// Variants 2 and 3 (option "assemble_variant").  ncu and the SASS of the plain kernel (profiles/r01c_ncu_assembly.txt,
-// profiles/r01_notes.md): it is issue-bound at 40 % of the DRAM bandwidth, and the instructions go into DIVERGENCE --
-// a warp holds 3.5 stored blocks whose contribution lists are 1 to 8 long (2.3 on average for hexahedra), the loop is
-// unrolled by four with predicated remainders, and every lane waits for the longest list of its warp: 221 warp
-// instructions per 32 entries where ~100 would do.  (The division by the runtime npe^2 is not the cost: the compiler
-// hoists the reciprocal out of the loop.)
-//   variant 2: a block is G groups of SS threads, a thread's entry (threadIdx.x % SS) and group are fixed once and the
-//              stored block advances by G per step in 32-bit arithmetic (no 64-bit division per entry);
-//   variant 3: the same, visiting the stored blocks in the order of `order` -- sorted by list length, longest first,
-//              ties in storage order (k_list_lengths + a stable radix sort, once per topology) -- so the lanes of a
-//              warp walk lists of (almost) one length.
-// Launch with blockDim.x == SS*G.  Per entry the additions and their order are unchanged -> same bits.
-template<int SS>
-static __global__ void k_assemble_gather_v2(const uint32_t * __restrict__ cptr, const uint32_t * __restrict__ csrc,
-                                            const double * __restrict__ ke, const double * __restrict__ scales,
-                                            uint32_t pp, const uint32_t * __restrict__ order,
-                                            const unsigned char * __restrict__ dirty, int all,
-                                            double * __restrict__ vals, uint32_t nnzb)
-{
-    const uint32_t G = blockDim.x/SS ;
-    const uint32_t g = threadIdx.x/SS ;
-    const uint32_t ent = threadIdx.x-g*SS ;
-    const uint32_t step = gridDim.x*G ;
-    for(uint32_t d0 = blockIdx.x*G ; d0 < nnzb ; d0 += step)      // d0 is uniform over the block
-    {
-        if(d0+g < nnzb)
-        {
-            const uint32_t d = order ? __ldg(order+d0+g) : d0+g ;
-            if(all || dirty[d])
-            {
-                const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
-                double a = 0., c = 0. ;
-                for(uint32_t p = p0 ; p < p1 ; p++)
-                {
-                    const uint32_t src = __ldg(csrc+p) ;
-                    const double y = __dsub_rn(__dmul_rn(__ldg(scales+src/pp), ld_stream(ke+(uint64_t)src*SS+ent)), c) ;
-                    const double t = __dadd_rn(a, y) ;
-                    c = __dsub_rn(__dsub_rn(t, a), y) ;
-                    a = t ;
-                }
-                vals[(uint64_t)d*SS+ent] = a ;
-            }
-        }
-        if(step > nnzb-d0) break ;                                  // d0 += step would wrap past 2^32
-    }
-}
-
-// keys and values of the length sort of variant 3: len[k] = length of the contribution list of stored block k, id[k] = k
-static __global__ void k_list_lengths(const uint32_t * __restrict__ cptr, uint64_t nnzb, uint32_t * __restrict__ len,
-                                      uint32_t * __restrict__ id)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; k < nnzb ; k += stride)
-    {
-        len[k] = cptr[k+1]-cptr[k] ;
-        id[k] = (uint32_t)k ;
     }
 }
 
@@ -189,34 +161,6 @@ static __global__ void k_bc_mask(const uint32_t * __restrict__ ids, uint64_t n, 
     }
 }
 
-// variant 1 of the elimination: besides the mask, the position of the node's first id in the sorted list, so that the
-// value of (node, component n) is values[off[node] + popcount(mask & ((1 << n) - 1))] -- one load instead of a
-// binary search of the whole list per fixed dof met (the plain kernel spends its time in those dependent loads:
-// long_scoreboard 66 warps per issue, profiles/r01c_ncu_assembly.txt)
-static __global__ void k_bc_mask_offsets(const uint32_t * __restrict__ ids, uint64_t n, int S, unsigned char * __restrict__ mask,
-                                         uint32_t * __restrict__ off)
-{
-    const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n ; i += stride)
-    {
-        const uint32_t node = ids[i]/S ;
-        if(i && ids[i-1]/S == node) continue ;
-        unsigned int bits = 0 ;
-        for(uint64_t j = i ; j < n && ids[j]/S == node ; j++) bits |= 1u << (ids[j]-node*S) ;
-        mask[node] = (unsigned char)bits ;
-        off[node] = (uint32_t)i ;
-    }
-}
-
-__device__ __forceinline__ double bc_value_at(const double * __restrict__ values, const uint32_t * __restrict__ off,
-                                              uint32_t node, unsigned int mask, int n)
-{
-    unsigned int below = mask & ((1u << n)-1u) ;
-    unsigned int cnt = 0 ;
-    while(below) { cnt += below & 1u ; below >>= 1 ; }
-    return values[off[node]+cnt] ;
-}
-
 __device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, const double * __restrict__ values,
                                            uint32_t n, uint32_t id)
 {
@@ -227,8 +171,8 @@ __device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, co
 // One thread per scalar row (node k, component m).  It walks the row's blocks in storage order and, inside each
 // block, the multipliers of the row's node ("in line", solvers/assembly.cpp:170-207) and then those of the column's
 // node ("in block", :210-253), ascending -- the order in which the reference updates externalForces[k*S+m].
-// OFFS: fix_ids / force_ids are the per-node offsets of k_bc_mask_offsets instead of the sorted id lists (variant 1)
-template<int S, bool OFFS = false>
+// (A per-node offset into the id list instead of the binary search below was measured: same time, profiles/r02_notes.md.)
+template<int S>
 static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint64_t nb,
                                    double * __restrict__ vals, double * __restrict__ forces, double * __restrict__ natural,
                                    const double * __restrict__ add_to_forces,
@@ -239,11 +183,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
                                    unsigned char * __restrict__ dirty)
 {
     // the imposed value of dof (node, n), whose bit is set in the node's mask
-    auto fixed_value = [&](uint32_t node, unsigned int mask, int n)
-    {
-        if(OFFS) return bc_value_at(fix_values, fix_ids, node, mask, n) ;
-        return bc_value(fix_ids, fix_values, nfix, node*S+n) ;
-    } ;
+    auto fixed_value = [&](uint32_t node, unsigned int, int n) { return bc_value(fix_ids, fix_values, nfix, node*S+n) ; } ;
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
     const uint64_t nrows = nb*S ;
     for(uint64_t row = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; row < nrows ; row += stride)
@@ -298,7 +238,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
             }
         }
         if(nforce && ((forcemask[k] >> m) & 1u))                // SET_FORCE_*: externalForces[id] += value (:262-268)
-            f = __dadd_rn(f, OFFS ? bc_value_at(force_values, force_ids, k, forcemask[k], m) : bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
+            f = __dadd_rn(f, bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
         if(add_to_forces)                                       // externalForces += addToExternalForces (:323-324)
             f = __dadd_rn(f, ((rm >> m) & 1u) ? 0. : add_to_forces[row]) ;
         forces[row] = f ;

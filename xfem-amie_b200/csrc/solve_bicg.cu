@@ -68,6 +68,7 @@ int solve_bicg_resident(amie_b200_ctx * ctx, int precond_kind, double epsilon, i
     cudaEventRecord(ctx->ev_a, ctx->stream) ;
     if((rc = ctx_ensure_bicg_vectors(ctx))) return rc ;
     if(precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx, precond_kind))) return rc ;        // :26-34
+    if(ctx->dist && (rc = dist_host_barrier(ctx))) return rc ;          // allocations done everywhere before the parts start waiting for one another
     const size_t vbytes = N*sizeof(double) ;
     const double vepsilon = epsilon*1e-1 ;                                          // :16
     uint64_t nit = 0 ;

@@ -8,6 +8,7 @@
 // whose scalars (rho, beta, pq, alpha, nit, the while() test) are updated on the device, so the
 // host only queues batches of iterations and polls a pinned copy of the state.
 #include "batch_loop.cuh"
+#include "kernels_vec_block.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -25,6 +26,15 @@ int launch_dir(const CgRun & R, bool first)
     amie_b200_ctx * ctx = R.ctx ;
     VecArgs a = vec_args(ctx, first ? 0 : R.rowstart, first ? fin_kind(ctx, FIN_CG_RHO0) : FIN_STORE, first ? 0 : 1) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
+    if(R.precond == PRECOND_BLOCK)
+    {
+        // one thread per node (kernels_vec_block.cuh)
+        grid = vec_grid(ctx, (a.end-a.begin)/ctx->S) ;
+        if(ctx->S == 2) { if(first) k_cg_dir_blk<2, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ; else k_cg_dir_blk<2, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ; }
+        else            { if(first) k_cg_dir_blk<3, true><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ; else k_cg_dir_blk<3, false><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ; }
+        ctx->stats.kernel_launches++ ;
+        return first ? after_reduce(ctx, FIN_CG_RHO0) : AMIE_B200_OK ;
+    }
     if(first)
     {
         // z = r ; P->precondition(r, z) ; p = z  over the whole vector (:183-186) ; last_rho over rows >= rowstart (:189).
@@ -49,7 +59,13 @@ int launch_update(const CgRun & R, bool first)
     const int kind = first ? FIN_CG_RHO_FIRST : FIN_CG_RHO ;
     VecArgs a = vec_args(ctx, R.rowstart, fin_kind(ctx, kind), 1) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
-    if(R.precond == PRECOND_JACOBI) k_cg_update<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    if(R.precond == PRECOND_BLOCK)
+    {
+        grid = vec_grid(ctx, (a.end-a.begin)/ctx->S) ;
+        if(ctx->S == 2) k_cg_update_blk<2><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+        else            k_cg_update_blk<3><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    }
+    else if(R.precond == PRECOND_JACOBI) k_cg_update<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     else                            k_cg_update<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     ctx->stats.kernel_launches++ ;
     return after_reduce(ctx, kind) ;
@@ -60,7 +76,13 @@ int launch_smooth(const CgRun & R)
     amie_b200_ctx * ctx = R.ctx ;
     VecArgs a = vec_args(ctx, R.rowstart, fin_kind(ctx, FIN_STORE), 0) ;
     int grid = vec_grid(ctx, a.end-a.begin) ;
-    if(R.precond == PRECOND_JACOBI) k_smooth<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    if(R.precond == PRECOND_BLOCK)
+    {
+        grid = vec_grid(ctx, (a.end-a.begin)/ctx->S) ;
+        if(ctx->S == 2) k_smooth_blk<2><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+        else            k_smooth_blk<3><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
+    }
+    else if(R.precond == PRECOND_JACOBI) k_smooth<PRECOND_JACOBI><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     else                            k_smooth<PRECOND_NULL><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(a) ;
     ctx->stats.kernel_launches++ ;
     return after_reduce(ctx, FIN_STORE) ;
@@ -100,9 +122,9 @@ int queue_iteration(const CgRun & R)
 int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int maxit, uint64_t nssor,
                       uint64_t rowstart, uint64_t colstart, uint64_t * nit_out, double * err_out, double * rho_out)
 {
-    if(precond_kind < AMIE_B200_PRECOND_JACOBI || precond_kind > AMIE_B200_PRECOND_DIAGONAL)
+    if(precond_kind < AMIE_B200_PRECOND_JACOBI || precond_kind > AMIE_B200_PRECOND_BLOCK3X3)
     {
-        ctx->set_error("pcg: preconditioner kind not on the device path (diagonal preconditioners and NullPreconditionner are)") ;
+        ctx->set_error("pcg: preconditioner kind not on the device path (diagonal and node-block preconditioners and NullPreconditionner are)") ;
         return AMIE_B200_ERR_UNSUPPORTED ;
     }
     const int S = ctx->S ;
@@ -118,7 +140,8 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     ctx_reset_solve_stats(ctx) ;
     cudaEvent_t ev0 = ctx->ev_a, ev1 = ctx->ev_b ;
     cudaEventRecord(ev0, ctx->stream) ;
-    CgRun R { ctx, precond_kind == AMIE_B200_PRECOND_NULL ? PRECOND_NULL : PRECOND_JACOBI, rowstart, colstart } ;
+    const bool block_precond = precond_kind == AMIE_B200_PRECOND_BLOCK2X2 || precond_kind == AMIE_B200_PRECOND_BLOCK3X3 ;
+    CgRun R { ctx, precond_kind == AMIE_B200_PRECOND_NULL ? PRECOND_NULL : (block_precond ? PRECOND_BLOCK : PRECOND_JACOBI), rowstart, colstart } ;
     const size_t vbytes = N*sizeof(double) ;
     int rc ;
     uint64_t nit = 0 ;
@@ -154,7 +177,8 @@ int solve_cg_resident(amie_b200_ctx * ctx, int precond_kind, double eps, int max
     }
     // :80-90
     // every diagonal preconditioner (t = v .* d) runs the Jacobi kernels on its own d
-    if(R.precond == PRECOND_JACOBI && (rc = ctx_ensure_dinv(ctx, precond_kind))) return rc ;
+    if(R.precond != PRECOND_NULL && (rc = ctx_ensure_dinv(ctx, precond_kind))) return rc ;
+    if(ctx->dist && (rc = dist_host_barrier(ctx))) return rc ;          // allocations done everywhere before the parts start waiting for one another
 
     const double realeps = std::max(1e-12, eps) ;                                   // :92
     // getForces().size() is the GLOBAL system size on a row-partitioned context

@@ -6,6 +6,7 @@
 #include <vector>
 #include <iostream>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 
 namespace
@@ -100,9 +101,17 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
     const size_t nb = A.row_size.size(), nnzb = A.column_index.size() ;
     const unsigned int * cp = nnzb ? &A.column_index[0] : nullptr ;
     const uint64_t h = hash_u32(cp, nnzb, 1)^hash_u32(nb ? &A.row_size[0] : nullptr, nb, 2) ;
-    // rowstart / colstart address AMIE's numbering (space-time planes): such assemblies keep it
+    // Renumbering (reverse Cuthill-McKee, once per topology): AMIE's mesher numbering has no locality, and the x gather
+    // of the SpMV pays for it -- measured on a 2.65 M-DOF tetrahedral system with a numbering without locality:
+    // 2.8 TB/s as it comes, 5.3 TB/s renumbered, PCG 2 126 -> 3 622 it/s (profiles/r02_notes.md).  On by default from
+    // 20 000 nodes up (smaller solves are launch-bound); AMIE_B200_RENUMBER=0 / 1 forces it off / on.
+    // rowstart / colstart address AMIE's numbering (space-time planes): such assemblies keep it; so does a
+    // multi-device context (AMIE_B200_DEVICES), which partitions the rows as they come.
     const char * env = getenv("AMIE_B200_RENUMBER") ;
-    const bool want_renumber = env && atoi(env) != 0 && a->rowstart == 0 && a->colstart == 0 && nb > 0 ;
+    const char * devs = getenv("AMIE_B200_DEVICES") ;
+    const bool multi = devs && strchr(devs, ',') ;
+    const bool asked = env ? atoi(env) != 0 : nb >= 20000 ;
+    const bool want_renumber = asked && !multi && a->rowstart == 0 && a->colstart == 0 && nb > 0 ;
     if(e.stride != A.stride || e.nb != nb || e.nnzb != nnzb || e.colptr != cp || e.colhash != h || e.renumbered != want_renumber)
     {
         int rc = 0 ;
@@ -195,7 +204,17 @@ void from_device_order(const std::vector<uint32_t> & perm, size_t stride, const 
 int precond_kind(Amie::Preconditionner * p, const Vector ** diagonal_out)
 {
     *diagonal_out = nullptr ;
-    if(!p) return AMIE_B200_PRECOND_JACOBI ;
+    // Inverse2x2Diagonal (solvers/inversediagonal.cpp:84-133): built on the device from the matrix being solved -- the
+    // usual `Inverse2x2Diagonal P(A)` on the assembly's own matrix (an object built from ANOTHER matrix is not told apart)
+    if(dynamic_cast<Amie::Inverse2x2Diagonal *>(p)) return AMIE_B200_PRECOND_BLOCK2X2 ;
+    if(!p)
+    {
+        // opt-in: node-block Jacobi where the caller passes nullptr (Assembly::cgsolve always does).  Other iteration
+        // counts than the reference's InverseDiagonal: AMIE_B200_BLOCK_JACOBI=1 says the host accepts that.
+        const char * e = getenv("AMIE_B200_BLOCK_JACOBI") ;
+        if(e && atoi(e) != 0) return -2 ;          // resolved by stride in the solver shim
+        return AMIE_B200_PRECOND_JACOBI ;
+    }
     if(dynamic_cast<Amie::NullPreconditionner *>(p)) return AMIE_B200_PRECOND_NULL ;
     if(Amie::InverseDiagonal * d = dynamic_cast<Amie::InverseDiagonal *>(p)) { *diagonal_out = &d->diagonal ; return AMIE_B200_PRECOND_DIAGONAL ; }
     if(Amie::InverseLumpedDiagonal * d = dynamic_cast<Amie::InverseLumpedDiagonal *>(p)) { *diagonal_out = &d->diagonal ; return AMIE_B200_PRECOND_DIAGONAL ; }

@@ -12,7 +12,8 @@ BiConjugateGradientStabilized::BiConjugateGradientStabilized(Assembly * a) :Line
 bool BiConjugateGradientStabilized::solve(const Vector &x0, Preconditionner * precond, const double epsilon , const int maxit , bool verbose )
 {
     const Vector * diagonal = nullptr ;
-    const int kind = AmieB200Shim::precond_kind(precond, &diagonal) ;
+    int kind = AmieB200Shim::precond_kind(precond, &diagonal) ;
+    if(kind == -2) kind = AMIE_B200_PRECOND_JACOBI ;      // AMIE_B200_BLOCK_JACOBI concerns PCG only
     if(kind < 0)
     {
         std::cerr << "amie_b200: this Preconditionner type is not available on the device (nullptr, NullPreconditionner and the diagonal classes of solvers/inversediagonal.h are)" << std::endl ;

@@ -19,7 +19,12 @@ ConjugateGradient::ConjugateGradient( Assembly* a ) :LinearSolver(a), r(0), z(0)
 bool ConjugateGradient::solve(const Vector &x0, Preconditionner * precond, const double eps, const int maxit, bool verbose)
 {
     const Vector * diagonal = nullptr ;
-    const int kind = AmieB200Shim::precond_kind(precond, &diagonal) ;
+    int kind = AmieB200Shim::precond_kind(precond, &diagonal) ;
+    if(kind == -2)
+    {
+        const size_t stride = assembly->getMatrix().stride ;
+        kind = stride == 2 ? AMIE_B200_PRECOND_BLOCK2X2 : (stride == 3 ? AMIE_B200_PRECOND_BLOCK3X3 : AMIE_B200_PRECOND_JACOBI) ;
+    }
     if(kind < 0)
     {
         std::cerr << "amie_b200: this Preconditionner type is not available on the device (nullptr, NullPreconditionner and the diagonal classes of solvers/inversediagonal.h are)" << std::endl ;
