@@ -461,27 +461,31 @@ def main():
                 pasm.upload_x0(None)
                 ok_, nit_, _, _ = pasm.pcg_resident(nssor=32, eps=eps)
                 return int(nit_), pasm.stats().solve_ms
-            lo_eps, hi_eps, best = None, None, None        # lo_eps: too few iterations, hi_eps: too many
+            tried = []                                      # (eps, nit, ms)
+            lo_eps, hi_eps = None, None                     # lo_eps: too few iterations, hi_eps: too many
             for eps in (1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8):
                 n_, ms_ = gpu_try(eps)
+                tried.append((eps, n_, ms_))
                 if n_ < 60:
                     lo_eps = eps
                     continue
-                best = (eps, n_, ms_)
                 hi_eps = eps
                 break
             tries = 0
-            while best and best[1] > 160 and lo_eps and tries < 7:
+            while hi_eps and lo_eps and tries < 6 and not any(60 <= t[1] <= 160 for t in tried):
                 mid = (lo_eps * hi_eps) ** 0.5
                 n_, ms_ = gpu_try(mid)
+                tried.append((mid, n_, ms_))
                 tries += 1
                 if n_ < 60:
                     lo_eps = mid
                 else:
                     hi_eps = mid
-                    best = (mid, n_, ms_)
-            if best is None:
-                best = (1e-10,) + gpu_try(1e-10)
+            # sqrt(|rho|) is not monotone along the iteration: nit(eps) jumps over plateaus, and the window can be empty.
+            # Then the longest solve below it (the CPU side must stay a bounded sample), else the shortest above.
+            inwin = [t for t in tried if 60 <= t[1] <= 160]
+            below = [t for t in tried if 10 <= t[1] < 60]
+            best = min(inwin, key=lambda t: t[1]) if inwin else (max(below, key=lambda t: t[1]) if below else min(tried, key=lambda t: t[1]))
             pair_eps = best[0]
             g_nit, g_ms = gpu_try(pair_eps)                # leaves the x of pair_eps on the device
             x_gpu = pasm.download_x()

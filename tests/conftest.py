@@ -84,3 +84,42 @@ def random_spd_blocks(stride, nb, seed):
             blk[:, :stride] = blocks[(i, j)].T        # element (r,c) at c*cl + r
             arr.append(blk.ravel())
     return rs, np.array(ci, np.uint32), np.concatenate(arr), rng.standard_normal(nb * stride)
+
+
+def with_enrichment_like_rows(S, n_extra, seed, ol):
+    """What XFEM enrichment does to the assembled system (elements/elements.cpp:3711-3717): extra block rows with
+    node-like ids beyond the mesh nodes, coupled to the nodes of the tetrahedra an inclusion surface cuts -- row lengths
+    anywhere between a handful and several dozen blocks -- and to one another; the rows of the nodes they touch grow by
+    as much.  Built on top of a system S (stride 3): symmetric, diagonally dominant additions, so still SPD."""
+    import scipy.sparse as sp
+    s, nb = S.stride, S.nb
+    rng = np.random.default_rng(seed)
+    A = S.to_scipy().tolil()
+    n2 = (nb + n_extra) * s
+    B = sp.lil_matrix((n2, n2))
+    B[:nb * s, :nb * s] = A
+    for e in range(n_extra):
+        row = nb + e
+        centre = int(rng.integers(0, nb))
+        k = int(rng.integers(3, 41))
+        nbrs = set(int(v) for v in np.clip(centre + rng.integers(-40, 41, k), 0, nb - 1))
+        if e and rng.random() < 0.6:
+            nbrs.add(nb + int(rng.integers(0, e)))          # enrichment dofs of neighbouring cut elements couple too
+        tot = 0.0
+        for c in nbrs:
+            blk = 0.05 * rng.standard_normal((s, s))
+            B[row * s:(row + 1) * s, c * s:(c + 1) * s] = blk
+            B[c * s:(c + 1) * s, row * s:(row + 1) * s] = blk.T
+            tot += np.abs(blk).sum()
+            for m in range(s):
+                B[c * s + m, c * s + m] += np.abs(blk).sum()
+        D = 0.05 * rng.standard_normal((s, s))
+        B[row * s:(row + 1) * s, row * s:(row + 1) * s] = 0.5 * (D + D.T) + np.eye(s) * (1.0 + tot)
+    Bb = sp.bsr_matrix(B.tocsr(), blocksize=(s, s))
+    Bb.sort_indices()
+    cl = s + s % 2
+    rs = np.diff(Bb.indptr).astype(np.uint32)
+    arr = np.zeros((Bb.indices.size, s, cl))
+    arr[:, :, :s] = Bb.data.transpose(0, 2, 1)
+    b = np.concatenate([S.b, 0.01 * rng.standard_normal(n_extra * s)])
+    return ol.Sys(s, nb + n_extra, rs, Bb.indices.astype(np.uint32), arr.reshape(-1), b)

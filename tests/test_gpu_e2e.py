@@ -109,8 +109,10 @@ def test_tripoint_damage_resolves_through_the_dropin(tmp_path):
     args = ["tripoint", "24", "@OUT", "6", "900", "4e-5"]
     K = 60
     u_ref, cg_ref, bi_ref, _ = run_until(REF, args, str(tmp_path), K, 600)
-    u_gpu, cg_gpu, bi_gpu, log = run_until(B200, args, str(tmp_path), K, 600, {"AMIE_B200_VERBOSE": "1"})
+    u_gpu, cg_gpu, bi_gpu, log = run_until(B200, args, str(tmp_path), K, 600, {"AMIE_B200_SHIM_TRACE": "1"})
     assert "amie_b200: set_" not in log and "no CPU fallback" not in log, log[-1500:]
+    # the shim uploads the matrix when it changed and only then: the second CG and the BiCGStab of a step see the same array
+    assert "amie_b200: matrix unchanged since the last solve: no upload" in log and "amie_b200: matrix upload:" in log, log[-1500:]
     n = min(len(cg_ref), len(cg_gpu))
     print(f"tripoint: {len(u_ref)} / {len(u_gpu)} load steps written, {len(cg_ref)} / {len(cg_gpu)} CG solves, "
           f"first counts {cg_ref[:8]} vs {cg_gpu[:8]}, last {cg_ref[n - 4:n]} vs {cg_gpu[n - 4:n]}")

@@ -142,6 +142,8 @@ def test_group_resident_sequence_and_generator(pkg, ol, systems, devices):
     # load-step loop without host vectors against the single-device context doing the same
     ref = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
     ref.sync_matrix()
+    for a in (a2, ref):
+        a.upload_x0(None)               # `displacements` before the first step: zero on both
     for step, f in enumerate((1.0, 1.5, 2.25)):
         for a in (a2, ref):
             a.upload_rhs(S.b * f)
@@ -157,8 +159,9 @@ def test_group_resident_sequence_and_generator(pkg, ol, systems, devices):
 
 
 def test_group_matches_single_device_iterates(pkg, systems, devices):
-    """Same system, a fixed number of iterations: the partitioned iterate equals the single-device one up to the
-    rounding of the dot products (the parts sum their rows in another order)."""
+    """Same system, the solve cut short by a loose tolerance (maxit bounds only the restarts, conjugategradient.cpp:93,
+    :121): the partitioned iterate equals the single-device one up to the rounding of the dot products (the parts sum
+    their rows in another order) -- same iteration, same field."""
     S = systems("S3-tet", 14)
     one = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array), S.b, device=0)
     grp = group_assembly(pkg, S, devices)
@@ -166,11 +169,11 @@ def test_group_matches_single_device_iterates(pkg, systems, devices):
     for a in (one, grp):
         cg = pkg.ConjugateGradient(a)
         cg.nssor = 32
-        cg.solve(None, None, 1e-10, 40)
-        assert cg.nit == 40
-        xs.append(cg.x.copy())
+        cg.solve(None, None, 1e-3, -1)
+        xs.append((int(cg.nit), cg.x.copy()))
         a.close()
-    assert rel_l2(xs[1], xs[0]) <= 1e-9
+    assert 5 < xs[0][0] == xs[1][0]
+    assert rel_l2(xs[1][1], xs[0][1]) <= 1e-9
 
 
 def test_group_errors(pkg, systems):

@@ -474,3 +474,31 @@ def test_pcg_parity_against_the_reference_at_scale(pkg, ol, preset, n):
     assert ok == bool(ret)
     assert abs(int(nit) - int(nit_ref)) <= NIT_TOL, (nit, nit_ref)
     assert rel_l2(x, x_ref) <= X_TOL
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0]])
+def test_enrichment_like_irregular_rows(pkg, ol, systems, devices):
+    """BASELINE.json config 5 at the level the solver sees it: XFEM enrichment appends block rows with node-like ids and
+    irregular lengths (3 .. 40+ blocks) and lengthens the rows of the nodes they touch.  (The reference build here cannot
+    produce them itself: FeatureTree::removeUnmeshedFeatures drops the ExpansiveZone3D inclusions of main_3d_asr before
+    enrichment, and kept alive as virtual features they crash its induced-BC update -- DESIGN.md section 7.)
+    Ragged tiles, rows beyond the stage capacity of the SpMV pipeline, one device and two parts."""
+    from conftest import with_enrichment_like_rows
+    S = with_enrichment_like_rows(systems("S3-tet", 12), 150, 7, ol)
+    assert S.row_size.max() >= 40 and S.row_size.min() <= 8
+    A = pkg.CoordinateIndexedSparseMatrix(S.row_size, S.column_index, S.stride, S.array)
+    asm = pkg.Assembly(A, S.b, devices=devices) if devices else pkg.Assembly(A, S.b, device=0)
+    v = np.random.default_rng(3).standard_normal(S.n)
+    scale = np.abs(S.to_scipy()).dot(np.abs(v)).max()
+    assert np.abs(asm.spmv(v) - ol.oracle_assign(S, v)).max() <= SPMV_TOL * scale
+    ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+    cg = pkg.ConjugateGradient(asm)
+    cg.nssor = 32
+    ok = cg.solve(None, None, 1e-10, -1)
+    assert ok == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= NIT_TOL, (cg.nit, info.nit)
+    assert rel_l2(cg.x, x_ref) <= X_TOL
+    bi = pkg.BiConjugateGradientStabilized(asm)
+    okb = bi.solve(None, None, 1e-10, -1)
+    retb, xb_ref, _ = ol.oracle_bicgstab(S)
+    assert okb == bool(retb) and rel_l2(bi.x, xb_ref) <= X_TOL
+    asm.close()

@@ -48,6 +48,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
         "WAIT_DONE:\n"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory") ;
 }
+// one lane polls the barrier, the others wait at the warp barrier: 31 lanes fewer hammering the shared-memory pipe
+// while a warp waits (the producer spends most of its life here).  The elected lane's acquire and the __syncwarp order
+// the stage's contents before every lane's later reads.
+__device__ __forceinline__ void mbar_wait_elect(uint64_t * bar, uint32_t parity, int lane)
+{
+    if(lane == 0) mbar_wait(bar, parity) ;
+    __syncwarp() ;
+}
 __device__ __forceinline__ void tma_bulk_g2s(void * dst_smem, const void * src_gmem, uint32_t bytes, uint64_t * bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -79,7 +87,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void * src_gmem, uint32_t 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory") ;
 }
 
-template<int R, int NST, int CAP, int STAGE_BYTES, int VAL_BYTES, int META_OFF, int PFD = 4, int BB = 72>
+template<int R, int NST, int CAP, int STAGE_BYTES, int VAL_BYTES, int META_OFF, int PFD = 4, int BB = 72, bool ELECT = false>
 __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char * smem, uint64_t * full, uint64_t * empty,
                                               uint32_t ntiles, int lane, uint32_t first = 0, uint32_t step = 1)
 {
@@ -131,7 +139,7 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
             }
             const int s = it%NST ;
             const uint32_t ph = (it/NST) & 1u ;
-            mbar_wait(empty+s, ph^1u) ;
+            if(ELECT) mbar_wait_elect(empty+s, ph^1u, lane) ; else mbar_wait(empty+s, ph^1u) ;
             unsigned char * stage = smem+s*STAGE_BYTES ;
             uint32_t * meta = reinterpret_cast<uint32_t *>(stage+META_OFF) ;
             const uint32_t r0 = a.row0+tile*R ;

@@ -78,10 +78,10 @@ static inline void launch_s3_tma(amie_b200_ctx * ctx, const SpmvArgs & args)
 }
 
 // row-thread pipeline: W compute warps (one 10-row tile each at a time), NST stages, CAP blocks per stage
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1, bool ELECT = false>
 static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB, NP> ;
+    auto kern = k_spmv_s3_rt<DOT, MINUS_B, W, NST, CAP, G, NB, NP, ELECT> ;
     constexpr int smem = RtLayout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+NP)*32 ;
     static int cache[AMIE_MAX_DEVICES] = {} ;
@@ -136,7 +136,9 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
             // fills its stage (27 blocks/row for Q1 hexahedra, 12-15 for linear tetrahedra).  Short rows mean small
             // tiles, and ONE producer warp (~0.3 us per tile) then caps the CTA: three producers there.
             const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
-            if(avg > 15.5 || ctx->opt_variant == 3)
+            if(ctx->opt_variant == 4)      launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1, 9, 1, true>(ctx, args) ;    // A/B: elected barrier polls
+            else if(ctx->opt_variant == 5) launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3, true>(ctx, args) ;
+            else if(avg > 15.5 || ctx->opt_variant == 3)
                 launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;   // 7 stages, not 8: leaves ~30 KB of L1 for the x gather
             else
                 launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3>(ctx, args) ;

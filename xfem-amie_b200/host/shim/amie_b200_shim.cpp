@@ -157,14 +157,14 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
         }
         e.have_values = check ;
         e.valhash = vh ;
-        if(getenv("AMIE_B200_VERBOSE"))
+        if(getenv("AMIE_B200_SHIM_TRACE"))
         {
             amie_b200_stats st ;
             if(amie_b200_get_stats(e.ctx, &st) == 0)
                 std::cerr << "amie_b200: matrix upload: structure " << st.structure_ms << " ms, values " << st.values_ms << " ms" << std::endl ;
         }
     }
-    else if(getenv("AMIE_B200_VERBOSE"))
+    else if(getenv("AMIE_B200_SHIM_TRACE"))
         std::cerr << "amie_b200: matrix unchanged since the last solve: no upload" << std::endl ;
     return e.ctx ;
 }
