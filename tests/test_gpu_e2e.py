@@ -80,11 +80,13 @@ def run_until(exe, args, tmp, max_solves, timeout_s, env_extra=None):
     env = dict(os.environ, OMP_NUM_THREADS="1", **(env_extra or {}))
     p = subprocess.Popen([exe] + [a if a != "@OUT" else out for a in args], cwd=tmp, stdout=subprocess.DEVNULL,
                          stderr=subprocess.PIPE, text=True, env=env)
-    cg, bi, log, t0 = [], [], [], time.time()
+    cg, bi, log, notes, t0 = [], [], [], set(), time.time()
     pat_cg = re.compile(r"CG \d+ converged after (\d+) iterations")
     pat_bi = re.compile(r"BiCGStab \d+ converged after (\d+) iterations")
     for line in p.stderr:
         log.append(line[-300:])
+        for part in line.split("amie_b200: ")[1:]:
+            notes.add(part.split(":")[0].strip()[:60])           # the shim's own messages, whatever progress output surrounds them
         m = pat_cg.search(line)
         if m:
             cg.append(int(m.group(1)))
@@ -95,7 +97,7 @@ def run_until(exe, args, tmp, max_solves, timeout_s, env_extra=None):
             break
     p.kill()
     p.wait()
-    return read_records(out), cg, bi, "".join(log[-40:])
+    return read_records(out), cg, bi, "".join(log[-40:]) + "\nshim notes: " + " | ".join(sorted(notes))
 
 
 def test_tripoint_damage_resolves_through_the_dropin(tmp_path):
@@ -112,7 +114,7 @@ def test_tripoint_damage_resolves_through_the_dropin(tmp_path):
     u_gpu, cg_gpu, bi_gpu, log = run_until(B200, args, str(tmp_path), K, 600, {"AMIE_B200_SHIM_TRACE": "1"})
     assert "amie_b200: set_" not in log and "no CPU fallback" not in log, log[-1500:]
     # the shim uploads the matrix when it changed and only then: the second CG and the BiCGStab of a step see the same array
-    assert "amie_b200: matrix unchanged since the last solve: no upload" in log and "amie_b200: matrix upload:" in log, log[-1500:]
+    assert "matrix unchanged since the last solve" in log and "matrix upload" in log, log[-600:]
     n = min(len(cg_ref), len(cg_gpu))
     print(f"tripoint: {len(u_ref)} / {len(u_gpu)} load steps written, {len(cg_ref)} / {len(cg_gpu)} CG solves, "
           f"first counts {cg_ref[:8]} vs {cg_gpu[:8]}, last {cg_ref[n - 4:n]} vs {cg_gpu[n - 4:n]}")

@@ -715,85 +715,7 @@ int amie_b200_spmv_resident(amie_b200_ctx * ctx, int reps, int variant, double *
         c.dot = DOT_YX ; c.finalize = FIN_STORE ;
         insolve = true ;
     }
-    auto one = [&]()
-    {
-        if(ctx->S == 2 && variant >= 90)
-        {
-            SpmvArgs args ;
-            args.rowptr = ctx->rowptr ; args.col = ctx->col ; args.vals = ctx->vals ;
-            args.x = c.x ; args.b = nullptr ; args.y = c.y ; args.w = nullptr ; args.d = nullptr ;
-            args.row0 = 0 ; args.nrows = (uint32_t)ctx->nb ; args.colstart_blk = 0 ; args.sign = 1. ;
-            args.st = ctx->st ; args.partials = ctx->partials ; args.finalize = FIN_STORE ; args.check_stop = 0 ;
-            switch(variant)
-            {
-            case 90 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 1>(ctx, args) ; break ;
-            case 91 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 2>(ctx, args) ; break ;
-            case 92 : launch_s2_rt<DOT_NONE, false, 6, 16, 144, 1, 4>(ctx, args) ; break ;
-            case 93 : launch_s2_rt<DOT_NONE, false, 8, 20, 144, 1, 4>(ctx, args) ; break ;
-            default : launch_spmv(ctx, c) ;
-            }
-        }
-        else if(ctx->S == 3 && variant >= 10)
-        {
-            // tuning configurations of the TMA pipeline (plain y = A x only)
-            SpmvArgs args ;
-            args.rowptr = ctx->rowptr ; args.col = ctx->col ; args.vals = ctx->vals ;
-            args.x = c.x ; args.b = nullptr ; args.y = c.y ; args.w = nullptr ; args.d = nullptr ;
-            args.row0 = 0 ; args.nrows = (uint32_t)ctx->nb ; args.colstart_blk = 0 ; args.sign = 1. ;
-            args.st = ctx->st ; args.partials = ctx->partials ; args.finalize = FIN_STORE ; args.check_stop = 0 ;
-            if(insolve)
-            {
-                args.finalize = FIN_STORE ;
-                switch(variant)
-                {
-                case 60 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
-                case 61 : launch_s3_rt<DOT_YX, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
-                case 62 : launch_s3_rt<DOT_YX, false, 4, 8, 270, 1, 9>(ctx, args) ; break ;
-                case 63 : launch_s3_rt<DOT_YX, false, 2, 8, 270, 2, 9>(ctx, args) ; break ;
-                case 64 : launch_s3_rt<DOT_YX, false, 2, 8, 270, 3, 9>(ctx, args) ; break ;
-                case 65 : launch_s3_rt<DOT_YX, false, 3, 7, 300, 1, 9>(ctx, args) ; break ;
-                case 66 : launch_s3_rt<DOT_YX, false, 3, 7, 270, 1, 9>(ctx, args) ; break ;
-                case 67 : launch_s3_rt<DOT_YX, false, 3, 6, 270, 1, 9>(ctx, args) ; break ;
-                case 68 : launch_s3_rt<DOT_YX, false, 3, 6, 330, 1, 9>(ctx, args) ; break ;
-                case 69 : launch_s3_rt<DOT_YX, false, 3, 7, 280, 1, 9>(ctx, args) ; break ;
-                case 70 : launch_s3_rt<DOT_YX, false, 3, 8, 272, 1, 9>(ctx, args) ; break ;
-                case 71 : launch_s3_rt<DOT_YX, false, 4, 8, 272, 1, 9>(ctx, args) ; break ;
-                default : launch_spmv(ctx, c) ;
-                }
-            }
-            else
-            switch(variant)
-            {
-            case 80 : launch_s3_rt<DOT_NONE, false, 3, 7, 270, 1, 9, 2>(ctx, args) ; break ;
-            case 81 : launch_s3_rt<DOT_NONE, false, 5, 12, 160, 1, 9, 2>(ctx, args) ; break ;
-            case 82 : launch_s3_rt<DOT_NONE, false, 5, 12, 160, 1, 9, 3>(ctx, args) ; break ;
-            case 83 : launch_s3_rt<DOT_NONE, false, 4, 9, 200, 1, 9, 2>(ctx, args) ; break ;
-            case 60 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 3>(ctx, args) ; break ;
-            case 61 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1, 9>(ctx, args) ; break ;
-            case 15 : launch_s3_tma<DOT_NONE, false, 8, 3, 240>(ctx, args) ; break ;
-            case 18 : launch_s3_tma<DOT_NONE, false, 8, 2, 240>(ctx, args) ; break ;
-            case 52 : launch_s3_rt<DOT_NONE, false, 5, 12, 176, 1>(ctx, args) ; break ;
-            case 53 : launch_s3_rt<DOT_NONE, false, 4, 12, 176, 2>(ctx, args) ; break ;
-            case 54 : launch_s3_rt<DOT_NONE, false, 6, 12, 176, 1>(ctx, args) ; break ;
-            case 55 : launch_s3_rt<DOT_NONE, false, 4, 10, 216, 1>(ctx, args) ; break ;
-            case 40 : launch_s3_rt<DOT_NONE, false, 2, 8, 270, 2>(ctx, args) ; break ;
-            case 41 : launch_s3_rt<DOT_NONE, false, 2, 8, 270, 1>(ctx, args) ; break ;
-            case 42 : launch_s3_rt<DOT_NONE, false, 4, 8, 270, 1>(ctx, args) ; break ;
-            case 43 : launch_s3_rt<DOT_NONE, false, 3, 8, 270, 1>(ctx, args) ; break ;
-            case 44 : launch_s3_rt<DOT_NONE, false, 1, 8, 270, 2>(ctx, args) ; break ;
-            case 45 : launch_s3_rt<DOT_NONE, false, 1, 8, 270, 4>(ctx, args) ; break ;
-            case 46 : launch_s3_rt<DOT_NONE, false, 2, 4, 270, 1>(ctx, args) ; break ;
-            case 47 : launch_s3_rt<DOT_NONE, false, 1, 4, 270, 2>(ctx, args) ; break ;
-            case 48 : launch_s3_rt<DOT_NONE, false, 2, 7, 300, 1>(ctx, args) ; break ;
-            case 49 : launch_s3_rt<DOT_NONE, false, 1, 2, 270, 1>(ctx, args) ; break ;
-            case 50 : launch_s3_rt<DOT_NONE, false, 1, 3, 270, 1>(ctx, args) ; break ;
-            case 51 : launch_s3_rt<DOT_NONE, false, 1, 3, 270, 2>(ctx, args) ; break ;
-            default : launch_spmv(ctx, c) ;
-            }
-        }
-        else
-            launch_spmv(ctx, c) ;
-    } ;
+    auto one = [&]() { launch_spmv_variant(ctx, c, variant, insolve) ; } ;
     one() ;                                                 // warm-up
     cudaEventRecord(ctx->ev_a, ctx->stream) ;
     for(int i = 0 ; i < reps ; i++) one() ;

@@ -31,27 +31,7 @@
 #include "krylov_scalars.cuh"
 #include "device_utils.cuh"
 
-enum { DOT_NONE = 0, DOT_YX = 1, DOT_YY = 2, DOT_YW = 3, DOT_OMEGA = 4 } ;
-
-struct SpmvArgs
-{
-    const uint32_t * rowptr ;
-    const uint32_t * col ;
-    const double * vals ;
-    const double * x ;
-    const double * b ;          // MINUS_B: y = sign*(A x - b)
-    double * y ;
-    const double * w ;          // DOT_YW: sum y.w ; DOT_OMEGA: s
-    const double * d ;          // DOT_OMEGA: inverse diagonal (NULL = identity)
-    uint32_t row0 ;             // first block row computed (rowstart / S)
-    uint32_t nrows ;            // block rows computed
-    uint32_t colstart_blk ;     // block columns < this are skipped (colstart / S)
-    double sign ;
-    KrylovState * st ;          // may be NULL (plain SpMV)
-    double * partials ;
-    int finalize ;              // FIN_* (krylov_scalars.cuh)
-    int check_stop ;
-} ;
+#include "spmv_args.h"
 
 // ---------------------------------------------------------------- stride 3 (27 active lanes of 32)
 template<int UMAX>

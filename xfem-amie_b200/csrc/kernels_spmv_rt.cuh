@@ -83,7 +83,7 @@ __device__ __forceinline__ void rt_blocks(uint32_t va, uint32_t xa, double & acc
     }
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1, bool ELECT = false>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NB = 9, int NP = 1>
 __global__ void __launch_bounds__((W+NP)*32) k_spmv_s3_rt(SpmvArgs a)
 {
     if(a.check_stop && a.st->stop) return ;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__((W+NP)*32) k_spmv_s3_rt(SpmvArgs a)
 
     if(wid >= W)
     {
-        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF, 4, 72, ELECT>(a, smem, full_v, empty, ntiles, lane, wid-W, NP) ;
+        tile_producer<R, NST, CAP, L::STAGE_BYTES, L::VAL_BYTES, L::META_OFF>(a, smem, full_v, empty, ntiles, lane, wid-W, NP) ;
     }
     else
     {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__((W+NP)*32) k_spmv_s3_rt(SpmvArgs a)
                 // full_v[s] of this phase also says the stage is FREE: the producer only refills it after the
                 // warp that computed its previous tile arrived on empty[s].  Nothing may be written into the
                 // stage (aux included) before this wait.
-                if(ELECT) mbar_wait_elect(full_v+s, (j/NST) & 1u, lane) ; else mbar_wait(full_v+s, (j/NST) & 1u) ;
+                mbar_wait(full_v+s, (j/NST) & 1u) ;
                 if(rl < (int)nr)
                 {
                     const size_t i = (size_t)(r0+rl)*3+r ;
