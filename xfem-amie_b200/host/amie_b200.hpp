@@ -46,6 +46,10 @@ struct NullPreconditionner : public Preconditionner { int kind() const override 
 struct InverseDiagonalSquared : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_DIAGONAL_SQUARED ; } } ;
 struct InverseLumpedDiagonal : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_LUMPED ; } } ;
 // a user-written preconditioner whose precondition(v, t) is t = v * d
+// node-block preconditioners, PCG only: solvers/inversediagonal.h:49-55 on stride-2 systems, and its 3x3 counterpart
+// (no reference class; opt-in, other iteration counts) on stride-3 systems -- built on the device from the matrix
+struct Inverse2x2Diagonal : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_BLOCK2X2 ; } } ;
+struct BlockJacobi3x3 : public Preconditionner { int kind() const override { return AMIE_B200_PRECOND_BLOCK3X3 ; } } ;
 struct DiagonalPreconditionner : public Preconditionner
 {
     Vector d ;
@@ -66,6 +70,13 @@ public:
     explicit Assembly(int device = 0)
     {
         ctx = amie_b200_create(&device, 1) ;
+        if(!ctx) throw std::runtime_error(std::string("amie_b200: ")+amie_b200_global_error()+" (no CPU fallback)") ;
+    }
+    // ONE context over several GPUs (block rows partitioned inside the library; the same calls with the same global
+    // arrays).  Needs CUDA_MODULE_LOADING=EAGER in the environment before CUDA initialises (see include/amie_b200.h).
+    Assembly(const int * devices, int ndev)
+    {
+        ctx = amie_b200_create(devices, ndev) ;
         if(!ctx) throw std::runtime_error(std::string("amie_b200: ")+amie_b200_global_error()+" (no CPU fallback)") ;
     }
     ~Assembly() { amie_b200_destroy(ctx) ; }
