@@ -43,18 +43,23 @@ def test_featuretree_step_with_dropin_solvers(tmp_path, mode, sampling):
     for a, b in zip(cg_ref, cg_gpu):
         assert abs(a - b) <= 2, (cg_ref, cg_gpu)
     assert u_ref.size == u_gpu.size and u_ref.size > 1000
-    # The 3D S1 system has a handful of DOFs (6 nodes at sampling 500) that the Krylov iteration does not pin
-    # down: the UNMODIFIED reference returns different values for exactly these DOFs when only its OpenMP thread
-    # count changes (rel-L2 7e-3 between 1 and 8 threads; tools/ notes in profiles/r01_notes.md), i.e. they
-    # react to last-bit rounding of the dot products.  They are excluded (and counted) here; every other DOF
-    # must agree to 1e-8.
+    # The 3D S1 system has a handful of DOFs that the Krylov iteration does not pin down: the UNMODIFIED reference
+    # returns different values for exactly these DOFs when only its OpenMP thread count changes (rel-L2 7e-3 to 9e-3
+    # between 1 thread and 2, 3 or 8 threads; none with 4), i.e. they react to last-bit rounding of the dot products.
+    # The set is PINNED: tests/golden/e2e-3d-500-rounding-sensitive-dofs.npy = the 27 DOFs (9 nodes) on which the
+    # reference differs from its own 1-thread run at 2 / 3 / 4 / 8 threads (generated in the build container with
+    # oracle/_ref/amie_e2e_ref).  Every DOF outside it must agree to 1e-8; nothing outside it may be loose.
     d = np.abs(u_gpu - u_ref)
     loose = d > 1e-7 * np.abs(u_ref).max()
+    pinned = np.zeros(u_ref.size, bool)
+    if mode == "3d":
+        pinned[np.load(os.path.join(ROOT, "tests", "golden", "e2e-3d-500-rounding-sensitive-dofs.npy"))] = True
     err_all = rel_l2(u_gpu, u_ref)
-    err = rel_l2(u_gpu[~loose], u_ref[~loose])
+    err = rel_l2(u_gpu[~pinned], u_ref[~pinned])
     print(f"e2e {mode}-{sampling}: {u_ref.size} DOF, CG {cg_ref} vs {cg_gpu}, BiCGStab {bi_ref} vs {bi_gpu}, "
-          f"rel-L2 {err:.3e} on {int((~loose).sum())} DOF ({int(loose.sum())} rounding-sensitive DOF excluded, rel-L2 with them {err_all:.3e})")
-    assert loose.sum() <= (0 if mode == "2d" else 24), np.flatnonzero(loose)
+          f"rel-L2 {err:.3e} on {int((~pinned).sum())} DOF ({int(pinned.sum())} pinned rounding-sensitive DOF set aside, "
+          f"{int(loose.sum())} of them loose in this run, rel-L2 with them {err_all:.3e})")
+    assert not (loose & ~pinned).any(), np.flatnonzero(loose & ~pinned)
     assert err <= 1e-8, err
 
 

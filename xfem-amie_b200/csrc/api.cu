@@ -239,6 +239,10 @@ amie_b200_ctx * amie_b200_create(const int * devices, int ndev)
     amie_b200_ctx * ctx = new amie_b200_ctx ;
     ctx->device = dev ;
     ctx->num_sms = prop.multiProcessorCount ;
+    // from here on a failure releases what was created so far (amie_b200_destroy tolerates null members)
+#undef G_TRY
+#define G_TRY(expr) do { cudaError_t _e = (expr) ; if(_e != cudaSuccess) { \
+        g_error = std::string(#expr) + ": " + cudaGetErrorString(_e) ; amie_b200_destroy(ctx) ; cudaGetLastError() ; return nullptr ; } } while(0)
     G_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) ;
     G_TRY(cudaMalloc(&ctx->st, sizeof(KrylovState))) ;
     G_TRY(cudaMemset(ctx->st, 0, sizeof(KrylovState))) ;
@@ -258,7 +262,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     if(!ctx) return ;
     if(ctx->group) { group_destroy(ctx) ; return ; }
     cudaSetDevice(ctx->device) ;
-    cudaStreamSynchronize(ctx->stream) ;
+    if(ctx->stream) cudaStreamSynchronize(ctx->stream) ;
     dist_destroy(ctx) ;
     if(ctx->graph_cg.exec) cudaGraphExecDestroy(ctx->graph_cg.exec) ;
     if(ctx->graph_bicg.exec) cudaGraphExecDestroy(ctx->graph_bicg.exec) ;
@@ -272,7 +276,7 @@ void amie_b200_destroy(amie_b200_ctx * ctx)
     if(ctx->ev_a) cudaEventDestroy(ctx->ev_a) ;
     if(ctx->ev_b) cudaEventDestroy(ctx->ev_b) ;
     for(int i = 0 ; i < 2 ; i++) if(ctx->ev_poll[i]) cudaEventDestroy(ctx->ev_poll[i]) ;
-    cudaStreamDestroy(ctx->stream) ;
+    if(ctx->stream) cudaStreamDestroy(ctx->stream) ;
     delete ctx ;
 }
 

@@ -130,7 +130,9 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
         double a = 0., c = 0. ;
         for(uint32_t p = p0 ; p < p1 ; p++, v += SS)
         {
-            const double y = __dsub_rn(ld_stream(v), c) ;
+            // plain cached load: the 72-byte pieces of a run share sectors from one step to the next, and with the
+            // neighbouring stored blocks of the warp -- L1 serves the second touch
+            const double y = __dsub_rn(__ldg(v), c) ;
             const double t = __dadd_rn(a, y) ;
             c = __dsub_rn(__dsub_rn(t, a), y) ;
             a = t ;
