@@ -18,6 +18,14 @@
 //                                                   driver's loop (:115-130), every step re-solving on ONE topology while damage
 //                                                   changes the values (BASELINE.json config 4).  out.bin then holds one record
 //                                                   per load step.
+//   amie_e2e_* asr <sampling> <out.bin> [dump.bin [zones [zone_radius]]]
+//                                                   examples/main_3d_asr.cpp:402-426 with n = 1 (one aggregate in a paste cube,
+//                                                   BASELINE.json config 5) and its gel pockets as ExpansiveZone3D features
+//                                                   (features/expansiveZone3d.cpp:38-125): XFEM enrichment of the tetrahedra a
+//                                                   pocket's surface cuts -- extra unknowns on their nodes, hence block rows of
+//                                                   irregular length behind the regular ones.  Elastic phases (the example's
+//                                                   moduli), pockets at fixed positions inside the aggregate, grown to a radius
+//                                                   the mesh resolves (the example grows them step by step from 1e-3).
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -39,6 +47,9 @@
 #include "features/sample.h"
 #include "features/sample3d.h"
 #include "features/inclusion3d.h"
+#include "features/expansiveZone3d.h"
+#include "features/expansiveZone.h"
+#include "features/inclusion.h"
 #include "physics/stiffness.h"
 #include "physics/stiffness_with_imposed_deformation.h"
 #include "physics/stiffness_and_fracture.h"
@@ -349,6 +360,78 @@ int main(int argc, char ** argv)
             fprintf(stderr, "tripoint: load step %zu converged %d unknowns %zu average damage %g\n", v, (int)go_on,
                     (size_t)F.getDisplacements(-1, false).size(), F.averageDamage) ;
         }
+    }
+    else if(mode == "asr")
+    {
+        const double scale = 100. ;
+        const double size = 0.15*scale, half = size/2 ;
+        const int nzones = argc > 5 ? atoi(argv[5]) : 6 ;
+        const double rz = argc > 6 ? atof(argv[6]) : 1.4 ;
+        Sample3D sample(nullptr, size, size, size, half, half, half) ;
+        FeatureTree F(&sample, 1, -1, 20) ;
+        sample.setBehaviour(new Stiffness(Tensor::cauchyGreen(12e9, 0.3, SPACE_THREE_DIMENSIONAL, PLANE_STRESS, YOUNG_POISSON))) ;
+        Inclusion3D * agg = new Inclusion3D(0.0623*scale, half, half, half) ;
+        agg->setBehaviour(new Stiffness(Tensor::cauchyGreen(59e9, 0.3, SPACE_THREE_DIMENSIONAL, PLANE_STRESS, YOUNG_POISSON))) ;
+        F.addFeature(&sample, agg) ;
+        const Matrix gel = Tensor::cauchyGreen(22e9, 0.3, SPACE_THREE_DIMENSIONAL, PLANE_STRESS, YOUNG_POISSON) ;
+        Vector swelling(0., 6) ;
+        swelling[0] = swelling[1] = swelling[2] = 0.05 ;
+        F.setSamplingNumber(sampling) ;
+        F.setMaxIterationsPerStep(2) ;
+        F.setOrder(LINEAR) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, LEFT)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ZETA, BACK)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(SET_STRESS_XI, RIGHT, 1e6)) ;
+        // a first step meshes the sample: features without mesh points of their own are dropped from the tree when the
+        // features are sampled (features/features.cpp:1811, :2561-2580), so the pockets join the meshed tree afterwards
+        // -- which is also when the example's pockets reach a size that cuts elements
+        F.step() ;
+        // pockets on a fixed pattern around the aggregate's centre, well inside it and apart from one another
+        static const double dir[8][3] = { {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {.6, .6, .5}, {-.6, -.5, -.6} } ;
+        for(int z = 0 ; z < nzones && z < 8 ; z++)
+        {
+            const double d = 3.4 ;
+            ExpansiveZone3D * pocket = new ExpansiveZone3D(nullptr, rz, half+d*dir[z][0], half+d*dir[z][1], half+d*dir[z][2], gel, swelling) ;
+            F.addFeature(agg, pocket) ;
+        }
+        F.step() ;
+        write_vec(argv[3], F.getDisplacements()) ;
+        if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
+    }
+    else if(mode == "asr2d")
+    {
+        // the 2D member of the same family (examples/main_asr_simple.cpp:641-704, examples/main_asr.cpp): an aggregate in a
+        // paste square with gel pockets as ExpansiveZone features (features/expansiveZone.cpp) -- XFEM enrichment of the
+        // triangles a pocket's rim cuts; elastic phases, pockets on a fixed pattern
+        const int nzones = argc > 5 ? atoi(argv[5]) : 6 ;
+        const double rz = argc > 6 ? atof(argv[6]) : 0.0016 ;
+        RectangularFeature sample(0.04, 0.04, 0., 0.) ;
+        sample.setBehaviour(new Stiffness(12e9, 0.3)) ;
+        FeatureTree F(&sample) ;
+        Inclusion * agg = new Inclusion(0.012, 0., 0.) ;
+        agg->setBehaviour(new Stiffness(59e9, 0.3)) ;
+        F.addFeature(&sample, agg) ;
+        const Matrix gel = Stiffness(22e9, 0.3).param ;
+        Vector swelling(0., 3) ;
+        swelling[0] = swelling[1] = 0.05 ;
+        F.setSamplingNumber(sampling) ;
+        F.setOrder(LINEAR) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, LEFT)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(SET_STRESS_XI, RIGHT, -5e6)) ;
+        const bool after = argc > 7 && atoi(argv[7]) ;
+        if(after) F.step() ;
+        static const double dir[8][2] = { {1, 0}, {-1, 0}, {0, 1}, {0, -1}, {.7, .7}, {-.7, .7}, {.7, -.7}, {-.7, -.7} } ;
+        for(int z = 0 ; z < nzones && z < 8 ; z++)
+        {
+            const double d = 0.0062 ;
+            ExpansiveZone * pocket = new ExpansiveZone(nullptr, rz, d*dir[z][0], d*dir[z][1], gel, swelling) ;
+            F.addFeature(agg, pocket) ;
+        }
+        F.step() ;
+        write_vec(argv[3], F.getDisplacements()) ;
+        if(argc > 4) dump_system(argv[4], F.getAssembly(false)) ;
     }
     else if(mode == "2d")
     {

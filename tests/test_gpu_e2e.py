@@ -109,12 +109,12 @@ def test_tripoint_damage_resolves_through_the_dropin(tmp_path):
     """BASELINE.json config 4: examples/main_tripoint.cpp (`24 0 3.9 1.2`, 8 994 unknowns): load steps on ONE topology,
     the damage iterations re-assembling the values and re-solving again and again.  The same unmodified FeatureTree
     driver with the reference solvers and with the drop-in translation units: the elastic load steps must give the
-    same displacement field (1e-8), and the CG iteration counts of the first 60 solver calls -- damage iterations included, where
+    same displacement field (1e-8), and the CG iteration counts of the first 48 solver calls -- damage iterations included, where
     every solution feeds the next matrix -- must agree within +-2."""
     if not (os.path.exists(REF) and os.path.exists(B200)):
         pytest.skip("oracle/_ref e2e binaries not prebuilt (no /root/reference at build time)")
     args = ["tripoint", "24", "@OUT", "6", "900", "4e-5"]
-    K = 60
+    K = 48
     u_ref, cg_ref, bi_ref, _ = run_until(REF, args, str(tmp_path), K, 600)
     u_gpu, cg_gpu, bi_gpu, log = run_until(B200, args, str(tmp_path), K, 600, {"AMIE_B200_SHIM_TRACE": "1"})
     assert "amie_b200: set_" not in log and "no CPU fallback" not in log, log[-1500:]
@@ -123,7 +123,7 @@ def test_tripoint_damage_resolves_through_the_dropin(tmp_path):
     n = min(len(cg_ref), len(cg_gpu))
     print(f"tripoint: {len(u_ref)} / {len(u_gpu)} load steps written, {len(cg_ref)} / {len(cg_gpu)} CG solves, "
           f"first counts {cg_ref[:8]} vs {cg_gpu[:8]}, last {cg_ref[n - 4:n]} vs {cg_gpu[n - 4:n]}")
-    assert n >= 30, (len(cg_ref), len(cg_gpu))           # 2 CG + 1 BiCGStab line per solve triple
+    assert n >= 24, (len(cg_ref), len(cg_gpu))           # 2 CG + 1 BiCGStab line per solve triple
     assert len(u_ref) >= 3 and len(u_gpu) >= 3
     worst = max(abs(a - b) for a, b in zip(cg_ref[:n], cg_gpu[:n]))
     assert worst <= 2, [(i, a, b) for i, (a, b) in enumerate(zip(cg_ref[:n], cg_gpu[:n])) if abs(a - b) > 2][:5]

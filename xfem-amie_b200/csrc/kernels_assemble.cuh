@@ -119,25 +119,58 @@ static __global__ void k_assemble_gather(const uint32_t * __restrict__ cptr, con
                                          unsigned char * __restrict__ dirty, int all,
                                          double * __restrict__ vals, uint64_t nent)
 {
+    // ncu on the first form of this kernel (profiles/r02_ncu_assemble_gather.txt): DRAM traffic = the algorithmic bytes,
+    // 97 % occupancy, and every stall a long_scoreboard -- two DEPENDENT latencies per entry (run offsets, then the
+    // run).  So the offsets of the NEXT entry of the grid-stride loop are fetched while the current run is summed, and
+    // the run is read two contributions at a time before the (sequential, order-preserving) compensated additions.
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
-    for(uint64_t idx = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; idx < nent ; idx += stride)
+    uint64_t idx = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ;
+    if(idx >= nent) return ;
+    uint64_t d = idx/SS ;
+    uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
+    bool todo = all || dirty[d] ;
+    for( ; idx < nent ; )
     {
-        const uint64_t d = idx/SS ;
-        const uint32_t ent = (uint32_t)(idx-d*SS) ;
-        if(!all && !dirty[d]) continue ;
-        const uint32_t p0 = __ldg(cptr+d), p1 = __ldg(cptr+d+1) ;
-        const double * v = placed+(uint64_t)p0*SS+ent ;
-        double a = 0., c = 0. ;
-        for(uint32_t p = p0 ; p < p1 ; p++, v += SS)
+        const uint64_t nidx = idx+stride ;
+        uint64_t nd = 0 ;
+        uint32_t np0 = 0, np1 = 0 ;
+        bool ntodo = false ;
+        if(nidx < nent)
         {
-            // plain cached load: the 72-byte pieces of a run share sectors from one step to the next, and with the
-            // neighbouring stored blocks of the warp -- L1 serves the second touch
-            const double y = __dsub_rn(__ldg(v), c) ;
-            const double t = __dadd_rn(a, y) ;
-            c = __dsub_rn(__dsub_rn(t, a), y) ;
-            a = t ;
+            nd = nidx/SS ;
+            np0 = __ldg(cptr+nd) ; np1 = __ldg(cptr+nd+1) ;
+            ntodo = all || dirty[nd] ;
         }
-        vals[idx] = a ;
+        if(todo)
+        {
+            const uint32_t ent = (uint32_t)(idx-d*SS) ;
+            const double * v = placed+(uint64_t)p0*SS+ent ;
+            double a = 0., c = 0. ;
+            uint32_t p = p0 ;
+            for( ; p+2 <= p1 ; p += 2, v += 2*SS)
+            {
+                // plain cached loads: the 72-byte pieces of a run share sectors from one step to the next, and with
+                // the neighbouring stored blocks of the warp -- L1 serves the second touch
+                const double v0 = __ldg(v), v1 = __ldg(v+SS) ;
+                double y = __dsub_rn(v0, c) ;
+                double t = __dadd_rn(a, y) ;
+                c = __dsub_rn(__dsub_rn(t, a), y) ;
+                a = t ;
+                y = __dsub_rn(v1, c) ;
+                t = __dadd_rn(a, y) ;
+                c = __dsub_rn(__dsub_rn(t, a), y) ;
+                a = t ;
+            }
+            if(p < p1)
+            {
+                const double y = __dsub_rn(__ldg(v), c) ;
+                const double t = __dadd_rn(a, y) ;
+                c = __dsub_rn(__dsub_rn(t, a), y) ;
+                a = t ;
+            }
+            vals[idx] = a ;
+        }
+        idx = nidx ; d = nd ; p0 = np0 ; p1 = np1 ; todo = ntodo ;
     }
 }
 

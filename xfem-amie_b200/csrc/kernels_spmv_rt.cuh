@@ -12,8 +12,8 @@
 //   warp W (producer): cp.async.bulk (1D TMA) of the tile's values + column indices -> full_v[s]
 //   warps 0..W-1     : tile j of this CTA belongs to warp j % W.  G of its own tiles ahead, a warp
 //                      waits full_v of that future tile and issues 8-byte cp.async gathers
-//                      x[3 col .. 3 col + 2] -> xs[stage] for every block (lane <-> block), plus the
-//                      own-row entries of b / x / w / d it will need at the end (aux[stage]).
+//                      x[3 col .. 3 col + 2] -> xs[stage] for every block (lane <-> element of xs), plus
+//                      the own-row entries of b / x / w / d it will need at the end (aux[stage]).
 //                      cp.async.wait_group<G> = "the gathers of the tile I compute now landed".
 //                      Compute: lane (row rl = lane/3, component r = lane%3) walks its row's blocks:
 //                      3 x (LDS value, LDS x, DFMA) per block; shared-memory reads are
@@ -29,7 +29,7 @@ struct RtLayout
 {
     static constexpr int VAL_BYTES = (CAP*72+16+15)/16*16 ;        // every region starts 16-byte aligned (TMA destinations)
     static constexpr int COL_BYTES = (CAP*4+16+15)/16*16 ;
-    static constexpr int XS_BYTES = (CAP*24+15)/16*16 ;
+    static constexpr int XS_BYTES = (CAP*24+15)/16*16 ;            // (>= 64 B: the gather's unpredicated index reads run up to 44 B past COL)
     static constexpr int AUX_BYTES = 4*32*8 ;                      // b, x, w, d of the tile's 30 scalar rows
     static constexpr int META_BYTES = 64 ;                         // 11 row pointers + 3 words
     static constexpr int STAGE_BYTES = (VAL_BYTES+COL_BYTES+XS_BYTES+AUX_BYTES+META_BYTES+127)/128*128 ;
@@ -149,25 +149,36 @@ __global__ void __launch_bounds__((W+NP)*32) k_spmv_s3_rt(SpmvArgs a)
                     const uint32_t * cs = reinterpret_cast<const uint32_t *>(stage+L::VAL_BYTES+meta[R+2]) ;
                     double * xs = reinterpret_cast<double *>(stage+L::VAL_BYTES+L::COL_BYTES) ;
                     const uint32_t nblk = meta[nr]-meta[0] ;
-                    // two phases, fully unrolled (a stage holds at most CAP blocks): all column-index reads
-                    // first, then the copies, so the LDS latency is paid once per tile and not once per block
-                    constexpr int GI = (CAP+31)/32 ;
-                    uint32_t cidx[GI] ;
+                    // lane <-> ELEMENT of the stage's x array (xs[e] = x[3 col(e/3) + e%3], e = lane + 32 g): the 32
+                    // copies of one LDGSTS land in 256 contiguous bytes of shared memory and read ~4 global lines
+                    // (a row's columns come in runs), where lane <-> block (three copies per lane, 24-byte stride)
+                    // touched ~11 lines per instruction and cost 10.9 shared-memory wavefronts each: 303 of the
+                    // kernel's 754 wavefronts per tile (ncu source page of the round-2 in-solve capture,
+                    // profiles/r02_notes.md section 8).  Column-index reads first, then the copies.
+                    constexpr int GE = (3*CAP+31)/32 ;
+                    const uint32_t nel = nblk*3u ;
+                    const uint32_t q0 = (uint32_t)lane/3u, q1 = ((uint32_t)lane+1u)/3u, q2 = ((uint32_t)lane+2u)/3u ;
+                    const uint32_t c0 = (uint32_t)lane-3u*q0, c1 = (uint32_t)lane+1u-3u*q1, c2 = (uint32_t)lane+2u-3u*q2 ;
+                    // index reads are NOT predicated: past the tile's last block they return whatever follows in the
+                    // stage (the region is followed by xs; RtLayout keeps (32 GE)/3 indices inside the stage) and
+                    // the value is only used under the copy's own predicate
+                    const uint32_t * cs0 = cs+q0, * cs1 = cs+q1, * cs2 = cs+q2 ;
+                    uint32_t cidx[GE] ;
                     #pragma unroll
-                    for(int g = 0 ; g < GI ; g++)
-                        cidx[g] = (lane+32u*g < nblk) ? cs[lane+32u*g] : 0u ;
-                    #pragma unroll
-                    for(int g = 0 ; g < GI ; g++)
+                    for(int g = 0 ; g < GE ; g++)
                     {
-                        const uint32_t bk = lane+32u*g ;
-                        if(bk < nblk)
-                        {
-                            const double * px = a.x+(size_t)cidx[g]*3 ;
-                            double * d = xs+(size_t)bk*3 ;
-                            cp_async_8(d, px) ;
-                            cp_async_8(d+1, px+1) ;
-                            cp_async_8(d+2, px+2) ;
-                        }
+                        const uint32_t m = (32u*g)%3u ;
+                        cidx[g] = (m == 0u ? cs0 : (m == 1u ? cs1 : cs2))[(32u*g)/3u] ;
+                    }
+                    // 3 col + c < 2^32: a block column index beyond 1.4e9 would need terabytes of matrix
+                    double * xl = xs+lane ;
+                    const int left = (int)nel-lane ;       // lane + 32 g < nel  <=>  32 g < left
+                    #pragma unroll
+                    for(int g = 0 ; g < GE ; g++)
+                    {
+                        const uint32_t m = (32u*g)%3u ;
+                        const uint32_t c = m == 0u ? c0 : (m == 1u ? c1 : c2) ;
+                        if(32*g < left) cp_async_8(xl+32*g, a.x+(cidx[g]*3u+c)) ;
                     }
                 }
             }
