@@ -405,11 +405,11 @@ int main(int argc, char ** argv)
         // paste square with gel pockets as ExpansiveZone features (features/expansiveZone.cpp) -- XFEM enrichment of the
         // triangles a pocket's rim cuts; elastic phases, pockets on a fixed pattern
         const int nzones = argc > 5 ? atoi(argv[5]) : 6 ;
-        const double rz = argc > 6 ? atof(argv[6]) : 0.0016 ;
-        RectangularFeature sample(0.04, 0.04, 0., 0.) ;
+        const double rz = argc > 6 ? atof(argv[6]) : 0.008 ;
+        RectangularFeature sample(0.2, 0.2, 0., 0.) ;
         sample.setBehaviour(new Stiffness(12e9, 0.3)) ;
         FeatureTree F(&sample) ;
-        Inclusion * agg = new Inclusion(0.012, 0., 0.) ;
+        Inclusion * agg = new Inclusion(0.06, 0., 0.) ;
         agg->setBehaviour(new Stiffness(59e9, 0.3)) ;
         F.addFeature(&sample, agg) ;
         const Matrix gel = Stiffness(22e9, 0.3).param ;
@@ -425,7 +425,7 @@ int main(int argc, char ** argv)
         static const double dir[8][2] = { {1, 0}, {-1, 0}, {0, 1}, {0, -1}, {.7, .7}, {-.7, .7}, {.7, -.7}, {-.7, -.7} } ;
         for(int z = 0 ; z < nzones && z < 8 ; z++)
         {
-            const double d = 0.0062 ;
+            const double d = 0.031 ;
             ExpansiveZone * pocket = new ExpansiveZone(nullptr, rz, d*dir[z][0], d*dir[z][1], gel, swelling) ;
             F.addFeature(agg, pocket) ;
         }

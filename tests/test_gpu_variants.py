@@ -77,3 +77,42 @@ def test_renumbered_device_matrix_gives_the_same_solve(pkg, ol, name):
     cg.nssor = 32
     assert cg.solve() and rel_l2(cg.x, 0.5 * G["cg_x"]) <= 1e-8
     asm.close()
+
+
+def test_spmv_2x2_column_mapping_gives_the_same_bits(pkg, ol, systems):
+    """Option "spmv_variant" 5: the 2x2 pipeline with lane <-> (block row, COLUMN) -- one LDS.128 + one LDS.64 per block,
+    partial sums exchanged once per tile.  The per-column FMA chains and the final (col 0) + (col 1) sum are the row
+    mapping's, so y must be bit-identical: uniform T3 rows, the rowstart / colstart forms, and ragged rows (short tiles,
+    oversize tiles that read from global memory)."""
+    from test_gpu_parity import assembly_of
+    rng = np.random.default_rng(11)
+    S = systems("S2-tri", 40)
+    cases = [S]
+    nb = 500
+    rows = []
+    for r in range(nb):
+        k = int(rng.choice([1, 2, 5, 7, 7, 7, 9, 12, 30]))
+        rows.append(sorted(set(rng.integers(0, nb, k).tolist()) | {r}))
+    rs = np.array([len(c) for c in rows], np.uint32)
+    ci = np.array([c for row in rows for c in row], np.uint32)
+    cases.append(ol.Sys(2, nb, rs, ci, rng.standard_normal(ci.size * 4), rng.standard_normal(nb * 2)))
+    for T in cases:
+        asm = assembly_of(pkg, T)
+        v = rng.standard_normal(T.n)
+        out = {}
+        for variant in (3, 5):                      # 3 = the 2x2 pipeline with the row mapping, whatever the row lengths
+            asm.set_option("spmv_variant", variant)
+            cs = 2 * (T.nb // 3)
+            out[variant] = (asm.spmv(v), asm.spmv(v, minus_b=T.b), asm.spmv(v, rowstart=cs, colstart=cs))
+        for a, b in zip(out[3], out[5]):
+            assert np.array_equal(a, b)
+        yo = ol.oracle_assign(T, v, None, 0, 0)
+        assert np.abs(out[5][0] - yo).max() <= 1e-12 * np.abs(yo).max()
+        if T is S:
+            asm.set_option("spmv_variant", 5)
+            cg = pkg.ConjugateGradient(asm)
+            cg.nssor = 32
+            ok = cg.solve(None, None, 1e-10, -1)
+            ret, x_ref, info = ol.oracle_cg(T, nssor=32)
+            assert ok == bool(ret) and abs(int(cg.nit) - int(info.nit)) <= 2
+        asm.close()

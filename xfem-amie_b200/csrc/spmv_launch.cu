@@ -58,10 +58,10 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1, int CM = 0>
 static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP> ;
+    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP, CM> ;
     constexpr int smem = Rt2Layout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+NP)*32 ;
     static int cache[AMIE_MAX_DEVICES] = {} ;
@@ -107,6 +107,11 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
         // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long
         const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
         int G = avg > 24. ? 32 : (avg > 10. ? 16 : 8) ;
+        if(ctx->opt_variant == 5)
+        {
+            launch_s2_rt<DOT, MINUS_B, 8, 20, 144, 1, 4, 1>(ctx, args) ;      // A/B: column mapping
+            return ;
+        }
         if((ctx->opt_variant == 0 && avg <= 9.) || ctx->opt_variant == 3)
         {
             // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh).  A 16-row tile is only ~3.6 KB, so the
