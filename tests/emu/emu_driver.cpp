@@ -53,7 +53,30 @@ int emu_precond_diagonal(int kind, int stride, uint64_t nb, const uint32_t * row
 // set_elements + update_elements + assemble (assemble.cu).  vals (compact) is input and output: with all == 0 only the
 // stored blocks touched by elements [mark_first, mark_first+mark_count) are re-accumulated (k_mark_dirty), like an
 // incremental damage step.  Returns 0, 1 (node id out of range), 2 (pair outside the pattern).
+static int emu_assemble_pm(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb, PartMap pm,
+                 uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
+                 int all, uint64_t mark_first, uint64_t mark_count, double * vals) ;
+
 int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
+                 uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
+                 int all, uint64_t mark_first, uint64_t mark_count, double * vals)
+{
+    const PartMap pm = { 0u, (uint32_t)nb, nullptr, 0u, (uint32_t)nb } ;
+    return emu_assemble_pm(stride, nb, row_size, col, nnzb, pm, n_elem, npe, ids, ke, scales, all, mark_first, mark_count, vals) ;
+}
+
+// one part of a row-partitioned matrix (dist.cu numbering): nb local rows = global rows [row_base, row_base+nb), col holds
+// LOCAL block columns (owned, then nb + position in the sorted halo list); ids stay GLOBAL, every part sees every element
+int emu_assemble_part(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
+                      uint64_t row_base, const uint32_t * halo, uint64_t nhalo, uint64_t nb_global,
+                      uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
+                      int all, uint64_t mark_first, uint64_t mark_count, double * vals)
+{
+    const PartMap pm = { (uint32_t)row_base, (uint32_t)nb, halo, (uint32_t)nhalo, (uint32_t)nb_global } ;
+    return emu_assemble_pm(stride, nb, row_size, col, nnzb, pm, n_elem, npe, ids, ke, scales, all, mark_first, mark_count, vals) ;
+}
+
+static int emu_assemble_pm(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb, PartMap pm,
                  uint64_t n_elem, int npe, const uint32_t * ids, const double * ke, const double * scales,
                  int all, uint64_t mark_first, uint64_t mark_count, double * vals)
 {
@@ -62,7 +85,7 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
     const uint32_t pp = (uint32_t)(npe*npe) ;
     std::vector<uint32_t> dest(nsrc ? nsrc : 1), count(nnzb+1, 0), cptr(nnzb+1, 0) ;
     int flag = 0 ;
-    emu_launch(GRID, BLOCK, [&]() { k_map_dest(rp.data(), col, (uint32_t)nb, ids, nsrc, npe, dest.data(), count.data(), &flag) ; }) ;
+    emu_launch(GRID, BLOCK, [&]() { k_map_dest(rp.data(), col, pm, ids, nsrc, npe, dest.data(), count.data(), &flag) ; }) ;
     if(flag) return flag ;
     for(uint64_t k = 0 ; k < nnzb ; k++) cptr[k+1] = cptr[k]+count[k] ;          // cub::DeviceScan::ExclusiveSum
     std::vector<uint32_t> csrc(cptr[nnzb] ? cptr[nnzb] : 1) ;
@@ -104,17 +127,45 @@ int emu_assemble(int stride, uint64_t nb, const uint32_t * row_size, const uint3
 
 // set_boundary_conditions (assemble.cu): masks, then the row-owned elimination; dirty_out (nnzb, may be NULL) receives
 // the stored blocks the elimination touched
+static int emu_dirichlet_pm(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb, PartMap pm,
+                  double * vals, double * forces, double * natural, const double * add_to_forces,
+                  uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out) ;
+
 int emu_dirichlet(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
                   double * vals, double * forces, double * natural, const double * add_to_forces,
                   uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
                   uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
 {
+    const PartMap pm = { 0u, (uint32_t)nb, nullptr, 0u, (uint32_t)nb } ;
+    return emu_dirichlet_pm(stride, nb, row_size, col, nnzb, pm, vals, forces, natural, add_to_forces, nfix, fix_ids, fix_values,
+                            nforce, force_ids, force_values, dirty_out) ;
+}
+
+// one part (see emu_assemble_part): vals / forces / natural / add_to_forces are the part's LOCAL rows, the id lists GLOBAL
+int emu_dirichlet_part(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb,
+                       uint64_t row_base, const uint32_t * halo, uint64_t nhalo, uint64_t nb_global,
+                       double * vals, double * forces, double * natural, const double * add_to_forces,
+                       uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                       uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
+{
+    const PartMap pm = { (uint32_t)row_base, (uint32_t)nb, halo, (uint32_t)nhalo, (uint32_t)nb_global } ;
+    return emu_dirichlet_pm(stride, nb, row_size, col, nnzb, pm, vals, forces, natural, add_to_forces, nfix, fix_ids, fix_values,
+                            nforce, force_ids, force_values, dirty_out) ;
+}
+
+static int emu_dirichlet_pm(int stride, uint64_t nb, const uint32_t * row_size, const uint32_t * col, uint64_t nnzb, PartMap pm,
+                  double * vals, double * forces, double * natural, const double * add_to_forces,
+                  uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                  uint64_t nforce, const uint32_t * force_ids, const double * force_values, unsigned char * dirty_out)
+{
     std::vector<uint32_t> rp = rowptr_of(nb, row_size) ;
-    std::vector<unsigned char> fixmask(nb ? nb : 1, 0), forcemask(nb ? nb : 1, 0) ;
+    const uint64_t ncols = nb+pm.nhalo ;
+    std::vector<unsigned char> fixmask(ncols ? ncols : 1, 0), forcemask(ncols ? ncols : 1, 0) ;
     (void)nnzb ;
-    if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask(fix_ids, nfix, stride, fixmask.data()) ; }) ;
-    if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask(force_ids, nforce, stride, forcemask.data()) ; }) ;
-    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N>(rp.data(), col, nb, vals, forces, natural, add_to_forces,
+    if(nfix)   emu_launch(GRID, BLOCK, [&]() { k_bc_mask(fix_ids, nfix, stride, pm, fixmask.data()) ; }) ;
+    if(nforce) emu_launch(GRID, BLOCK, [&]() { k_bc_mask(force_ids, nforce, stride, pm, forcemask.data()) ; }) ;
+    BY_STRIDE(stride, emu_launch(GRID, BLOCK, [&]() { k_dirichlet<N>(rp.data(), col, nb, pm, vals, forces, natural, add_to_forces,
                                                                        fixmask.data(), fix_ids, fix_values, (uint32_t)nfix,
                                                                        forcemask.data(), force_ids, force_values, (uint32_t)nforce, dirty_out) ; }))
     return 0 ;

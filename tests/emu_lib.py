@@ -90,6 +90,55 @@ def assemble(stride, row_size, column_index, ids, ke, scales, vals=None, mark=No
     return rc, out
 
 
+def split_rows(row_size, column_index, parts):
+    """The numbering dist.cu gives each part of a row-partitioned matrix: rows [r0, r1) of the global structure, the
+    column indices renumbered IN PLACE (owned: c - r0, foreign: nb + position in the sorted halo list), so the blocks of a
+    row stay in global ascending order.  Returns [(r0, r1, k0, k1, row_size_local, col_local, halo)] for bounds `parts`."""
+    rs = np.ascontiguousarray(row_size, np.uint32)
+    ci = np.ascontiguousarray(column_index, np.uint32)
+    rp = np.concatenate([[0], np.cumsum(rs, dtype=np.int64)])
+    out = []
+    for r0, r1 in zip(parts[:-1], parts[1:]):
+        k0, k1 = int(rp[r0]), int(rp[r1])
+        c = ci[k0:k1].astype(np.int64)
+        own = (c >= r0) & (c < r1)
+        halo = np.unique(c[~own]).astype(np.uint32)
+        loc = np.where(own, c - r0, (r1 - r0) + np.searchsorted(halo, c)).astype(np.uint32)
+        out.append((int(r0), int(r1), k0, k1, rs[r0:r1].copy(), loc, halo))
+    return out
+
+
+def assemble_part(stride, part, nb_global, ids, ke, scales=None, vals=None, mark=None):
+    r0, r1, k0, k1, rs, loc, halo = part
+    ids = np.ascontiguousarray(ids, np.uint32)
+    ke = np.ascontiguousarray(ke, np.float64)
+    scales = None if scales is None else np.ascontiguousarray(scales, np.float64)
+    s = int(stride)
+    out = np.zeros(loc.size * s * s) if vals is None else np.array(vals, np.float64)
+    first, count = (0, 0) if mark is None else mark
+    rc = emu().emu_assemble_part(s, u64(rs.size), _vp(rs), _vp(loc), u64(loc.size), u64(r0), _vp(halo), u64(halo.size), u64(nb_global),
+                                 u64(ids.shape[0]), int(ids.shape[1]), _vp(ids), _vp(ke), _vp(scales),
+                                 1 if mark is None else 0, u64(first), u64(count), _vp(out))
+    return rc, out
+
+
+def dirichlet_part(stride, part, nb_global, vals_compact, forces, fix_ids, fix_values, force_ids=None, force_values=None,
+                   natural=None, add_to_forces=None):
+    r0, r1, k0, k1, rs, loc, halo = part
+    vals, forces = np.array(vals_compact, np.float64), np.array(forces, np.float64)
+    nat = None if natural is None else np.array(natural, np.float64)
+    add = None if add_to_forces is None else np.ascontiguousarray(add_to_forces, np.float64)
+    fi, fv = np.ascontiguousarray(fix_ids, np.uint32), np.ascontiguousarray(fix_values, np.float64)
+    gi = np.ascontiguousarray([] if force_ids is None else force_ids, np.uint32)
+    gv = np.ascontiguousarray([] if force_values is None else force_values, np.float64)
+    dirty = np.zeros(max(1, loc.size), np.uint8)
+    rc = emu().emu_dirichlet_part(int(stride), u64(rs.size), _vp(rs), _vp(loc), u64(loc.size), u64(r0), _vp(halo), u64(halo.size),
+                                  u64(nb_global), _vp(vals), _vp(forces), _vp(nat), _vp(add),
+                                  u64(fi.size), _vp(fi), _vp(fv), u64(gi.size), _vp(gi), _vp(gv), _vp(dirty))
+    assert rc == 0, rc
+    return vals, forces, nat, dirty[:loc.size]
+
+
 def dirichlet(stride, row_size, column_index, vals_compact, forces, fix_ids, fix_values, force_ids=None, force_values=None,
               natural=None, add_to_forces=None):
     rs = np.ascontiguousarray(row_size, np.uint32)

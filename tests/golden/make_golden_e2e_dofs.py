@@ -38,5 +38,6 @@ def main(sampling):
 
 
 if __name__ == "__main__":
-    for smp in ([int(a) for a in sys.argv[1:]] or [500, 1000]):
+    # (sampling 1000 has no closed set: the union keeps growing with every thread count -- tests/test_gpu_e2e.py)
+    for smp in ([int(a) for a in sys.argv[1:]] or [500]):
         main(smp)

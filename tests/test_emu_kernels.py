@@ -93,6 +93,66 @@ def test_assemble_and_eliminate_reproduce_the_featuretree_matrix(ol, name):
     assert dirty.any()
 
 
+@pytest.mark.parametrize("name,cuts", [("AMIE-2d-s20-assembly.npz", (0.5,)), ("AMIE-3d-s400-assembly.npz", (0.3, 0.55, 0.9))])
+def test_partitioned_assembly_and_elimination_reproduce_the_featuretree_matrix(ol, name, cuts):
+    """The same kernels on the parts of a row-partitioned matrix (the numbering of csrc/dist.cu: owned columns, then the
+    halo; a row's blocks still in global order): every part sees the whole element list and the global id lists of the
+    boundary conditions, builds its own gather map for the rows it owns, and the parts put together give the FeatureTree
+    matrix and force vector bit for bit."""
+    G = np.load(os.path.join(GOLDEN, name))
+    s, nb = int(G["stride"]), int(G["nb"])
+    el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
+    bounds = [0] + [int(c * nb) for c in cuts] + [nb]
+    parts = em.split_rows(G["row_size"], G["column_index"], bounds)
+    assert any(p[6].size for p in parts)
+    vals_all, forces_all, dirty_any = [], [], False
+    for part in parts:
+        r0, r1 = part[0], part[1]
+        rc, vals = em.assemble_part(s, part, nb, el.ids, el.ke, el.scales)
+        assert rc == 0
+        vals, forces, _, dirty = em.dirichlet_part(s, part, nb, vals, np.zeros((r1 - r0) * s), G["fix_ids"], G["fix_values"])
+        vals_all.append(vals)
+        forces_all.append(forces)
+        dirty_any |= bool(dirty.any())
+    assert same_bits(em.padded(np.concatenate(vals_all), s), G["array_post"])
+    if bool(G["forces_comparable"]):
+        assert same_bits(np.concatenate(forces_all), G["forces_post"])
+    assert dirty_any
+    # a node id beyond the GLOBAL matrix is an error on every part; a pair outside the pattern on the part that owns the row
+    bad = el.ids.copy()
+    bad[0, 0] = nb + 3
+    assert all(em.assemble_part(s, part, nb, bad, el.ke, el.scales)[0] == 1 for part in parts)
+
+
+@pytest.mark.parametrize("stride", [2, 3])
+def test_partitioned_dirichlet_kernel_matches_oracle(ol, stride):
+    """All of set_boundary_conditions on three parts: imposed displacements, imposed forces, the natural-condition vector
+    and the additional forces, ids global, vectors sliced."""
+    nb = 90
+    rs, ci, arr, b = random_spd_blocks(stride, nb, 900 + stride)
+    n = nb * stride
+    rng = np.random.default_rng(40 + stride)
+    vals = em.compact(arr, stride)
+    parts = em.split_rows(rs, ci, [0, 31, 58, nb])
+    for nfix in (1, n // 4, n):
+        fix = np.sort(rng.choice(n, nfix, replace=False)).astype(np.uint32)
+        fv = rng.standard_normal(nfix)
+        rest = np.setdiff1d(np.arange(n), fix)
+        frc = np.sort(rng.choice(rest, min(9, rest.size), replace=False)).astype(np.uint32)
+        frv = rng.standard_normal(frc.size)
+        nat, add = rng.standard_normal(n), rng.standard_normal(n)
+        a0, f0, n0, _ = ol.oracle_set_bcs(stride, nb, rs, ci, arr, b, fix, fv, frc, frv, nat, add)
+        got_v, got_f, got_n = [], [], []
+        for part in parts:
+            r0, r1, k0, k1 = part[:4]
+            sl = slice(r0 * stride, r1 * stride)
+            v1, f1, n1, _ = em.dirichlet_part(stride, part, nb, vals[k0 * stride * stride:k1 * stride * stride], b[sl], fix, fv, frc, frv,
+                                              nat[sl], add[sl])
+            got_v.append(v1) ; got_f.append(f1) ; got_n.append(n1)
+        assert same_bits(em.padded(np.concatenate(got_v), stride), a0), nfix
+        assert same_bits(np.concatenate(got_f), f0) and same_bits(np.concatenate(got_n), n0), nfix
+
+
 @pytest.mark.parametrize("stride", [1, 2, 3, 4, 6])
 def test_dirichlet_kernel_matches_oracle(ol, stride):
     nb = 70

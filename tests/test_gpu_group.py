@@ -189,12 +189,12 @@ def test_group_errors(pkg, systems):
         asm.upload_rhs(S.b)                 # before set_structure
     assert e.value.code == pkg.ERR_STATE
     asm.sync_matrix()
+    # the matrix comes back in the caller's numbering, whatever the parts number their columns like
+    rs, ci, arr, _ = asm.download_matrix()
+    assert np.array_equal(rs, S.row_size) and np.array_equal(ci, S.column_index) and np.array_equal(arr, S.array)
     with pytest.raises(pkg.AmieB200Error) as e:
-        asm.download_matrix()
-    assert e.value.code == pkg.ERR_UNSUPPORTED
-    with pytest.raises(pkg.AmieB200Error) as e:
-        asm.set_elements(np.zeros((1, 8), np.uint32))
-    assert e.value.code == pkg.ERR_UNSUPPORTED
+        asm.set_elements(np.full((1, 8), S.nb + 7, np.uint32))      # a node beyond the (global) matrix
+    assert e.value.code == pkg.ERR_ARG
     asm.close()
     # strides other than 2 and 3 stay on one device
     from conftest import random_spd_blocks
@@ -204,3 +204,105 @@ def test_group_errors(pkg, systems):
         a4.sync_matrix()
     assert e.value.code == pkg.ERR_UNSUPPORTED
     a4.close()
+
+
+@pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
+def test_group_assembly_and_elimination_reproduce_the_featuretree_matrix(pkg, ol, devices, name):
+    """SURVEY section 8 row f1 on a multi-device context: every device sees the whole element list (global node ids) and the
+    global id lists of the boundary conditions, and keeps what lands on the block rows it owns.  The parts put together
+    are the matrix and the force vector the unmodified FeatureTree solved, bit for bit; the solve that follows runs on
+    the device-assembled parts without a host matrix."""
+    import os
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", name)))
+    s, nb = int(G["stride"]), int(G["nb"])
+    el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
+    asm = pkg.Assembly(None, None, devices=devices)
+    asm.set_structure_only(s, G["row_size"], G["column_index"])
+    asm.set_elements(el.ids)
+    asm.update_elements(0, el.ke, el.scales)
+    asm.assemble()
+    assert np.array_equal(asm.download_matrix()[2], ol.oracle_assemble(s, nb, G["row_size"], G["column_index"], el))
+    asm.upload_rhs(np.zeros(nb * s))
+    asm.set_boundary_conditions(G["fix_ids"], G["fix_values"])
+    assert np.array_equal(asm.download_matrix()[2], G["array_post"])
+    if bool(G["forces_comparable"]):
+        assert np.array_equal(asm.download_rhs(), G["forces_post"])
+        S = ol.Sys(s, nb, G["row_size"], G["column_index"], G["array_post"], G["forces_post"])
+        ret, x_ref, info = ol.oracle_cg(S, nssor=32)
+        asm.upload_x0(None)
+        ok, nit, err, rho = asm.pcg_resident(nssor=32)
+        assert ok == bool(ret) and abs(int(nit) - int(info.nit)) <= NIT_TOL
+        assert rel_l2(asm.download_x(), x_ref) <= X_TOL
+    # a damage-like step: some elements change, only their stored blocks are re-accumulated -- on every device
+    rng = np.random.default_rng(4)
+    first, count = el.n_elem // 4, max(1, el.n_elem // 6)
+    el.ke[first:first + count] *= rng.uniform(0.1, 0.9, (count, 1, 1, 1))
+    asm.update_elements(first, el.ke[first:first + count], el.scales[first:first + count])
+    asm.assemble()
+    assert np.array_equal(asm.download_matrix()[2], ol.oracle_assemble(s, nb, G["row_size"], G["column_index"], el))
+    asm.close()
+
+
+@pytest.mark.parametrize("stride", [2, 3])
+def test_group_set_boundary_conditions_matches_oracle(pkg, ol, devices, stride):
+    """Imposed displacements, imposed forces, the natural-condition vector and the additional forces, all at once."""
+    from conftest import random_spd_blocks
+    nb = 90
+    rs, ci, arr, b = random_spd_blocks(stride, nb, 900 + stride)
+    n = nb * stride
+    rng = np.random.default_rng(40 + stride)
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(rs, ci, stride, arr), b, devices=devices)
+    for nfix in (1, n // 4, n):
+        fix = np.sort(rng.choice(n, nfix, replace=False)).astype(np.uint32)
+        fv = rng.standard_normal(nfix)
+        rest = np.setdiff1d(np.arange(n), fix)
+        frc = np.sort(rng.choice(rest, min(9, rest.size), replace=False)).astype(np.uint32)
+        frv = rng.standard_normal(frc.size)
+        nat, add = rng.standard_normal(n), rng.standard_normal(n)
+        a0, f0, n0, _ = ol.oracle_set_bcs(stride, nb, rs, ci, arr, b, fix, fv, frc, frv, nat, add)
+        asm.values_changed()
+        asm.sync_matrix()
+        asm.upload_rhs(b)
+        asm.set_boundary_conditions(fix, fv, frc, frv, add, nat)
+        assert np.array_equal(asm.download_matrix()[2], a0)
+        assert np.array_equal(asm.download_rhs(), f0)
+        assert np.array_equal(nat, n0)
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["AMIE-2d-s20-fields.npz", "AMIE-3di-s400-fields.npz"])
+def test_group_field_recovery_matches_reference_bits(pkg, ol, devices, name):
+    """SURVEY section 8 row f2 on a multi-device context: the ELEMENTS are split over the devices, each holds the whole
+    displacement field.  From a host field and from the resident solution of a solve (gathered from the parts over the
+    peer links): the bits ElementState::getField gave inside the FeatureTree run."""
+    import os
+    from test_gpu_recovery import same_bits
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    dim = int(g["dshape"].shape[2])
+    sysname = name.replace("-fields", "").replace("3di", "3d")
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", sysname))
+    s, nb = int(G["stride"]), int(G["nb"])
+    assert s == dim
+    asm = pkg.Assembly(pkg.CoordinateIndexedSparseMatrix(G["row_size"], G["column_index"], s, G["array"]), G["b"], devices=devices)
+    asm.sync_matrix()
+    asm.set_element_kinematics(dim, g["ids"], g["dshape"], g["jinv"])
+    asm.set_element_behaviour(g["tensors"], g["imposed_strain"], g["imposed_stress"], g["tensor_of_elem"])
+    tot, mech, sig = asm.element_fields(g["u"])
+    assert same_bits(tot, g["total_strain"]) and same_bits(mech, g["mechanical_strain"]) and same_bits(sig, g["real_stress"])
+    for field, key, dbl in ((0, "principal_total_strain", True), (2, "principal_real_stress", False)):
+        if key in g.files:
+            assert same_bits(asm.element_principal(field), g[key])
+    # one behaviour per element (cut like the elements), and the field taken from the devices after a solve
+    ne = g["ids"].shape[0]
+    C = g["tensors"][g["tensor_of_elem"]]
+    es, ss = g["imposed_strain"][g["tensor_of_elem"]], g["imposed_stress"][g["tensor_of_elem"]]
+    asm.set_element_behaviour(C, es, ss, None)
+    asm.upload_rhs(G["b"])
+    asm.upload_x0(None)
+    ok, nit, err, rho = asm.pcg_resident(nssor=32)
+    x = asm.download_x()
+    got = asm.element_fields(None)
+    want = ol.oracle_element_fields(dim, g["ids"], g["dshape"], g["jinv"], x, C, es, ss, None)
+    for a, b in zip(got, want):
+        assert same_bits(a, b)
+    asm.close()

@@ -80,7 +80,8 @@ def test_renumbered_device_matrix_gives_the_same_solve(pkg, ol, name):
 
 
 def test_spmv_2x2_column_mapping_gives_the_same_bits(pkg, ol, systems):
-    """Option "spmv_variant" 5: the 2x2 pipeline with lane <-> (block row, COLUMN) -- one LDS.128 + one LDS.64 per block,
+    """The 2x2 pipeline with lane <-> (block row, COLUMN) (the default; "spmv_variant" 5 forces it whatever the row
+    lengths, 4 is the row mapping it replaced) -- one LDS.128 + one LDS.64 per block,
     partial sums exchanged once per tile.  The per-column FMA chains and the final (col 0) + (col 1) sum are the row
     mapping's, so y must be bit-identical: uniform T3 rows, the rowstart / colstart forms, and ragged rows (short tiles,
     oversize tiles that read from global memory)."""
@@ -100,11 +101,11 @@ def test_spmv_2x2_column_mapping_gives_the_same_bits(pkg, ol, systems):
         asm = assembly_of(pkg, T)
         v = rng.standard_normal(T.n)
         out = {}
-        for variant in (3, 5):                      # 3 = the 2x2 pipeline with the row mapping, whatever the row lengths
+        for variant in (4, 5):                      # 4 = the 2x2 pipeline with the row mapping, 5 = with the column mapping
             asm.set_option("spmv_variant", variant)
             cs = 2 * (T.nb // 3)
             out[variant] = (asm.spmv(v), asm.spmv(v, minus_b=T.b), asm.spmv(v, rowstart=cs, colstart=cs))
-        for a, b in zip(out[3], out[5]):
+        for a, b in zip(out[4], out[5]):
             assert np.array_equal(a, b)
         yo = ol.oracle_assign(T, v, None, 0, 0)
         assert np.abs(out[5][0] - yo).max() <= 1e-12 * np.abs(yo).max()

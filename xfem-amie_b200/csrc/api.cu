@@ -22,7 +22,7 @@ void ctx_free_matrix(amie_b200_ctx * ctx)
     ctx->alloc_gen++ ;
     assembly_map_destroy(ctx) ;          // the gather lists index the stored blocks of this topology
     field_map_destroy(ctx) ;             // element data belongs to the topology too
-    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ; dfree(ctx->block_to) ;
+    dfree(ctx->rowptr) ; dfree(ctx->col) ; dfree(ctx->vals) ; dfree(ctx->dinv) ; dfree(ctx->user_diag) ; dfree(ctx->block_to) ; dfree(ctx->halo_glob) ;
     ctx->dinv_len = 0 ;
     ctx->have_structure = ctx->have_values = ctx->dinv_valid = false ;
 }
@@ -532,7 +532,7 @@ int amie_b200_download_vector(amie_b200_ctx * ctx, int which, double * out)
 int amie_b200_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out, double * array_padded_out)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
-    if(ctx->group) return group_unsupported(ctx, "download_matrix") ;
+    if(ctx->group) return group_download_matrix(ctx, row_size_out, column_index_out, array_padded_out) ;
     if(!ctx->have_structure) { ctx->set_error("download_matrix: no matrix") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     if(row_size_out)

@@ -21,6 +21,7 @@
 // Traffic: gather = element blocks once (8 s^2 B each) + 4 B of list offsets per stored block + the stored blocks
 // written once; elimination = column indices + a per-node mask byte, values only where a fixed dof is involved.
 #include "context.h"
+#include "group.h"
 #include "kernels_assemble.cuh"
 #include <algorithm>
 #include <vector>
@@ -82,11 +83,22 @@ uint64_t assembly_map_bytes(const amie_b200_ctx * ctx)
 
 // ---------------------------------------------------------------------------------------------------- API
 
-static int require_single(amie_b200_ctx * ctx, const char * what)
+static int require_structure(amie_b200_ctx * ctx, const char * what)
 {
-    if(ctx->dist || ctx->group) { ctx->set_error(std::string(what)+": not available on a row-partitioned / multi-device context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     if(!ctx->have_structure) { ctx->set_error(std::string(what)+" before set_structure") ; return AMIE_B200_ERR_STATE ; }
     return AMIE_B200_OK ;
+}
+
+// the numbering of the matrix this context holds (kernels_assemble.cuh): the whole matrix, or one part of a partitioned one
+static PartMap part_map(const amie_b200_ctx * ctx)
+{
+    PartMap pm ;
+    pm.row_base = (uint32_t)ctx->row_base ;
+    pm.nb = (uint32_t)ctx->nb ;
+    pm.halo = ctx->halo_glob ;
+    pm.nhalo = (uint32_t)(ctx->ncols_local > ctx->nb ? ctx->ncols_local-ctx->nb : 0) ;
+    pm.nb_global = (uint32_t)(ctx->nb_global ? ctx->nb_global : ctx->nb) ;
+    return pm ;
 }
 
 static bool ascending_unique(const uint32_t * ids, uint64_t n, uint64_t limit)
@@ -101,7 +113,8 @@ extern "C" {
 int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const uint32_t * elem_ids)
 {
     if(!ctx || npe < 1 || npe > 64 || (!elem_ids && n_elem)) return AMIE_B200_ERR_ARG ;
-    int rc = require_single(ctx, "set_elements") ;
+    if(ctx->group) return group_set_elements(ctx, n_elem, npe, elem_ids) ;
+    int rc = require_structure(ctx, "set_elements") ;
     if(rc) return rc ;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     assembly_map_destroy(ctx) ;
@@ -130,7 +143,7 @@ int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const 
     MAP_TRY(cudaMemsetAsync(count, 0, (nnzb+1)*sizeof(uint32_t), ctx->stream)) ;
     MAP_TRY(cudaMemsetAsync(ctx->flag, 0, sizeof(int), ctx->stream)) ;
     if(nsrc)
-        k_map_dest<<<vec_grid(ctx, nsrc), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, (uint32_t)ctx->nb, ids, nsrc, npe,
+        k_map_dest<<<vec_grid(ctx, nsrc), AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, part_map(ctx), ids, nsrc, npe,
                                                                              m->dest_of_src, count, ctx->flag) ;
     MAP_TRY(cudaMemcpyAsync(&bad, ctx->flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) ;
     MAP_TRY(cudaStreamSynchronize(ctx->stream)) ;
@@ -174,6 +187,7 @@ int amie_b200_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const 
 int amie_b200_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t count, const double * ke, const double * scales)
 {
     if(!ctx || (!ke && count)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_update_elements(ctx, first, count, ke, scales) ;
     AssemblyMap * m = ctx->amap ;
     if(!m || !m->built) { ctx->set_error("update_elements before set_elements") ; return AMIE_B200_ERR_STATE ; }
     if(first+count > m->n_elem) { ctx->set_error("update_elements: element range out of bounds") ; return AMIE_B200_ERR_ARG ; }
@@ -226,6 +240,7 @@ int amie_b200_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t coun
 int amie_b200_assemble(amie_b200_ctx * ctx)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_assemble(ctx) ;
     AssemblyMap * m = ctx->amap ;
     if(!m || !m->built || !m->have_ke) { ctx->set_error("assemble before set_elements + update_elements") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
@@ -265,23 +280,28 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
                                       const double * add_to_forces, double * natural_inout)
 {
     if(!ctx || (nfix && (!fix_ids || !fix_values)) || (nforce && (!force_ids || !force_values))) return AMIE_B200_ERR_ARG ;
-    int rc = require_single(ctx, "set_boundary_conditions") ;
+    if(ctx->group) return group_set_boundary_conditions(ctx, nfix, fix_ids, fix_values, nforce, force_ids, force_values, add_to_forces, natural_inout) ;
+    int rc = require_structure(ctx, "set_boundary_conditions") ;
     if(rc) return rc ;
     if(!ctx->have_values || !ctx->have_rhs)
     { ctx->set_error("set_boundary_conditions needs the matrix values (set_values / assemble) and the force vector (upload_rhs)") ; return AMIE_B200_ERR_STATE ; }
     if(ctx->S > 8) { ctx->set_error("set_boundary_conditions: stride > 8") ; return AMIE_B200_ERR_UNSUPPORTED ; }
-    if(!ascending_unique(fix_ids, nfix, ctx->N) || !ascending_unique(force_ids, nforce, ctx->N))
+    // the id lists are GLOBAL dof ids; on one part of a partitioned matrix add_to_forces / natural_inout are the part's rows
+    const PartMap pm = part_map(ctx) ;
+    const uint64_t n_global = (uint64_t)pm.nb_global*ctx->S ;
+    const uint64_t ncols = std::max<uint64_t>(ctx->ncols_local, ctx->nb) ;
+    if(!ascending_unique(fix_ids, nfix, n_global) || !ascending_unique(force_ids, nforce, n_global))
     { ctx->set_error("set_boundary_conditions: dof ids must be ascending, unique and < N (Assembly sorts its multipliers by id)") ; return AMIE_B200_ERR_ARG ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
     if(!ctx->amap) ctx->amap = new AssemblyMap ;              // only the mask scratch is used
     AssemblyMap * m = ctx->amap ;
-    if(m->mask_nb != ctx->nb)
+    if(m->mask_nb != ncols)
     {
         afree(m->fixmask) ; afree(m->forcemask) ;
         m->mask_nb = 0 ;
-        CUDA_TRY(ctx, cudaMalloc(&m->fixmask, std::max<uint64_t>(ctx->nb, 1))) ;
-        CUDA_TRY(ctx, cudaMalloc(&m->forcemask, std::max<uint64_t>(ctx->nb, 1))) ;
-        m->mask_nb = ctx->nb ;
+        CUDA_TRY(ctx, cudaMalloc(&m->fixmask, std::max<uint64_t>(ncols, 1))) ;
+        CUDA_TRY(ctx, cudaMalloc(&m->forcemask, std::max<uint64_t>(ncols, 1))) ;
+        m->mask_nb = ncols ;
     }
     uint32_t * d_ids = nullptr ;
     double * d_vals = nullptr, * d_add = nullptr, * d_nat = nullptr ;
@@ -295,15 +315,15 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     {
         BC_TRY(cudaMemcpyAsync(d_ids, fix_ids, nfix*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals, fix_values, nfix*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-        BC_TRY(cudaMemsetAsync(m->fixmask, 0, ctx->nb, ctx->stream)) ;
-        k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, m->fixmask) ;
+        BC_TRY(cudaMemsetAsync(m->fixmask, 0, ncols, ctx->stream)) ;
+        k_bc_mask<<<vec_grid(ctx, nfix), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids, nfix, ctx->S, pm, m->fixmask) ;
     }
     if(nforce)
     {
         BC_TRY(cudaMemcpyAsync(d_ids+nfix, force_ids, nforce*sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) ;
         BC_TRY(cudaMemcpyAsync(d_vals+nfix, force_values, nforce*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-        BC_TRY(cudaMemsetAsync(m->forcemask, 0, ctx->nb, ctx->stream)) ;
-        k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, m->forcemask) ;
+        BC_TRY(cudaMemsetAsync(m->forcemask, 0, ncols, ctx->stream)) ;
+        k_bc_mask<<<vec_grid(ctx, nforce), AMIE_VEC_THREADS, 0, ctx->stream>>>(d_ids+nfix, nforce, ctx->S, pm, m->forcemask) ;
     }
     if(add_to_forces)
     {
@@ -318,7 +338,7 @@ int amie_b200_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const 
     unsigned char * dirty = (m->built && !m->all_dirty) ? m->dirty : nullptr ;
     BC_TRY(cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     const int grid = vec_grid(ctx, ctx->N) ;
-#define DIRICHLET(N) k_dirichlet<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, ctx->vals, ctx->b, d_nat, d_add, \
+#define DIRICHLET(N) k_dirichlet<N><<<grid, AMIE_VEC_THREADS, 0, ctx->stream>>>(ctx->rowptr, ctx->col, ctx->nb, pm, ctx->vals, ctx->b, d_nat, d_add, \
         m->fixmask, d_ids, d_vals, (uint32_t)nfix, m->forcemask, d_ids+nfix, d_vals+nfix, (uint32_t)nforce, dirty)
     if(ctx->N)
         switch(ctx->S)

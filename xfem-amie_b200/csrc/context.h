@@ -26,6 +26,7 @@ struct amie_b200_ctx
     uint64_t nnzb = 0 ;
     uint64_t N = 0 ;           // local DOF
     uint64_t ncols_local = 0 ; // block columns addressable by local col indices (nb + halo)
+    uint32_t * halo_glob = nullptr ; // row-partitioned context: the sorted GLOBAL block columns of the halo (ncols_local - nb entries, device)
     uint32_t * rowptr = nullptr ;
     uint32_t * col = nullptr ;
     double * vals = nullptr ;

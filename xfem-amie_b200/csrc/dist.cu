@@ -730,6 +730,10 @@ static int dist_finish_structure(amie_b200_ctx * ctx)
     k_remap_cols<<<vec_grid(ctx, ctx->nnzb), 256, 0, st>>>(ctx->col, ctx->nnzb, r0, r1, tmp, (uint32_t)d->nhalo, nbl) ;
     CUDA_TRY(ctx, cudaStreamSynchronize(st)) ;
     CUDA_TRY(ctx, cudaGetLastError()) ;
+    // the halo list stays on the device: the value assembly and the elimination translate global node ids with it
+    if(ctx->halo_glob) { cudaFree(ctx->halo_glob) ; ctx->halo_glob = nullptr ; }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->halo_glob, std::max<uint64_t>(d->nhalo, 1)*sizeof(uint32_t))) ;
+    CUDA_TRY(ctx, cudaMemcpy(ctx->halo_glob, tmp, d->nhalo*sizeof(uint32_t), cudaMemcpyDeviceToDevice)) ;
     cudaFree(tmp) ;
 
     // ---- who owns which slice of the halo

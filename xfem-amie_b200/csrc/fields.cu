@@ -29,6 +29,7 @@
 // of the measured copy peak), 0.83 ms with per-element behaviours = 5.0 TB/s (77 %); DRAM traffic 2.08 / 4.39 GB
 // against 1.96 / 4.19 GB algorithmic; stalls are all long_scoreboard at 50 % occupancy (56 registers).
 #include "context.h"
+#include "group.h"
 #include "kernels_fields.cuh"
 #include <algorithm>
 #include <vector>
@@ -93,7 +94,9 @@ int amie_b200_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int n
                                      const double * dshape, const double * jinv)
 {
     if(!ctx || npe < 1 || npe > 64 || (n_elem && (!elem_ids || !dshape || !jinv))) return AMIE_B200_ERR_ARG ;
-    if(ctx->dist || ctx->group) { ctx->set_error("set_element_kinematics: not available on a row-partitioned / multi-device context yet") ; return AMIE_B200_ERR_UNSUPPORTED ; }
+    // A multi-device context splits the ELEMENTS into one contiguous range per device (group.cu); each device then holds
+    // a full-length copy of the displacement field, so element ids stay global and any element can be computed anywhere.
+    if(ctx->group) return group_set_element_kinematics(ctx, n_elem, npe, dim, elem_ids, dshape, jinv) ;
     if(!ctx->have_structure) { ctx->set_error("set_element_kinematics before set_structure") ; return AMIE_B200_ERR_STATE ; }
     if((dim != 2 && dim != 3) || dim != ctx->S)
     {
@@ -139,6 +142,7 @@ int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, con
                                     const uint32_t * tensor_of_elem)
 {
     if(!ctx || !n_tensors || !tensors) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_set_element_behaviour(ctx, n_tensors, tensors, imposed_strain, imposed_stress, tensor_of_elem) ;
     FieldMap * m = ctx->fmap ;
     if(!m) { ctx->set_error("set_element_behaviour before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
     if(!tensor_of_elem && n_tensors != m->n_elem)
@@ -176,28 +180,33 @@ int amie_b200_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, con
     return AMIE_B200_OK ;
 }
 
-int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u,
-                             double * total_strain_out, double * mechanical_strain_out, double * real_stress_out)
+}   // extern "C"
+
+// the device buffer a displacement field of n doubles is staged in (host-supplied fields; on a multi-device context the
+// resident solution gathered from every part)
+int fields_u_buffer(amie_b200_ctx * ctx, uint64_t n, double ** out)
 {
-    if(!ctx || (!u && n_u)) return AMIE_B200_ERR_ARG ;
+    FieldMap * m = ctx->fmap ;
+    if(!m) { ctx->set_error("element_fields before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    if(m->u_tmp_len < n)
+    {
+        ffree(m->u_tmp) ; m->u_tmp_len = 0 ;
+        CUDA_TRY(ctx, cudaMalloc(&m->u_tmp, std::max<uint64_t>(n, 1)*sizeof(double))) ;
+        m->u_tmp_len = n ;
+    }
+    *out = m->u_tmp ;
+    return AMIE_B200_OK ;
+}
+
+// du: the displacement field on this device, `len` doubles, indexed by the (global) node ids of the elements
+int fields_run(amie_b200_ctx * ctx, const double * du, uint64_t len, uint64_t h2d,
+               double * total_strain_out, double * mechanical_strain_out, double * real_stress_out)
+{
     FieldMap * m = ctx->fmap ;
     if(!m) { ctx->set_error("element_fields before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
     if(!m->have_behaviour) { ctx->set_error("element_fields before set_element_behaviour") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
-    const double * du = ctx->x ;        // the resident solution of the last solve
-    uint64_t len = ctx->N ;
-    uint64_t h2d = 0 ;
-    if(u)
-    {
-        if(m->u_tmp_len < n_u)
-        {
-            ffree(m->u_tmp) ; m->u_tmp_len = 0 ;
-            CUDA_TRY(ctx, cudaMalloc(&m->u_tmp, n_u*sizeof(double))) ;
-            m->u_tmp_len = n_u ;
-        }
-        CUDA_TRY(ctx, cudaMemcpyAsync(m->u_tmp, u, n_u*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
-        du = m->u_tmp ; len = n_u ; h2d = n_u*sizeof(double) ;
-    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream)) ;
     if(m->n_elem)
     {
@@ -234,9 +243,41 @@ int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u
     return AMIE_B200_OK ;
 }
 
+extern "C" {
+
+int amie_b200_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u,
+                             double * total_strain_out, double * mechanical_strain_out, double * real_stress_out)
+{
+    if(!ctx || (!u && n_u)) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_element_fields(ctx, u, n_u, total_strain_out, mechanical_strain_out, real_stress_out) ;
+    FieldMap * m = ctx->fmap ;
+    if(!m) { ctx->set_error("element_fields before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    if(!m->have_behaviour) { ctx->set_error("element_fields before set_element_behaviour") ; return AMIE_B200_ERR_STATE ; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    const double * du = ctx->x ;        // the resident solution of the last solve
+    uint64_t len = ctx->N ;
+    uint64_t h2d = 0 ;
+    if(u)
+    {
+        double * buf = nullptr ;
+        int rc = fields_u_buffer(ctx, n_u, &buf) ;
+        if(rc) return rc ;
+        CUDA_TRY(ctx, cudaMemcpyAsync(buf, u, n_u*sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) ;
+        du = buf ; len = n_u ; h2d = n_u*sizeof(double) ;
+    }
+    else if(ctx->dist)
+    {
+        // one rank of a partitioned matrix only holds its own rows of the solution; element ids are global
+        ctx->set_error("element_fields on one rank of a row-partitioned matrix: pass the displacement field (all rows)") ;
+        return AMIE_B200_ERR_UNSUPPORTED ;
+    }
+    return fields_run(ctx, du, len, h2d, total_strain_out, mechanical_strain_out, real_stress_out) ;
+}
+
 int amie_b200_element_principal(amie_b200_ctx * ctx, int field, double * principal_out)
 {
     if(!ctx || !principal_out || field < 0 || field > 2) return AMIE_B200_ERR_ARG ;
+    if(ctx->group) return group_element_principal(ctx, field, principal_out) ;
     FieldMap * m = ctx->fmap ;
     if(!m || !m->have_fields) { ctx->set_error("element_principal before element_fields") ; return AMIE_B200_ERR_STATE ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;

@@ -401,6 +401,9 @@ int group_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
             a.spmv_algorithmic_bytes += s.spmv_algorithmic_bytes ;
             a.device_bytes += s.device_bytes ;
             a.solve_ms = std::max(a.solve_ms, s.solve_ms) ;
+            a.assemble_ms = std::max(a.assemble_ms, s.assemble_ms) ; a.bc_ms = std::max(a.bc_ms, s.bc_ms) ;
+            a.fields_ms = std::max(a.fields_ms, s.fields_ms) ;
+            a.field_elements += s.field_elements ;
             a.h2d_ms = std::max(a.h2d_ms, s.h2d_ms) ; a.d2h_ms = std::max(a.d2h_ms, s.d2h_ms) ;
             // per-launch SpMV time: keep the slowest device's average (spmv_ms_total / spmv_timed)
             if(s.spmv_timed && a.spmv_timed && s.spmv_ms_total/s.spmv_timed > a.spmv_ms_total/a.spmv_timed)
@@ -409,6 +412,7 @@ int group_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out)
     }
     a.stride = ctx->S ; a.nb = ctx->nb ; a.nnzb = ctx->nnzb ; a.ndof = ctx->N ;
     a.structure_ms = ctx->stats.structure_ms ; a.values_ms = ctx->stats.values_ms ;
+    if(ctx->stats.elements_ms > 0.) a.elements_ms = ctx->stats.elements_ms ;
     *out = a ;
     return AMIE_B200_OK ;
 }
@@ -422,4 +426,177 @@ int group_set_option(amie_b200_ctx * ctx, const char * key, int64_t value)
         if(rc) { ctx->set_error(c->err) ; return rc ; }
     }
     return AMIE_B200_OK ;
+}
+
+// ------------------------------------------------------------------ the matrix back on the host (tests)
+
+int group_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out, double * array_padded_out)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("download_matrix: no matrix") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    const uint64_t per_block = (uint64_t)ctx->S*(ctx->S+ctx->S%2) ;
+    rc = g->run([&](int r) -> int
+    {
+        amie_b200_ctx * c = g->child[r] ;
+        uint32_t * ci = column_index_out ? column_index_out+g->blk_off[r] : nullptr ;
+        int e = amie_b200_download_matrix(c, row_size_out ? row_size_out+g->bounds[r] : nullptr, ci,
+                                          array_padded_out ? array_padded_out+g->blk_off[r]*per_block : nullptr) ;
+        if(e || !ci) return e ;
+        // the part's column indices are local (owned, then the halo): back to the caller's numbering
+        const uint64_t nhalo = c->ncols_local > c->nb ? c->ncols_local-c->nb : 0 ;
+        std::vector<uint32_t> halo(nhalo) ;
+        if(nhalo && cudaMemcpy(halo.data(), c->halo_glob, nhalo*sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        { c->set_error("download_matrix: halo list") ; return AMIE_B200_ERR_CUDA ; }
+        for(uint64_t k = 0 ; k < c->nnzb ; k++)
+            ci[k] = ci[k] < c->nb ? ci[k]+(uint32_t)c->row_base : halo[ci[k]-c->nb] ;
+        return AMIE_B200_OK ;
+    }) ;
+    return harvest(ctx, rc) ;
+}
+
+// ------------------------------------------------------------------ value assembly + elimination (assemble.cu per device)
+
+int group_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const uint32_t * elem_ids)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("set_elements before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    const double t0 = wall_now() ;
+    // the whole list on every device: the map build keeps what lands on the device's own block rows
+    rc = g->run([&](int r) -> int { return amie_b200_set_elements(g->child[r], n_elem, npe, elem_ids) ; }) ;
+    if(rc) return harvest(ctx, rc) ;
+    ctx->stats.elements_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
+}
+
+int group_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t count, const double * ke, const double * scales)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    // every device reads the same host range over its own PCIe link and places the blocks of its rows
+    rc = g->run([&](int r) -> int { return amie_b200_update_elements(g->child[r], first, count, ke, scales) ; }) ;
+    return harvest(ctx, rc) ;
+}
+
+int group_assemble(amie_b200_ctx * ctx)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    rc = g->run([&](int r) -> int { return amie_b200_assemble(g->child[r]) ; }) ;
+    if(rc) return harvest(ctx, rc) ;
+    ctx->have_values = true ;
+    return AMIE_B200_OK ;
+}
+
+int group_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                                  uint64_t nforce, const uint32_t * force_ids, const double * force_values,
+                                  const double * add_to_forces, double * natural_inout)
+{
+    if(!ctx->have_values || !ctx->have_rhs)
+    { ctx->set_error("set_boundary_conditions needs the matrix values (set_values / assemble) and the force vector (upload_rhs)") ; return AMIE_B200_ERR_STATE ; }
+    // the id lists are global and go to every device (a row also needs the imposed values of the foreign nodes it
+    // couples to); the vectors are cut into the devices' rows
+    return group_sliced(ctx, [&](amie_b200_ctx * c, uint64_t d0, uint64_t) -> int
+    {
+        return amie_b200_set_boundary_conditions(c, nfix, fix_ids, fix_values, nforce, force_ids, force_values,
+                                                 add_to_forces ? add_to_forces+d0 : nullptr, natural_inout ? natural_inout+d0 : nullptr) ;
+    }) ;
+}
+
+// ------------------------------------------------------------------ field recovery (fields.cu per device)
+
+int group_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int npe, int dim, const uint32_t * elem_ids,
+                                 const double * dshape, const double * jinv)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("set_element_kinematics before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    g->elem_bounds.assign(g->world+1, 0) ;
+    for(int r = 0 ; r <= g->world ; r++) g->elem_bounds[r] = n_elem*(uint64_t)r/(uint64_t)g->world ;
+    g->field_dim = dim ; g->field_nc = dim == 2 ? 3 : 6 ;
+    rc = g->run([&](int r) -> int
+    {
+        const uint64_t e0 = g->elem_bounds[r], ne = g->elem_bounds[r+1]-e0 ;
+        return amie_b200_set_element_kinematics(g->child[r], ne, npe, dim, elem_ids ? elem_ids+e0*npe : nullptr,
+                                                dshape ? dshape+e0*(uint64_t)npe*dim : nullptr, jinv ? jinv+e0*(uint64_t)dim*dim : nullptr) ;
+    }) ;
+    if(rc) { g->elem_bounds.clear() ; return harvest(ctx, rc) ; }
+    return AMIE_B200_OK ;
+}
+
+int group_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, const double * tensors, const double * imposed_strain,
+                                const double * imposed_stress, const uint32_t * tensor_of_elem)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    if(g->elem_bounds.empty()) { ctx->set_error("set_element_behaviour before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    const uint64_t nc = (uint64_t)g->field_nc ;
+    if(!tensor_of_elem && n_tensors != g->elem_bounds[g->world])
+    { ctx->set_error("set_element_behaviour: without tensor_of_elem there must be one behaviour per element") ; return AMIE_B200_ERR_ARG ; }
+    rc = g->run([&](int r) -> int
+    {
+        const uint64_t e0 = g->elem_bounds[r], ne = g->elem_bounds[r+1]-e0 ;
+        if(!ne) return AMIE_B200_OK ;
+        // a behaviour table is small and goes to every device whole; one behaviour per element is cut like the elements
+        if(tensor_of_elem) return amie_b200_set_element_behaviour(g->child[r], n_tensors, tensors, imposed_strain, imposed_stress, tensor_of_elem+e0) ;
+        return amie_b200_set_element_behaviour(g->child[r], ne, tensors+e0*nc*nc, imposed_strain ? imposed_strain+e0*nc : nullptr,
+                                               imposed_stress ? imposed_stress+e0*nc : nullptr, nullptr) ;
+    }) ;
+    return harvest(ctx, rc) ;
+}
+
+int group_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u, double * total_strain_out,
+                         double * mechanical_strain_out, double * real_stress_out)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    if(g->elem_bounds.empty()) { ctx->set_error("element_fields before set_element_kinematics") ; return AMIE_B200_ERR_STATE ; }
+    const uint64_t nc = (uint64_t)g->field_nc, S = (uint64_t)ctx->S ;
+    rc = g->run([&](int r) -> int
+    {
+        amie_b200_ctx * c = g->child[r] ;
+        const uint64_t e0 = g->elem_bounds[r] ;
+        if(g->elem_bounds[r+1] == e0) return AMIE_B200_OK ;
+        double * t = total_strain_out ? total_strain_out+e0*nc : nullptr ;
+        double * m = mechanical_strain_out ? mechanical_strain_out+e0*nc : nullptr ;
+        double * s = real_stress_out ? real_stress_out+e0*nc : nullptr ;
+        if(u) return amie_b200_element_fields(c, u, n_u, t, m, s) ;
+        // the resident solution: every part's rows, straight from the devices that hold them (peer copies), into this
+        // device's full-length buffer.  The solve that produced them has returned, so the parts' x are complete.
+        double * buf = nullptr ;
+        int e = fields_u_buffer(c, ctx->N, &buf) ;
+        if(e) return e ;
+        for(int q = 0 ; q < g->world ; q++)
+        {
+            const uint64_t d0 = g->bounds[q]*S, nd = (g->bounds[q+1]-g->bounds[q])*S ;
+            if(nd && cudaMemcpyAsync(buf+d0, g->child[q]->x, nd*sizeof(double), cudaMemcpyDefault, c->stream) != cudaSuccess)
+            { c->set_error(std::string("element_fields: gathering the solution: ")+cudaGetErrorString(cudaGetLastError())) ; return AMIE_B200_ERR_CUDA ; }
+        }
+        return fields_run(c, buf, ctx->N, 0, t, m, s) ;
+    }) ;
+    return harvest(ctx, rc) ;
+}
+
+int group_element_principal(amie_b200_ctx * ctx, int field, double * principal_out)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    LocalGroup * g = ctx->group ;
+    if(g->elem_bounds.empty()) { ctx->set_error("element_principal before element_fields") ; return AMIE_B200_ERR_STATE ; }
+    const uint64_t dim = (uint64_t)g->field_dim ;
+    rc = g->run([&](int r) -> int
+    {
+        const uint64_t e0 = g->elem_bounds[r] ;
+        if(g->elem_bounds[r+1] == e0) return AMIE_B200_OK ;
+        return amie_b200_element_principal(g->child[r], field, principal_out+e0*dim) ;
+    }) ;
+    return harvest(ctx, rc) ;
 }

@@ -24,6 +24,9 @@ struct LocalGroup
     std::vector<uint64_t> bounds ;            // block-row partition, world+1
     std::vector<uint64_t> blk_off ;           // stored blocks in front of each part, world+1
     bool broken = false ;                     // a collective was abandoned: the children are out of step for good
+    std::vector<uint64_t> elem_bounds ;       // field recovery: elements [elem_bounds[r], elem_bounds[r+1]) live on device r
+    int field_nc = 0, field_dim = 0 ;
+    bool field_shared_behaviours = false ;    // set_element_behaviour came with tensor_of_elem (one table on every device)
 
     // ---- exchange slots: rank r writes [r], barrier, everybody reads, barrier
     void * ptr[GROUP_MAX] = {} ;
@@ -73,6 +76,26 @@ int group_sliced(amie_b200_ctx * ctx, const std::function<int(amie_b200_ctx *, u
 int group_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 int group_set_option(amie_b200_ctx * ctx, const char * key, int64_t value) ;
 int group_unsupported(amie_b200_ctx * ctx, const char * what) ;
+int group_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out, double * array_padded_out) ;
+// the rows next to the solve.  Value assembly: every device sees the whole element list (global node ids) and keeps the
+// contributions to the block rows it owns.  Field recovery: the ELEMENTS are split, every device holds the whole field.
+int group_set_elements(amie_b200_ctx * ctx, uint64_t n_elem, int npe, const uint32_t * elem_ids) ;
+int group_update_elements(amie_b200_ctx * ctx, uint64_t first, uint64_t count, const double * ke, const double * scales) ;
+int group_assemble(amie_b200_ctx * ctx) ;
+int group_set_boundary_conditions(amie_b200_ctx * ctx, uint64_t nfix, const uint32_t * fix_ids, const double * fix_values,
+                                  uint64_t nforce, const uint32_t * force_ids, const double * force_values,
+                                  const double * add_to_forces, double * natural_inout) ;
+int group_set_element_kinematics(amie_b200_ctx * ctx, uint64_t n_elem, int npe, int dim, const uint32_t * elem_ids,
+                                 const double * dshape, const double * jinv) ;
+int group_set_element_behaviour(amie_b200_ctx * ctx, uint64_t n_tensors, const double * tensors, const double * imposed_strain,
+                                const double * imposed_stress, const uint32_t * tensor_of_elem) ;
+int group_element_fields(amie_b200_ctx * ctx, const double * u, uint64_t n_u, double * total_strain_out,
+                         double * mechanical_strain_out, double * real_stress_out) ;
+int group_element_principal(amie_b200_ctx * ctx, int field, double * principal_out) ;
+// fields.cu
+int fields_u_buffer(amie_b200_ctx * ctx, uint64_t n, double ** out) ;
+int fields_run(amie_b200_ctx * ctx, const double * du, uint64_t len, uint64_t h2d,
+               double * total_strain_out, double * mechanical_strain_out, double * real_stress_out) ;
 
 // dist.cu: make `ctx` rank `rank` of `g` (the in-process counterpart of amie_b200_dist_init)
 int dist_init_local(amie_b200_ctx * ctx, int rank, LocalGroup * g) ;

@@ -6,10 +6,43 @@
 #define NO_NODE 0xFFFFFFFFu
 #define NO_DEST 0xFFFFFFFFu
 
+// ---------------------------------------------------------------------------------------------------- numbering
+
+// The numbering of the matrix a context holds.  Single device: local == global ({0, nb, nullptr, 0}).  One part of a
+// row-partitioned matrix (dist.cu): local block rows [0, nb) are the global rows row_base .. row_base+nb, and the local
+// block column l >= nb is halo[l-nb] (the sorted global ids of the foreign columns the part's rows touch).  The blocks of
+// a row stay in GLOBAL ascending order in storage (dist.cu renumbers the column indices in place), which is the order
+// the reference walks them in -- so the kernels below search and walk rows through global_of().
+struct PartMap
+{
+    uint32_t row_base ;
+    uint32_t nb ;                 // owned block rows
+    const uint32_t * halo ;
+    uint32_t nhalo ;
+    uint32_t nb_global ;
+
+    __host__ __device__ uint32_t global_of(uint32_t l) const { return l < nb ? l+row_base : halo[l-nb] ; }
+    __host__ __device__ bool owns(uint32_t g) const { return g >= row_base && g-row_base < nb ; }
+    // local block column of global node g; NO_NODE when the part neither owns it nor has it in its halo
+    __host__ __device__ uint32_t local_of(uint32_t g) const
+    {
+        if(owns(g)) return g-row_base ;
+        uint32_t lo = 0, hi = nhalo ;
+        while(lo < hi)
+        {
+            const uint32_t mid = lo+((hi-lo) >> 1) ;
+            if(halo[mid] < g) lo = mid+1 ; else hi = mid ;
+        }
+        return (lo < nhalo && halo[lo] == g) ? nb+lo : 0xFFFFFFFFu ;
+    }
+} ;
+
 // ---------------------------------------------------------------------------------------------------- map build
 
-// element block (e, j, k) -> stored block (ids[j], ids[k]); counts the contributions of every stored block
-static __global__ void k_map_dest(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint32_t nb,
+// element block (e, j, k) -> stored block (ids[j], ids[k]); counts the contributions of every stored block.
+// Node ids are GLOBAL; blocks whose row belongs to another part of a partitioned matrix get NO_DEST here (that part
+// builds the same map over the same element list and keeps them).
+static __global__ void k_map_dest(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, PartMap pm,
                                   const uint32_t * __restrict__ ids, uint64_t nsrc, int npe,
                                   uint32_t * __restrict__ dest_of_src, uint32_t * __restrict__ count, int * __restrict__ flag)
 {
@@ -23,12 +56,19 @@ static __global__ void k_map_dest(const uint32_t * __restrict__ rowptr, const ui
         uint32_t d = NO_DEST ;
         if(rj != NO_NODE && ck != NO_NODE)
         {
-            if(rj >= nb || ck >= nb) { *flag = 1 ; }
-            else
+            if(rj >= pm.nb_global || ck >= pm.nb_global) { *flag = 1 ; }
+            else if(pm.owns(rj))
             {
-                const uint32_t k1 = __ldg(rowptr+rj+1) ;
-                const uint32_t k = row_lower_bound(col, __ldg(rowptr+rj), k1, ck) ;
-                if(k < k1 && __ldg(col+k) == ck) { d = k ; atomicAdd(count+k, 1u) ; }
+                const uint32_t lr = rj-pm.row_base ;
+                uint32_t k0 = __ldg(rowptr+lr) ;
+                const uint32_t k1 = __ldg(rowptr+lr+1) ;
+                uint32_t hi = k1 ;
+                while(k0 < hi)                      // the row's blocks ascend in GLOBAL column order
+                {
+                    const uint32_t mid = k0+((hi-k0) >> 1) ;
+                    if(pm.global_of(__ldg(col+mid)) < ck) k0 = mid+1 ; else hi = mid ;
+                }
+                if(k0 < k1 && pm.global_of(__ldg(col+k0)) == ck) { d = k0 ; atomicAdd(count+k0, 1u) ; }
                 else *flag = 2 ;
             }
         }
@@ -182,17 +222,20 @@ static __global__ void k_clear_dirty(unsigned char * __restrict__ dirty, uint64_
 
 // ---------------------------------------------------------------------------------------------------- elimination
 
-// ids ascending and unique: the first thread of every node gathers the node's bits (no atomics)
-static __global__ void k_bc_mask(const uint32_t * __restrict__ ids, uint64_t n, int S, unsigned char * __restrict__ mask)
+// ids (GLOBAL dof ids) ascending and unique: the first thread of every node gathers the node's bits (no atomics).
+// mask is indexed by LOCAL block column (owned rows, then the halo); nodes the part does not see are skipped.
+static __global__ void k_bc_mask(const uint32_t * __restrict__ ids, uint64_t n, int S, PartMap pm, unsigned char * __restrict__ mask)
 {
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
     for(uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; i < n ; i += stride)
     {
         const uint32_t node = ids[i]/S ;
         if(i && ids[i-1]/S == node) continue ;
+        const uint32_t local = pm.local_of(node) ;
+        if(local == NO_NODE) continue ;
         unsigned int bits = 0 ;
         for(uint64_t j = i ; j < n && ids[j]/S == node ; j++) bits |= 1u << (ids[j]-node*S) ;
-        mask[node] = (unsigned char)bits ;
+        mask[local] = (unsigned char)bits ;
     }
 }
 
@@ -207,8 +250,10 @@ __device__ __forceinline__ double bc_value(const uint32_t * __restrict__ ids, co
 // block, the multipliers of the row's node ("in line", solvers/assembly.cpp:170-207) and then those of the column's
 // node ("in block", :210-253), ascending -- the order in which the reference updates externalForces[k*S+m].
 // (A per-node offset into the id list instead of the binary search below was measured: same time, profiles/r02_notes.md.)
+// On one part of a partitioned matrix the rows, `forces`, `natural`, `add_to_forces` and the masks are LOCAL, the id
+// lists GLOBAL; a row's blocks are stored in global column order, so the updates of f keep the reference's order.
 template<int S>
-static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint64_t nb,
+static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const uint32_t * __restrict__ col, uint64_t nb, PartMap pm,
                                    double * __restrict__ vals, double * __restrict__ forces, double * __restrict__ natural,
                                    const double * __restrict__ add_to_forces,
                                    const unsigned char * __restrict__ fixmask, const uint32_t * __restrict__ fix_ids,
@@ -218,7 +263,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
                                    unsigned char * __restrict__ dirty)
 {
     // the imposed value of dof (node, n), whose bit is set in the node's mask
-    auto fixed_value = [&](uint32_t node, unsigned int, int n) { return bc_value(fix_ids, fix_values, nfix, node*S+n) ; } ;
+    auto fixed_value = [&](uint32_t node, unsigned int, int n) { return bc_value(fix_ids, fix_values, nfix, pm.global_of(node)*S+n) ; } ;
     const uint64_t stride = (uint64_t)gridDim.x*blockDim.x ;
     const uint64_t nrows = nb*S ;
     for(uint64_t row = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x ; row < nrows ; row += stride)
@@ -273,7 +318,7 @@ static __global__ void k_dirichlet(const uint32_t * __restrict__ rowptr, const u
             }
         }
         if(nforce && ((forcemask[k] >> m) & 1u))                // SET_FORCE_*: externalForces[id] += value (:262-268)
-            f = __dadd_rn(f, bc_value(force_ids, force_values, nforce, (uint32_t)row)) ;
+            f = __dadd_rn(f, bc_value(force_ids, force_values, nforce, (uint32_t)row+pm.row_base*S)) ;
         if(add_to_forces)                                       // externalForces += addToExternalForces (:323-324)
             f = __dadd_rn(f, ((rm >> m) & 1u) ? 0. : add_to_forces[row]) ;
         forces[row] = f ;

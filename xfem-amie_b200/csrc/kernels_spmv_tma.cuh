@@ -93,12 +93,15 @@ __device__ __forceinline__ void tile_producer(const SpmvArgs & a, unsigned char 
     constexpr int PD = 8 ;
     static_assert(PFD < PD, "prefetch distance") ;
     uint32_t rpq[PD] ;
+    // Unconditional, clamped loads (tile -> the last tile, row -> the end of the range; lanes past a short tile's rows
+    // read a valid word nobody uses): a predicated load goes through a temporary register and a MOV that waits for it
+    // right here, which stalled this warp for a whole memory latency per tile (7 % of the kernel's warp samples,
+    // profiles/r02_notes.md section 8) instead of leaving the load in flight until its tile comes up PD tiles later.
+    const uint32_t row_end = a.row0+a.nrows ;
     auto load_rp = [&](uint32_t t) -> uint32_t
     {
-        if(t >= ntiles) return 0u ;
-        const uint32_t r0 = a.row0+t*R ;
-        const uint32_t nr = min((uint32_t)R, a.row0+a.nrows-r0) ;
-        return lane <= (int)nr ? __ldg(a.rowptr+r0+lane) : 0u ;
+        const uint32_t r0 = a.row0+min(t, ntiles-1u)*R ;
+        return __ldg(a.rowptr+min(r0+(uint32_t)lane, row_end)) ;
     } ;
     const uint32_t tstride = step*gridDim.x ;
     #pragma unroll
