@@ -61,8 +61,11 @@ typedef struct amie_b200_ctx amie_b200_ctx ;
  *     context per device, halo and reductions over NVLink peer memory (csrc/group.cu, csrc/dist.cu).  Needs a
  *     peer-to-peer path between the devices and CUDA_MODULE_LOADING=EAGER (set automatically when AMIE_B200_DEVICES
  *     lists several devices at load time).  Strides 2 and 3.  An ordinal may be listed more than once (several parts on
- *     one GPU: how the path is tested on a one-GPU box).  Not on a multi-device context: set_block_map,
- *     download_matrix, the value-assembly and field-recovery rows (AMIE_B200_ERR_UNSUPPORTED).
+ *     one GPU: how the path is tested on a one-GPU box).  The value-assembly rows (set_elements / update_elements /
+ *     assemble / set_boundary_conditions) send the element list and the id lists to every device, which keeps what lands
+ *     on the block rows it owns; the field-recovery rows split the ELEMENTS over the devices, each holding the whole
+ *     displacement field (from the host, or gathered from the parts over the peer links).  Element and dof ids stay the
+ *     caller's global ones throughout.  Not on a multi-device context: set_block_map (AMIE_B200_ERR_UNSUPPORTED).
  *   One process per GPU (torchrun, MPI) uses amie_b200_dist_init (below) instead.
  * Returns NULL on failure (see amie_b200_global_error). */
 amie_b200_ctx * amie_b200_create(const int * devices, int ndev) ;

@@ -289,9 +289,15 @@ def test_group_field_recovery_matches_reference_bits(pkg, ol, devices, name):
     asm.set_element_behaviour(g["tensors"], g["imposed_strain"], g["imposed_stress"], g["tensor_of_elem"])
     tot, mech, sig = asm.element_fields(g["u"])
     assert same_bits(tot, g["total_strain"]) and same_bits(mech, g["mechanical_strain"]) and same_bits(sig, g["real_stress"])
-    for field, key, dbl in ((0, "principal_total_strain", True), (2, "principal_real_stress", False)):
+    for field, key in ((0, "principal_total_strain"), (2, "principal_real_stress")):
         if key in g.files:
-            assert same_bits(asm.element_principal(field), g[key])
+            got = asm.element_principal(field)
+            # 2D: only sqrt reaches the results -> the reference's bits; 3D goes through pow / atan2 / cos / sin of the
+            # device math library and is held to 1e-12 like on one device (tests/test_gpu_recovery.py)
+            if dim == 2:
+                assert same_bits(got, g[key])
+            else:
+                assert np.abs(got - g[key]).max() <= 1e-12 * np.abs(g[key]).max()
     # one behaviour per element (cut like the elements), and the field taken from the devices after a solve
     ne = g["ids"].shape[0]
     C = g["tensors"][g["tensor_of_elem"]]

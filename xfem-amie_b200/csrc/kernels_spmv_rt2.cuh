@@ -25,36 +25,7 @@ struct Rt2Layout
     static constexpr int TOTAL_BYTES = NST*STAGE_BYTES+2*NST*8+16 ;
 } ;
 
-template<int Q, int NB>
-struct Rt2Load
-{
-    static __device__ __forceinline__ void run(uint32_t va, uint32_t xa, double (&v0)[NB], double (&v1)[NB], double (&x0)[NB], double (&x1)[NB])
-    {
-        v0[Q] = lds_f64<Q*32>(va) ; v1[Q] = lds_f64<Q*32+16>(va) ;
-        x0[Q] = lds_f64<Q*16>(xa) ; x1[Q] = lds_f64<Q*16+8>(xa) ;
-        Rt2Load<Q+1, NB>::run(va, xa, v0, v1, x0, x1) ;
-    }
-} ;
-template<int NB>
-struct Rt2Load<NB, NB>
-{
-    static __device__ __forceinline__ void run(uint32_t, uint32_t, double (&)[NB], double (&)[NB], double (&)[NB], double (&)[NB]) { }
-} ;
-
-template<int NB>
-__device__ __forceinline__ void rt2_blocks(uint32_t va, uint32_t xa, double & acc0, double & acc1)
-{
-    double v0[NB], v1[NB], x0[NB], x1[NB] ;
-    Rt2Load<0, NB>::run(va, xa, v0, v1, x0, x1) ;
-    #pragma unroll
-    for(int q = 0 ; q < NB ; q++)
-    {
-        acc0 = fma(v0[q], x0[q], acc0) ;
-        acc1 = fma(v1[q], x1[q], acc1) ;
-    }
-}
-
-// Column mapping (CM): lane (rl, c) holds COLUMN c of its block row's blocks -- A(0,c), A(1,c) are 16 contiguous, 16-byte
+// Column mapping: lane (rl, c) holds COLUMN c of its block row's blocks -- A(0,c), A(1,c) are 16 contiguous, 16-byte
 // aligned bytes (one LDS.128) and only x_c is needed (one LDS.64): 2 shared-memory instructions / 6 wavefronts per block
 // instead of 4 / 8, conflict-free for rows of 7 blocks (row stride 224 B: four block rows x 2 columns fill the 128 B of
 // a quarter-warp pass; the row mapping collides block rows rl and rl + 4).  The two partial sums per row are the same
@@ -93,7 +64,7 @@ __device__ __forceinline__ void rt2_blocks_cm(uint32_t va, uint32_t xa, double &
     }
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1, int CM = 0>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
 __global__ void __launch_bounds__((W+NP)*32) k_spmv_s2_rt(SpmvArgs a)
 {
     if(a.check_stop && a.st->stop) return ;
@@ -128,7 +99,7 @@ __global__ void __launch_bounds__((W+NP)*32) k_spmv_s2_rt(SpmvArgs a)
     else
     {
         const int rl = lane >> 1 ;              // block row inside the tile
-        const int r = lane & 1 ;                // row component
+        const int r = lane & 1 ;                // the block COLUMN this lane multiplies, and the row component it stores
 
         auto issue_gather = [&](uint32_t j)
         {
@@ -208,64 +179,33 @@ __global__ void __launch_bounds__((W+NP)*32) k_spmv_s2_rt(SpmvArgs a)
                     }
                     const uint32_t n = k1-k0 ;
                     uint32_t t = 0 ;
-                    if(CM)
-                    {
-                        // r is this lane's COLUMN here
-                        const uint32_t va = smem_u32(stage+meta[R+1])+(k0-k_lo)*32u+(uint32_t)r*16u ;
-                        const uint32_t xa = smem_u32(stage+L::VAL_BYTES+L::COL_BYTES)+(k0-k_lo)*16u+(uint32_t)r*8u ;
-                        if(n == 7u)
-                        {
-                            rt2_blocks_cm<7>(va, xa, acc0, acc1) ;
-                            t = 7 ;
-                        }
-                        for( ; t+4 <= n ; t += 4) rt2_blocks_cm<4>(va+t*32, xa+t*16, acc0, acc1) ;
-                        for( ; t < n ; t++)       rt2_blocks_cm<1>(va+t*32, xa+t*16, acc0, acc1) ;
-                    }
-                    else
-                    {
-                    const uint32_t va = smem_u32(stage+meta[R+1])+(k0-k_lo)*32u+(uint32_t)r*8u ;
-                    const uint32_t xa = smem_u32(stage+L::VAL_BYTES+L::COL_BYTES)+(k0-k_lo)*16u ;
+                    const uint32_t va = smem_u32(stage+meta[R+1])+(k0-k_lo)*32u+(uint32_t)r*16u ;
+                    const uint32_t xa = smem_u32(stage+L::VAL_BYTES+L::COL_BYTES)+(k0-k_lo)*16u+(uint32_t)r*8u ;
                     if(n == 7u)
                     {
-                        rt2_blocks<7>(va, xa, acc0, acc1) ;      // the interior row of a T3 mesh
+                        rt2_blocks_cm<7>(va, xa, acc0, acc1) ;       // the interior row of a T3 mesh
                         t = 7 ;
                     }
-                    for( ; t+4 <= n ; t += 4) rt2_blocks<4>(va+t*32, xa+t*16, acc0, acc1) ;
-                    for( ; t < n ; t++)       rt2_blocks<1>(va+t*32, xa+t*16, acc0, acc1) ;
-                    }
+                    for( ; t+4 <= n ; t += 4) rt2_blocks_cm<4>(va+t*32, xa+t*16, acc0, acc1) ;
+                    for( ; t < n ; t++)       rt2_blocks_cm<1>(va+t*32, xa+t*16, acc0, acc1) ;
                 }
                 else
                 {
                     if(a.colstart_blk) k0 = row_lower_bound(a.col, k0, k1, a.colstart_blk) ;
                     for(uint32_t k = k0 ; k < k1 ; k++)
                     {
-                        if(CM)
-                        {
-                            const double * v = a.vals+(size_t)k*4+2*r ;
-                            const double xc = __ldg(a.x+(size_t)__ldg(a.col+k)*2+r) ;
-                            acc0 = fma(ld_stream(v), xc, acc0) ;
-                            acc1 = fma(ld_stream(v+1), xc, acc1) ;
-                        }
-                        else
-                        {
-                        const double * v = a.vals+(size_t)k*4+r ;
-                        const double * px = a.x+(size_t)__ldg(a.col+k)*2 ;
-                        acc0 = fma(ld_stream(v), __ldg(px), acc0) ;
-                        acc1 = fma(ld_stream(v+2), __ldg(px+1), acc1) ;
-                        }
+                        const double * v = a.vals+(size_t)k*4+2*r ;
+                        const double xc = __ldg(a.x+(size_t)__ldg(a.col+k)*2+r) ;
+                        acc0 = fma(ld_stream(v), xc, acc0) ;
+                        acc1 = fma(ld_stream(v+1), xc, acc1) ;
                     }
                 }
                 const size_t i = (size_t)(r0+rl)*2+r ;
-                double yv ;
-                if(CM)
-                {
-                    // lane c holds (row 0, row 1) partial sums of column c; row r = this lane's c.  Both lanes of a block
-                    // row are active together (rl < nr), so the exchange is safe inside this branch.
-                    const double give = r == 0 ? acc1 : acc0 ;
-                    const double got = __shfl_xor_sync(__activemask(), give, 1) ;
-                    yv = r == 0 ? acc0+got : got+acc1 ;
-                }
-                else yv = acc0+acc1 ;
+                // lane c holds the (row 0, row 1) partial sums of column c; it stores row r = c.  Both lanes of a block row
+                // are active together (rl < nr), so the exchange is safe inside this branch.
+                const double give = r == 0 ? acc1 : acc0 ;
+                const double got = __shfl_xor_sync(__activemask(), give, 1) ;
+                double yv = r == 0 ? acc0+got : got+acc1 ;
                 if(MINUS_B) yv -= aux[lane] ;
                 yv *= a.sign ;
                 a.y[i] = yv ;

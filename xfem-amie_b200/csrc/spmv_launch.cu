@@ -58,10 +58,10 @@ static inline void launch_s3_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
     kern<<<grid, threads, smem, ctx->stream>>>(args) ;
 }
 
-template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1, int CM = 0>
+template<int DOT, bool MINUS_B, int W, int NST, int CAP, int G, int NP = 1>
 static inline void launch_s2_rt(amie_b200_ctx * ctx, const SpmvArgs & args)
 {
-    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP, CM> ;
+    auto kern = k_spmv_s2_rt<DOT, MINUS_B, W, NST, CAP, G, NP> ;
     constexpr int smem = Rt2Layout<NST, CAP>::TOTAL_BYTES ;
     constexpr int threads = (W+NP)*32 ;
     static int cache[AMIE_MAX_DEVICES] = {} ;
@@ -96,17 +96,13 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
             // fills its stage (27 blocks/row for Q1 hexahedra, 12-15 for linear tetrahedra).  Short rows mean small
             // tiles, and ONE producer warp (~0.3 us per tile) then caps the CTA: three producers there.
             const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
-            // (variant 6, A/B of round 2: one more stage -- 8 x 28 KB / 13 x 17 KB fill the 227 KB, nothing left for L1)
+            // Stages fill the 227 KB: 8 x 28 KB / 13 x 17 KB.  (Round 1 kept ~30 KB back as L1 for the x gather; since the
+            // gather touches a third of the lines it did, the extra stage in flight is worth more: hexahedra 6.27 -> 6.23 ms
+            // in the solve, tetrahedra 3.50 -> 3.38 ms, profiles/r02_notes.md section 9.)
             if(avg > 15.5 || ctx->opt_variant == 3)
-            {
-                if(ctx->opt_variant == 6) launch_s3_rt<DOT, MINUS_B, 3, 8, 270, 1>(ctx, args) ;
-                else launch_s3_rt<DOT, MINUS_B, 3, 7, 270, 1>(ctx, args) ;   // 7 stages, not 8: leaves ~30 KB of L1 for the x gather
-            }
+                launch_s3_rt<DOT, MINUS_B, 3, 8, 270, 1>(ctx, args) ;
             else
-            {
-                if(ctx->opt_variant == 6) launch_s3_rt<DOT, MINUS_B, 5, 13, 160, 1, 9, 3>(ctx, args) ;
-                else launch_s3_rt<DOT, MINUS_B, 5, 12, 160, 1, 9, 3>(ctx, args) ;
-            }
+                launch_s3_rt<DOT, MINUS_B, 5, 13, 160, 1, 9, 3>(ctx, args) ;
         }
     }
     else
@@ -114,22 +110,12 @@ static inline void spmv_dispatch(amie_b200_ctx * ctx, const SpmvArgs & args)
         // rows are short in 2D (about 7 blocks): 8 lanes per row unless rows are long
         const double avg = ctx->nb ? (double)ctx->nnzb/(double)ctx->nb : 0. ;
         int G = avg > 24. ? 32 : (avg > 10. ? 16 : 8) ;
-        if(ctx->opt_variant == 4)
+        if((ctx->opt_variant == 0 && avg <= 9.) || ctx->opt_variant == 3)
         {
-            launch_s2_rt<DOT, MINUS_B, 8, 20, 144, 1, 4, 0>(ctx, args) ;      // A/B: the row mapping (lane <-> scalar row)
-            return ;
-        }
-        if(ctx->opt_variant == 6)
-        {
-            launch_s2_rt<DOT, MINUS_B, 8, 24, 144, 1, 4, 1>(ctx, args) ;      // A/B: 24 stages
-            return ;
-        }
-        if((ctx->opt_variant == 0 && avg <= 9.) || ctx->opt_variant == 3 || ctx->opt_variant == 5)
-        {
-            // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh), column mapping.  A 16-row tile is only
-            // ~3.6 KB, so the per-tile producer cost dominates: FOUR producer warps (1 producer: 1.4 TB/s, 4: 4.8 TB/s
-            // on S2-tri-4096)
-            launch_s2_rt<DOT, MINUS_B, 8, 20, 144, 1, 4, 1>(ctx, args) ;
+            // row-thread TMA pipeline for 2x2 blocks (kernels_spmv_rt2.cuh).  A 16-row tile is only ~3.6 KB, so the per-tile
+            // producer cost dominates: FOUR producer warps (1 producer: 1.4 TB/s, 4: 4.8 TB/s on S2-tri-4096); 24 stages
+            // instead of 20 change nothing (profiles/r02_notes.md section 9)
+            launch_s2_rt<DOT, MINUS_B, 8, 20, 144, 1, 4>(ctx, args) ;
             return ;
         }
         if(ctx->opt_variant == 8 || ctx->opt_variant == 16 || ctx->opt_variant == 32) G = ctx->opt_variant ;
