@@ -182,17 +182,20 @@ def host_bytes_needed(preset, n):
     return nb * per_row * (8 * st * (st + st % 2) + 8) + 16 * 8 * nb * st
 
 
-def same_size_sample(preset, n, eps, cores, want_x_path=None, spmv_reps=3):
+def same_size_sample(preset, n, eps, cores, want_x_path=None, spmv_reps=3, x0_path=None):
     """The reference's solve of the WORKLOAD-size system, truncated by a looser eps (maxit bounds only the restarts of
     ConjugateGradient::solve, conjugategradient.cpp:93,121, never the inner loop, so a tolerance is the one way to get
-    a bounded sample of the same system).  The matrix is generated straight into the reference's storage."""
+    a bounded sample of the same system), optionally from a starting vector (x0_path: .npy).  The matrix is generated
+    straight into the reference's storage."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     if ol.ref() is None:
         return None
     t0 = time.time()
+    x0 = np.load(x0_path) if x0_path else None
     ret, x, nit, wall, spmv_s, dims = ol.ref_cg_synth(preset, n, eps=eps, nssor=32, nthreads=cores, spmv_reps=spmv_reps,
-                                                      want_x=want_x_path is not None)
+                                                      want_x=want_x_path is not None, x0=x0)
+    del x0
     out = {"workload": f"{preset}-{n}", "ndof": dims["nb"] * dims["stride"], "eps": eps, "nit": int(nit), "solve_s": wall,
            "it_per_s": nit / wall if wall > 0 else None, "converged": bool(ret), "total_s": time.time() - t0,
            "spmv": spmv_rates(dims["stride"], dims["nb"], dims["nnzb"], spmv_s) if spmv_s else None}
@@ -200,6 +203,73 @@ def same_size_sample(preset, n, eps, cores, want_x_path=None, spmv_reps=3):
         np.save(want_x_path, x)
         out["x_checksum"] = float(np.abs(x).sum())
     return out
+
+
+PAIR_WINDOW = (60, 160)        # iterations a same-size sample should take: ~1 minute of the reference at 50 M unknowns
+PAIR_MIN_NIT = 10              # fewer iterations than this time nothing
+
+
+def bracket_nit(solve, eps_list, tries=6, window=PAIR_WINDOW):
+    """solve(eps) -> (nit, ms), nit a non-increasing step function of eps.  Walk eps_list (descending) until a solve takes
+    at least window[0] iterations, then bisect log(eps) between the last too-short and the first long-enough solve.
+    Returns every (eps, nit, ms) tried."""
+    tried = []
+    lo_eps, hi_eps = None, None                     # lo_eps: too few iterations, hi_eps: enough or too many
+    for eps in eps_list:
+        n_, ms_ = solve(eps)
+        tried.append((eps, n_, ms_))
+        if n_ < window[0]:
+            lo_eps = eps
+            continue
+        hi_eps = eps
+        break
+    k = 0
+    while hi_eps and lo_eps and k < tries and not any(window[0] <= t[1] <= window[1] for t in tried):
+        mid = (lo_eps * hi_eps) ** 0.5
+        n_, ms_ = solve(mid)
+        tried.append((mid, n_, ms_))
+        k += 1
+        if n_ < window[0]:
+            lo_eps = mid
+        else:
+            hi_eps = mid
+    return tried
+
+
+def choose_sample(tried, window=PAIR_WINDOW, min_nit=PAIR_MIN_NIT, max_above=0):
+    """The tolerance whose solve is a bounded, non-trivial sample: inside the window the shortest; else the longest
+    below it that still iterates (>= min_nit); else, if allowed, the shortest above it (<= max_above); else None."""
+    inwin = [t for t in tried if window[0] <= t[1] <= window[1]]
+    if inwin:
+        return min(inwin, key=lambda t: t[1])
+    below = [t for t in tried if min_nit <= t[1] < window[0]]
+    if below:
+        return max(below, key=lambda t: t[1])
+    above = [t for t in tried if window[1] < t[1] <= max_above]
+    return min(above, key=lambda t: t[1]) if above else None
+
+
+def search_same_size_sample(solve_cold, solve_warm_from):
+    """Which truncated solve both sides run on the workload-size system.
+    solve_cold(eps) -> (nit, ms) from x0 = 0.  sqrt(|rho|) is not monotone along the iteration: on the benchmark system
+    nit(eps) jumps from a handful of iterations to ~600 (a plateau), so a tolerance alone may give no bounded sample.
+    Then: start where the shortest long-enough cold solve stopped -- solve_warm_from(eps_a) -> solve_warm(eps) -> (nit,
+    ms), which restarts from that solution -- and tighten the tolerance until the restarted solve iterates long enough.
+    Returns (eps, nit, eps_a or None, tried_cold, tried_warm) or None."""
+    cold = bracket_nit(solve_cold, (1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8))
+    best = choose_sample(cold)
+    if best:
+        return best[0], best[1], None, cold, []
+    long_enough = [t for t in cold if t[1] >= PAIR_WINDOW[0]]
+    if not long_enough:
+        return None
+    eps_a = min(long_enough, key=lambda t: t[1])[0]
+    solve_warm = solve_warm_from(eps_a)
+    warm = bracket_nit(solve_warm, [eps_a * f for f in (0.5, 0.2, 0.1, 0.03, 0.01, 1e-3, 1e-4, 1e-5)])
+    best = choose_sample(warm, max_above=400)
+    if best:
+        return best[0], best[1], eps_a, cold, warm
+    return None
 
 
 def pick_same_size_n(preset, n):
@@ -227,7 +297,8 @@ def run_reference_arm(args, rank):
         # called by the GPU arm: one small full solve (+ the reference's SpMV) and the same-size truncated solve
         out = {"cores": cores, "env": env, "small": cpu_reference_rate(args.preset, args.cpu_n, cores)}
         if args.pair_n:
-            out["same_size"] = same_size_sample(args.preset, args.pair_n, args.pair_eps, cores, want_x_path=args.pair_x)
+            out["same_size"] = same_size_sample(args.preset, args.pair_n, args.pair_eps, cores, want_x_path=args.pair_x,
+                                                x0_path=args.pair_x0)
         print(json.dumps(out), flush=True)
         return
     # driver-launched: K bounded steps.  One full solve costs ~3e-7 n^4 s on 16 cores: size the mesh to the step budget.
@@ -276,12 +347,14 @@ def run_reference_arm(args, rank):
 PAIR_EPS_DEFAULT = 1e-2
 
 
-def cpu_leg(args, pair_n, pair_eps, pair_x):
+def cpu_leg(args, pair_n, pair_eps, pair_x, pair_x0=None):
     """cpu_baseline of the GPU arm: the reference arm in a process of its own (oracle/ libraries only, pinned threads)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-leg", "--preset", args.preset,
            "--mesh-n", str(args.n), "--cpu-n", str(args.cpu_n)]
     if pair_n:
         cmd += ["--pair-n", str(pair_n), "--pair-eps", repr(pair_eps), "--pair-x", pair_x]
+        if pair_x0:
+            cmd += ["--pair-x0", pair_x0]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS")}
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1800)
     if p.returncode != 0:
@@ -327,6 +400,7 @@ def main():
     ap.add_argument("--pair-n", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--pair-eps", type=float, default=PAIR_EPS_DEFAULT, help=argparse.SUPPRESS)
     ap.add_argument("--pair-x", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--pair-x0", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.n is None:
         args.n = int(os.environ.get("AMIE_BENCH_N", 4096 if args.preset.startswith("S2") else 256))
@@ -456,45 +530,54 @@ def main():
                 psyn = pkg.Synth(args.preset, pair_n)
                 pasm = pkg.Assembly(device=local_rank)
                 psyn.to_device(pasm)
-            # nit(eps) is a non-increasing step function: bracket the target window [60, 160] from both sides, then
-            # bisect log(eps) (a GPU solve of this length takes a second or two); the reference solves the same eps
-            def gpu_try(eps):
+            # The GPU searches the sample (a solve of this length takes a second or two); the reference then runs exactly
+            # that solve: same tolerance, same starting vector.
+            pair_x0 = os.path.join("/tmp", f"amie_bench_pair_x0_{os.getpid()}.npy")
+            warm_x0 = {}
+
+            def gpu_cold(eps):
                 pasm.upload_x0(None)
                 ok_, nit_, _, _ = pasm.pcg_resident(nssor=32, eps=eps)
                 return int(nit_), pasm.stats().solve_ms
-            tried = []                                      # (eps, nit, ms)
-            lo_eps, hi_eps = None, None                     # lo_eps: too few iterations, hi_eps: too many
-            for eps in (1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8):
-                n_, ms_ = gpu_try(eps)
-                tried.append((eps, n_, ms_))
-                if n_ < 60:
-                    lo_eps = eps
-                    continue
-                hi_eps = eps
-                break
-            tries = 0
-            while hi_eps and lo_eps and tries < 6 and not any(60 <= t[1] <= 160 for t in tried):
-                mid = (lo_eps * hi_eps) ** 0.5
-                n_, ms_ = gpu_try(mid)
-                tried.append((mid, n_, ms_))
-                tries += 1
-                if n_ < 60:
-                    lo_eps = mid
+
+            def gpu_warm_from(eps_a):
+                gpu_cold(eps_a)
+                warm_x0["x"] = pasm.download_x()
+
+                def gpu_warm(eps):
+                    pasm.upload_x0(warm_x0["x"])
+                    ok_, nit_, _, _ = pasm.pcg_resident(nssor=32, eps=eps)
+                    return int(nit_), pasm.stats().solve_ms
+                return gpu_warm
+            try:
+                found = search_same_size_sample(gpu_cold, gpu_warm_from)
+            except Exception as exc:                           # a sample is a nicety: never lose the bench line over it
+                print(f"[bench] same-size sample search failed: {exc!r}", file=sys.stderr)
+                found = None
+            if found:
+                pair_eps, _, eps_a, tried_cold, tried_warm = found
+                if eps_a is None:
+                    g_nit, g_ms = gpu_cold(pair_eps)           # leaves the x of pair_eps on the device
                 else:
-                    hi_eps = mid
-            # sqrt(|rho|) is not monotone along the iteration: nit(eps) jumps over plateaus, and the window can be empty.
-            # Then the longest solve below it (the CPU side must stay a bounded sample), else the shortest above.
-            inwin = [t for t in tried if 60 <= t[1] <= 160]
-            below = [t for t in tried if 10 <= t[1] < 60]
-            best = min(inwin, key=lambda t: t[1]) if inwin else (max(below, key=lambda t: t[1]) if below else min(tried, key=lambda t: t[1]))
-            pair_eps = best[0]
-            g_nit, g_ms = gpu_try(pair_eps)                # leaves the x of pair_eps on the device
-            x_gpu = pasm.download_x()
-            pair = {"workload": f"{args.preset}-{pair_n}", "eps": pair_eps, "gpu_nit": int(g_nit), "gpu_solve_ms": g_ms,
-                    "gpu_it_per_s": g_nit / (g_ms * 1e-3) if g_ms else None, "gpus": ngpu if pasm is asm else 1}
+                    np.save(pair_x0, warm_x0["x"])
+                    pasm.upload_x0(warm_x0["x"])
+                    ok_, g_nit, _, _ = pasm.pcg_resident(nssor=32, eps=pair_eps)
+                    g_nit, g_ms = int(g_nit), pasm.stats().solve_ms
+                x_gpu = pasm.download_x()
+                pair = {"workload": f"{args.preset}-{pair_n}", "eps": pair_eps, "gpu_nit": int(g_nit), "gpu_solve_ms": g_ms,
+                        "gpu_it_per_s": g_nit / (g_ms * 1e-3) if g_ms else None, "gpus": ngpu if pasm is asm else 1,
+                        "x0": "zero" if eps_a is None else f"the solution of the same system at eps {eps_a:g} (computed on the GPU, handed to the reference)",
+                        "searched": {"cold": [(e, n) for e, n, _ in tried_cold], "warm": [(e, n) for e, n, _ in tried_warm]}}
+                if eps_a is None:
+                    pair_x0 = None
+            else:
+                pair_x0 = None
+            warm_x0.clear()
             if pasm is not asm:
                 pasm.close()
-        r = cpu_leg(args, pair_n, pair["eps"] if pair else PAIR_EPS_DEFAULT, pair_x)
+        r = cpu_leg(args, pair_n if pair else 0, pair["eps"] if pair else PAIR_EPS_DEFAULT, pair_x, pair_x0 if pair else None)
+        if pair and pair_x0 and os.path.exists(pair_x0):
+            os.remove(pair_x0)
         if "error" in r:
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "reference", "sample": "cpu leg failed: " + r["error"]}
         else:

@@ -213,9 +213,25 @@ int amie_ref_cg(int stride, uint64_t nb, const uint32_t * row_size, const uint32
 // straight into the reference's own storage, so a benchmark-size matrix (43 GB of padded values at 50 M DOF) exists
 // once in host memory, not twice.  spmv_reps > 0 additionally times assign(y, A*b) on that matrix (seconds per call).
 typedef int (*amie_ref_fill_fn)(void * user, uint32_t * column_index, double * array_padded, double * forces) ;
+int amie_ref_cg_fill_x0(int stride, uint64_t nb, const uint32_t * row_size, uint64_t nnzb, amie_ref_fill_fn fill, void * user,
+                        const double * x0, uint64_t nx0,
+                        double eps, int maxit, uint64_t nssor, int nthreads, int spmv_reps,
+                        double * x_out, uint64_t * nit_out, double * wall_s_out, double * spmv_s_out, char * log, uint64_t logcap) ;
+
 int amie_ref_cg_fill(int stride, uint64_t nb, const uint32_t * row_size, uint64_t nnzb, amie_ref_fill_fn fill, void * user,
                      double eps, int maxit, uint64_t nssor, int nthreads, int spmv_reps,
                      double * x_out, uint64_t * nit_out, double * wall_s_out, double * spmv_s_out, char * log, uint64_t logcap)
+{
+    return amie_ref_cg_fill_x0(stride, nb, row_size, nnzb, fill, user, nullptr, 0, eps, maxit, nssor, nthreads, spmv_reps,
+                               x_out, nit_out, wall_s_out, spmv_s_out, log, logcap) ;
+}
+
+// the same from a starting vector (ConjugateGradient::solve(x0, ...), conjugategradient.cpp:95-104): a bounded sample of a
+// long solve is "start where a shorter solve stopped, tighten the tolerance a little"
+int amie_ref_cg_fill_x0(int stride, uint64_t nb, const uint32_t * row_size, uint64_t nnzb, amie_ref_fill_fn fill, void * user,
+                        const double * x0, uint64_t nx0,
+                        double eps, int maxit, uint64_t nssor, int nthreads, int spmv_reps,
+                        double * x_out, uint64_t * nit_out, double * wall_s_out, double * spmv_s_out, char * log, uint64_t logcap)
 {
 #ifdef HAVE_OPENMP
     if(nthreads > 0) omp_set_num_threads(nthreads) ;
@@ -244,7 +260,8 @@ int amie_ref_cg_fill(int stride, uint64_t nb, const uint32_t * row_size, uint64_
     }
     Amie::ConjugateGradient cg(&a) ;
     cg.nssor = nssor ;
-    Vector vx0(0., 0) ;
+    Vector vx0(0., x0 ? nx0 : 0) ;
+    if(x0 && nx0) std::memcpy(&vx0[0], x0, nx0*sizeof(double)) ;
     double t0 = now() ;
     bool ok = cg.solve(vx0, nullptr, eps, maxit, false) ;
     double t1 = now() ;

@@ -244,7 +244,7 @@ def ref_cg(S, x0=None, precond=0, eps=1e-10, maxit=-1, nssor=32, rowstart=0, col
     return ret, x, nit.value, wall.value, log.value.decode(errors="replace")
 
 
-def ref_cg_synth(preset, n, eps=1e-10, maxit=-1, nssor=32, nthreads=1, spmv_reps=0, seed=1, want_x=True):
+def ref_cg_synth(preset, n, eps=1e-10, maxit=-1, nssor=32, nthreads=1, spmv_reps=0, seed=1, want_x=True, x0=None):
     """The reference's ConjugateGradient::solve on the synthetic system `preset`-n, generated straight into the
     reference's own storage (one copy of the matrix in host memory: benchmark sizes).  Returns
     (ret, x or None, nit, solve seconds, seconds per assign(y, A*b) or None, dict(stride, nb, nnzb))."""
@@ -265,13 +265,16 @@ def ref_cg_synth(preset, n, eps=1e-10, maxit=-1, nssor=32, nthreads=1, spmv_reps
     x = np.zeros(nb.value * st.value) if want_x else None
     nit, wall, spmv_s = u64(), f64(), f64(-1.0)
     log = ctypes.create_string_buffer(8192)
-    R.amie_ref_cg_fill.argtypes = [ctypes.c_int, u64, ctypes.c_void_p, u64, FILL, ctypes.c_void_p, f64, ctypes.c_int, u64,
-                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                   ctypes.c_void_p, ctypes.c_char_p, u64]
-    ret = R.amie_ref_cg_fill(st.value, nb.value, _vp(rs), tot.value, cb, None, eps, int(maxit), int(nssor), int(nthreads),
-                             int(spmv_reps), _vp(x), ctypes.cast(ctypes.byref(nit), ctypes.c_void_p),
-                             ctypes.cast(ctypes.byref(wall), ctypes.c_void_p), ctypes.cast(ctypes.byref(spmv_s), ctypes.c_void_p),
-                             log, 8192)
+    x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+    R.amie_ref_cg_fill_x0.argtypes = [ctypes.c_int, u64, ctypes.c_void_p, u64, FILL, ctypes.c_void_p, ctypes.c_void_p, u64,
+                                      f64, ctypes.c_int, u64,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_char_p, u64]
+    ret = R.amie_ref_cg_fill_x0(st.value, nb.value, _vp(rs), tot.value, cb, None, _vp(x0), 0 if x0 is None else x0.size,
+                                eps, int(maxit), int(nssor), int(nthreads),
+                                int(spmv_reps), _vp(x), ctypes.cast(ctypes.byref(nit), ctypes.c_void_p),
+                                ctypes.cast(ctypes.byref(wall), ctypes.c_void_p), ctypes.cast(ctypes.byref(spmv_s), ctypes.c_void_p),
+                                log, 8192)
     L.amie_b200_synth_destroy(h)
     if ret < 0:
         raise RuntimeError("amie_ref_cg_fill: the generator failed")
