@@ -1,6 +1,6 @@
-"""bench.py's search for the same-size sample both sides solve (cpu_baseline.same_size_pair): the tolerance -- and, when
-nit(eps) jumps over the window as on the benchmark system, the starting vector -- that makes the reference's solve of the
-workload-size system a bounded, non-trivial sample.  Host logic only; the solver behind it here is the oracle."""
+"""bench.py's search for the same-size sample both sides solve (cpu_baseline.same_size_pair): the tolerance that makes the
+reference's solve of the workload-size system a bounded, non-trivial sample -- or the finding that there is none (nit(eps)
+jumps over the window on the benchmark system).  Host logic only; the solver behind it here is the oracle."""
 import importlib.util
 import os
 
@@ -28,31 +28,22 @@ def step_function(table):
     return solve
 
 
-def test_window_found_from_a_cold_start(bench):
+def test_window_found(bench):
     cold = step_function([(5e-2, 0), (2e-3, 25), (4e-4, 90), (1e-5, 400), (0, 2500)])
     calls = []
-    found = bench.search_same_size_sample(lambda e: (calls.append(e), cold(e))[1], lambda eps_a: pytest.fail("no warm start needed"))
-    eps, nit, eps_a, tried_cold, tried_warm = found
-    assert eps_a is None and 60 <= nit <= 160 and cold(eps)[0] == nit and not tried_warm
-    assert len(calls) <= 8 + 6
+    eps, nit, tried = bench.search_same_size_sample(lambda e: (calls.append(e), cold(e))[1])
+    assert 60 <= nit <= 160 and cold(eps)[0] == nit
+    assert len(calls) <= 8 + 6 and len(tried) == len(calls)
 
 
-def test_plateau_takes_the_warm_start(bench):
-    """The benchmark system: a handful of iterations, then ~600 (profiles/r02_notes.md section 5).  No cold sample in
-    [10, 160] -> restart from the shortest long-enough solve and tighten."""
+def test_plateau_gives_no_sample_unless_the_long_one_is_accepted(bench):
+    """The benchmark system: a handful of iterations, then ~600 (profiles/r02_notes.md sections 5 and 10).  A degenerate
+    sample (0 or 3 iterations time nothing) is never returned."""
     cold = step_function([(5e-2, 0), (4e-3, 3), (1e-6, 600), (0, 2500)])
-    started = {}
-
-    def warm_from(eps_a):
-        started["eps_a"] = eps_a
-        return lambda eps: ((0, 0.) if eps >= eps_a * 0.45 else (int(40 * np.log10(eps_a / eps)), 1.))
-    eps, nit, eps_a, tried_cold, tried_warm = bench.search_same_size_sample(cold, warm_from)
-    assert eps_a == started["eps_a"] and cold(eps_a)[0] == 600
-    assert 60 <= nit <= 160 and eps < eps_a and tried_warm
-    # nothing usable anywhere: no sample rather than a degenerate one (0 iterations time nothing)
-    assert bench.search_same_size_sample(step_function([(0, 2)]), warm_from) is None
-    never = bench.search_same_size_sample(cold, lambda eps_a: (lambda eps: (0, 0.)))
-    assert never is None
+    assert bench.search_same_size_sample(cold) is None
+    eps, nit, tried = bench.search_same_size_sample(cold, long_ok=True)
+    assert nit == 600 and cold(eps)[0] == 600
+    assert bench.search_same_size_sample(step_function([(0, 2)]), long_ok=True) is None
 
 
 def test_choose_sample_never_returns_a_trivial_solve(bench):
@@ -64,33 +55,24 @@ def test_choose_sample_never_returns_a_trivial_solve(bench):
 
 
 def test_search_with_the_oracle_as_the_solver(bench, pkg, ol):
-    """The real thing at a small size: cold and restarted solves of S3-hex-14 through the oracle; what the search returns
-    is reproduced by a direct solve with the tolerance and starting vector it names."""
+    """The real thing at a small size: solves of S3-hex-14 through the oracle; what the search returns is reproduced by a
+    direct solve with the tolerance it names."""
     from conftest import make_sys
     S = make_sys(pkg, ol, "S3-hex", 14, 1)
 
     def cold(eps):
         ret, x, info = ol.oracle_cg(S, nssor=32, eps=eps)
         return int(info.nit), 0.
-
-    def warm_from(eps_a):
-        ret, xa, info = ol.oracle_cg(S, nssor=32, eps=eps_a)
-
-        def warm(eps):
-            ret, x, info = ol.oracle_cg(S, x0=xa, nssor=32, eps=eps)
-            return int(info.nit), 0.
-        return warm
-    found = bench.search_same_size_sample(cold, warm_from)
+    found = bench.search_same_size_sample(cold)
     assert found is not None
-    eps, nit, eps_a, tried_cold, tried_warm = found
-    assert nit >= bench.PAIR_MIN_NIT
-    again = cold(eps)[0] if eps_a is None else warm_from(eps_a)(eps)[0]
-    assert again == nit
+    eps, nit, tried = found
+    assert nit >= bench.PAIR_MIN_NIT and cold(eps)[0] == nit
 
 
 def test_reference_restart_entry_matches_the_oracle(pkg, ol):
-    """oracle/ref_harness.cpp amie_ref_cg_fill_x0 (the reference's own ConjugateGradient::solve(x0, ...) on the generated
-    system, what bench.py's CPU leg runs for a restarted sample) against the oracle restatement: same count, same bits."""
+    """oracle/ref_harness.cpp amie_ref_cg_fill / amie_ref_cg_fill_x0 (the reference's own ConjugateGradient::solve on the
+    system generated into its storage -- what bench.py's CPU leg runs -- from zero and from a starting vector) against the
+    oracle restatement: same count, same bits."""
     if ol.ref() is None:
         pytest.skip("oracle/_ref not built")
     from conftest import make_sys
