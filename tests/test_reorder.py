@@ -61,3 +61,25 @@ def test_rcm_handles_disconnected_graphs_and_is_deterministic(pkg):
     ci = np.array([0, 1, 0, 1, 2, 1, 2, 3, 4, 5, 4, 5, 6, 5, 6], np.uint32)
     p1, p2 = pkg.rcm_order(rs, ci), pkg.rcm_order(rs, ci)
     assert np.array_equal(p1, p2) and np.array_equal(np.sort(p1), np.arange(7))
+
+
+def test_gather_of_a_device_slice_under_a_block_map(pkg):
+    """amie_b200_set_block_map on a multi-device context (csrc/group.cu): device r holds the stored blocks
+    [k0, k1) of the renumbered structure, which are blocks block_from[k0:k1] of the caller's array -- gathered on the
+    host by amie_b200_gather_blocks before the upload.  Against numpy indexing, padded 3x3 and 2x2 blocks."""
+    import ctypes
+    from conftest import random_spd_blocks
+    L = pkg.lib()
+    L.amie_b200_gather_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    L.amie_b200_gather_blocks.restype = None
+    for stride in (2, 3):
+        rs, ci, arr, b = random_spd_blocks(stride, 60, 70 + stride)
+        per_block = stride * (stride + stride % 2)
+        perm = pkg.rcm_order(rs, ci)
+        rs2, ci2, frm = pkg.permute_structure(rs, ci, perm)
+        want = arr.reshape(-1, per_block)[frm]
+        k0, k1 = frm.size // 3, frm.size - 5                       # some device's range of stored blocks
+        src = np.ascontiguousarray(frm[k0:k1], np.uint32)
+        out = np.zeros((k1 - k0) * per_block)
+        L.amie_b200_gather_blocks(arr.ctypes.data, src.ctypes.data, k1 - k0, per_block, out.ctypes.data)
+        assert np.array_equal(out.reshape(-1, per_block), want[k0:k1])

@@ -444,7 +444,7 @@ int amie_b200_set_values(amie_b200_ctx * ctx, const double * array)
 int amie_b200_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to)
 {
     if(!ctx) return AMIE_B200_ERR_ARG ;
-    if(ctx->group) return group_unsupported(ctx, "set_block_map") ;
+    if(ctx->group) return group_set_block_map(ctx, block_to) ;
     if(!ctx->have_structure) { ctx->set_error("set_block_map before set_structure") ; return AMIE_B200_ERR_STATE ; }
     if(ctx->dist) { ctx->set_error("set_block_map: not available on a row-partitioned context") ; return AMIE_B200_ERR_UNSUPPORTED ; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
@@ -783,4 +783,56 @@ int amie_b200_inverse_diagonal(amie_b200_ctx * ctx, double * d_out)
     return AMIE_B200_OK ;
 }
 
+}
+
+
+// Values of this context's stored blocks j = 0 .. nnzb-1 taken from blocks src[j] of a host array in the reference's
+// padded layout (a multi-device context under a block map, group.cu: the blocks of one device's rows are scattered over
+// the caller's array).  Host gather into a staging chunk, then the usual K-Repack; one chunk of host memory.
+void amie_b200_gather_blocks(const double * array, const uint32_t * src, uint64_t nblk, uint64_t per_block, double * out)
+{
+    #pragma omp parallel for schedule(static)
+    for(long long j = 0 ; j < (long long)nblk ; j++)
+        std::memcpy(out+(uint64_t)j*per_block, array+(uint64_t)src[j]*per_block, per_block*sizeof(double)) ;
+}
+
+int ctx_set_values_from(amie_b200_ctx * ctx, const double * array, const uint32_t * src)
+{
+    if(!ctx->have_structure) { ctx->set_error("set_values before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    const double t0 = wall_now() ;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device)) ;
+    const int S = ctx->S, cl = S+S%2 ;
+    const uint64_t per_block = (uint64_t)S*cl ;
+    const uint64_t chunk_blocks = std::min<uint64_t>(std::max<uint64_t>(ctx->nnzb, 1), (64ull << 20)/(per_block*8)) ;
+    std::vector<double> host(chunk_blocks*per_block) ;
+    double * stage = nullptr ;
+    if(cl != S) CUDA_TRY(ctx, cudaMalloc(&stage, chunk_blocks*per_block*sizeof(double))) ;
+    int rc = AMIE_B200_OK ;
+    for(uint64_t k = 0 ; k < ctx->nnzb && !rc ; k += chunk_blocks)
+    {
+        const uint64_t nblk = std::min(chunk_blocks, ctx->nnzb-k) ;
+        amie_b200_gather_blocks(array, src+k, nblk, per_block, host.data()) ;
+        cudaError_t e ;
+        if(cl == S)
+            e = cudaMemcpyAsync(ctx->vals+k*per_block, host.data(), nblk*per_block*sizeof(double), cudaMemcpyHostToDevice, ctx->stream) ;
+        else
+        {
+            e = cudaMemcpyAsync(stage, host.data(), nblk*per_block*sizeof(double), cudaMemcpyHostToDevice, ctx->stream) ;
+            if(e == cudaSuccess)
+            {
+                if(S == 3) k_repack<3><<<vec_grid(ctx, nblk*9), 256, 0, ctx->stream>>>(stage, ctx->vals+k*9, nblk) ;
+                else       k_repack<1><<<vec_grid(ctx, nblk), 256, 0, ctx->stream>>>(stage, ctx->vals+k, nblk) ;
+                e = cudaGetLastError() ;
+            }
+        }
+        // the host chunk is reused: the copy out of it must be over before the next gather
+        if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream) ;
+        if(e != cudaSuccess) { ctx->set_error(std::string("set_values (gathered): ")+cudaGetErrorString(e)) ; rc = AMIE_B200_ERR_CUDA ; }
+    }
+    if(stage) cudaFree(stage) ;
+    if(rc) return rc ;
+    ctx->have_values = true ;
+    ctx->dinv_valid = false ;
+    ctx->stats.values_ms = (wall_now()-t0)*1e3 ;
+    return AMIE_B200_OK ;
 }

@@ -255,6 +255,7 @@ int group_set_structure(amie_b200_ctx * ctx, int stride, uint64_t nb, const uint
         if(acc != nnzb) { ctx->set_error("set_structure: sum(row_size) != nnzb") ; return AMIE_B200_ERR_ARG ; }
     }
     ctx->have_structure = ctx->have_values = ctx->have_rhs = false ;
+    g->block_from.clear() ;                   // a block map belongs to the structure it was given for
     rc = g->run([&](int r) -> int
     {
         amie_b200_ctx * c = g->child[r] ;
@@ -278,7 +279,11 @@ int group_set_values(amie_b200_ctx * ctx, const double * array)
     LocalGroup * g = ctx->group ;
     const double t0 = wall_now() ;
     const uint64_t per_block = (uint64_t)ctx->S*(ctx->S+ctx->S%2) ;
-    rc = g->run([&](int r) -> int { return amie_b200_set_values(g->child[r], array+g->blk_off[r]*per_block) ; }) ;
+    if(!g->block_from.empty())
+        // under a block map the blocks of a device's rows are scattered over the caller's array: gathered on the host
+        rc = g->run([&](int r) -> int { return ctx_set_values_from(g->child[r], array, g->block_from.data()+g->blk_off[r]) ; }) ;
+    else
+        rc = g->run([&](int r) -> int { return amie_b200_set_values(g->child[r], array+g->blk_off[r]*per_block) ; }) ;
     if(rc) return harvest(ctx, rc) ;
     ctx->have_values = true ;
     ctx->stats.values_ms = (wall_now()-t0)*1e3 ;
@@ -599,4 +604,30 @@ int group_element_principal(amie_b200_ctx * ctx, int field, double * principal_o
         return amie_b200_element_principal(g->child[r], field, principal_out+e0*dim) ;
     }) ;
     return harvest(ctx, rc) ;
+}
+
+
+// ------------------------------------------------------------------ renumbered device matrix (amie_b200_set_block_map)
+
+// block k of the caller's array -> stored block block_to[k] of the structure set_structure was given (the renumbered
+// one).  The stored blocks are cut by rows over the devices, so each device needs the INVERSE restricted to its range.
+int group_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to)
+{
+    int rc = check_usable(ctx) ;
+    if(rc) return rc ;
+    if(!ctx->have_structure) { ctx->set_error("set_block_map before set_structure") ; return AMIE_B200_ERR_STATE ; }
+    LocalGroup * g = ctx->group ;
+    g->block_from.clear() ;
+    ctx->have_values = false ;                // whatever was uploaded before was in the other order
+    for(auto * c : g->child) { c->have_values = false ; c->dinv_valid = false ; }
+    if(!block_to) return AMIE_B200_OK ;
+    const uint32_t none = 0xFFFFFFFFu ;
+    std::vector<uint32_t> from(ctx->nnzb, none) ;
+    for(uint64_t k = 0 ; k < ctx->nnzb ; k++)
+    {
+        if(block_to[k] >= ctx->nnzb || from[block_to[k]] != none) { ctx->set_error("set_block_map: not a permutation of the stored blocks") ; return AMIE_B200_ERR_ARG ; }
+        from[block_to[k]] = (uint32_t)k ;
+    }
+    g->block_from.swap(from) ;
+    return AMIE_B200_OK ;
 }

@@ -27,6 +27,7 @@ struct LocalGroup
     std::vector<uint64_t> elem_bounds ;       // field recovery: elements [elem_bounds[r], elem_bounds[r+1]) live on device r
     int field_nc = 0, field_dim = 0 ;
     bool field_shared_behaviours = false ;    // set_element_behaviour came with tensor_of_elem (one table on every device)
+    std::vector<uint32_t> block_from ;        // set_block_map: stored block j holds block block_from[j] of the caller's array (empty: identity)
 
     // ---- exchange slots: rank r writes [r], barrier, everybody reads, barrier
     void * ptr[GROUP_MAX] = {} ;
@@ -76,6 +77,10 @@ int group_sliced(amie_b200_ctx * ctx, const std::function<int(amie_b200_ctx *, u
 int group_get_stats(const amie_b200_ctx * ctx, amie_b200_stats * out) ;
 int group_set_option(amie_b200_ctx * ctx, const char * key, int64_t value) ;
 int group_unsupported(amie_b200_ctx * ctx, const char * what) ;
+int group_set_block_map(amie_b200_ctx * ctx, const uint32_t * block_to) ;
+// api.cu: the values of ctx's stored blocks from blocks src[j] of a host array (host gather + K-Repack)
+int ctx_set_values_from(amie_b200_ctx * ctx, const double * array, const uint32_t * src) ;
+extern "C" void amie_b200_gather_blocks(const double * array, const uint32_t * src, uint64_t nblk, uint64_t per_block, double * out) ;
 int group_download_matrix(amie_b200_ctx * ctx, uint32_t * row_size_out, uint32_t * column_index_out, double * array_padded_out) ;
 // the rows next to the solve.  Value assembly: every device sees the whole element list (global node ids) and keeps the
 // contributions to the block rows it owns.  Field recovery: the ELEMENTS are split, every device holds the whole field.

@@ -105,13 +105,14 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
     // of the SpMV pays for it -- measured on a 2.65 M-DOF tetrahedral system with a numbering without locality:
     // 2.8 TB/s as it comes, 5.3 TB/s renumbered, PCG 2 126 -> 3 622 it/s (profiles/r02_notes.md).  On by default from
     // 20 000 nodes up (smaller solves are launch-bound); AMIE_B200_RENUMBER=0 / 1 forces it off / on.
-    // rowstart / colstart address AMIE's numbering (space-time planes): such assemblies keep it; so does a
-    // multi-device context (AMIE_B200_DEVICES), which partitions the rows as they come.
+    // rowstart / colstart address AMIE's numbering (space-time planes): such assemblies keep it.  A multi-device
+    // context (AMIE_B200_DEVICES) keeps it by default too -- it partitions the rows as they come -- and renumbers when
+    // AMIE_B200_RENUMBER=1 asks for it (contiguous row ranges of a Cuthill-McKee numbering have small halos).
     const char * env = getenv("AMIE_B200_RENUMBER") ;
     const char * devs = getenv("AMIE_B200_DEVICES") ;
     const bool multi = devs && strchr(devs, ',') ;
-    const bool asked = env ? atoi(env) != 0 : nb >= 20000 ;
-    const bool want_renumber = asked && !multi && a->rowstart == 0 && a->colstart == 0 && nb > 0 ;
+    const bool asked = env ? atoi(env) != 0 : (nb >= 20000 && !multi) ;
+    const bool want_renumber = asked && a->rowstart == 0 && a->colstart == 0 && nb > 0 ;
     if(e.stride != A.stride || e.nb != nb || e.nnzb != nnzb || e.colptr != cp || e.colhash != h || e.renumbered != want_renumber)
     {
         int rc = 0 ;
