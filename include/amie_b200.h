@@ -65,7 +65,8 @@ typedef struct amie_b200_ctx amie_b200_ctx ;
  *     assemble / set_boundary_conditions) send the element list and the id lists to every device, which keeps what lands
  *     on the block rows it owns; the field-recovery rows split the ELEMENTS over the devices, each holding the whole
  *     displacement field (from the host, or gathered from the parts over the peer links).  Element and dof ids stay the
- *     caller's global ones throughout.  Not on a multi-device context: set_block_map (AMIE_B200_ERR_UNSUPPORTED).
+ *     caller's global ones throughout.  set_block_map works too (each device's values are gathered on the host from
+ *     the caller's array through the inverse map).
  *   One process per GPU (torchrun, MPI) uses amie_b200_dist_init (below) instead.
  * Returns NULL on failure (see amie_b200_global_error). */
 amie_b200_ctx * amie_b200_create(const int * devices, int ndev) ;
