@@ -118,3 +118,60 @@ def test_partitioned_spmv_world2_gloo(preset, n):
         plane = n * n if preset != "S2-tri" else n
         assert 0 < nhalo <= plane + n + 2          # one node plane (line in 2D) per neighbour
         assert ninterior >= nbl - 2 * plane - 2 * n - 2
+
+
+def _assembly_worker(rank, world, port, name, out):
+    """One rank of a row-partitioned value assembly + elimination: the whole element list and the global id lists on
+    every rank, the rank's own rows out (kernel sources through the host emulation), gathered over gloo."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    import emu_lib as em
+    import oracle_lib as ol
+    pkg = g.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G = np.load(os.path.join(ROOT, "tests", "golden", name))
+    s, nb = int(G["stride"]), int(G["nb"])
+    el = ol.Elements(s, G["elem_ids"], G["elem_ke"], G["scales"])
+    bounds = pkg.partition_rows(G["row_size"], world).astype(np.int64)
+    part = em.split_rows(G["row_size"], G["column_index"], [int(b) for b in bounds])[rank]
+    r0, r1, k0, k1 = part[:4]
+    # the halo list of this numbering is what csrc/partition.cpp computes for the rank
+    assert np.array_equal(part[6], pkg.partition_halo(r0, r1, part[4], G["column_index"][k0:k1]))
+    rc, vals = em.assemble_part(s, part, nb, el.ids, el.ke, el.scales)
+    assert rc == 0
+    vals, forces, _, _ = em.dirichlet_part(s, part, nb, vals, np.zeros((r1 - r0) * s), G["fix_ids"], G["fix_values"])
+    # every rank learns every part (sizes differ: pad to the largest)
+    sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([vals.size, forces.size]))
+    nv, nf = max(int(t[0]) for t in sizes), max(int(t[1]) for t in sizes)
+    pv, pf = torch.zeros(nv, dtype=torch.float64), torch.zeros(nf, dtype=torch.float64)
+    pv[:vals.size] = torch.from_numpy(vals)
+    pf[:forces.size] = torch.from_numpy(forces)
+    allv = [torch.zeros(nv, dtype=torch.float64) for _ in range(world)]
+    allf = [torch.zeros(nf, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allv, pv)
+    dist.all_gather(allf, pf)
+    V = np.concatenate([allv[q][:int(sizes[q][0])].numpy() for q in range(world)])
+    F = np.concatenate([allf[q][:int(sizes[q][1])].numpy() for q in range(world)])
+    same = lambda a, b: np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+    out[rank] = (bool(same(em.padded(V, s), G["array_post"])),
+                 bool(same(F, G["forces_post"])) if bool(G["forces_comparable"]) else True, int(part[6].size))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["AMIE-2d-s20-assembly.npz", "AMIE-3d-s400-assembly.npz"])
+def test_partitioned_assembly_world2_gloo(name):
+    """N > 1 form of SURVEY section 8 row f1: two processes, each assembling and eliminating the block rows it owns from
+    the whole element list; the parts gathered over gloo are the matrix (and forces) the unmodified FeatureTree solved."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    mp.spawn(_assembly_worker, args=(world, port, name, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        matrix_ok, forces_ok, nhalo = out[rank]
+        assert matrix_ok and forces_ok and nhalo > 0
