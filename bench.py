@@ -585,7 +585,7 @@ def main():
     except Exception:
         pass
     if s == 3:
-        kernel = "k_spmv_s3_rt" + ("m" if args.spmv_variant in (4, 5, 6, 7) else "") + "<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)"
+        kernel = "k_spmv_s3_rt<DOT_YX> (q = A p fused with p.q; TMA bulk-copy pipeline)"
     else:
         kernel = "k_spmv_s2_rt<DOT_YX> (row-thread TMA pipeline, 2x2 blocks)"
     par = None

@@ -5,8 +5,10 @@
 //   block = 4 doubles (32 B, always 16-byte aligned: the TMA copies need no lead skipping)
 //   x     = one 16-byte cp.async per block (x node = 2 doubles, 16-byte aligned)
 //   2D rows are short (T3 meshes: ~7 blocks), so a stage is small (CAP 144 blocks = 8.6 KB) and there is
-//   room for 6 compute warps and 16 stages: in 2D the vector traffic weighs as much as the matrix
-//   (144 B/DOF of SpMV against 120 B/DOF of vector kernels), and per-row fixed costs dominate.
+//   room for 8 compute warps, 4 producer warps and 20 stages (spmv_launch.cu): in 2D the vector traffic
+//   weighs as much as the matrix (144 B/DOF of SpMV against 120 B/DOF of vector kernels), and per-row
+//   fixed costs dominate.
+//   lane  = (block row, block COLUMN) for the products, (block row, row component) for the store (below)
 #pragma once
 #include "kernels_spmv_rt.cuh"
 
@@ -28,8 +30,10 @@ struct Rt2Layout
 // Column mapping: lane (rl, c) holds COLUMN c of its block row's blocks -- A(0,c), A(1,c) are 16 contiguous, 16-byte
 // aligned bytes (one LDS.128) and only x_c is needed (one LDS.64): 2 shared-memory instructions / 6 wavefronts per block
 // instead of 4 / 8, conflict-free for rows of 7 blocks (row stride 224 B: four block rows x 2 columns fill the 128 B of
-// a quarter-warp pass; the row mapping collides block rows rl and rl + 4).  The two partial sums per row are the same
-// FMA chains as in the row mapping (acc_c over the row's blocks), exchanged once per tile: y_r = acc_r(col 0) + acc_r(col 1).
+// a quarter-warp pass; a lane per scalar row collides block rows rl and rl + 4: measured 192 M -> 150 M shared-memory
+// wavefronts per launch on S2-tri-4096, profiles/r02_notes.md section 8).  The two partial sums per row are the FMA chains
+// a lane per scalar row forms (acc_c over the row's blocks), exchanged once per tile: y_r = acc_r(col 0) + acc_r(col 1) --
+// same bits (checked on B200 against that mapping before it was deleted).
 template<int OFF>
 __device__ __forceinline__ void lds_v2f64(uint32_t base, double & v0, double & v1)
 {
