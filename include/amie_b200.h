@@ -316,6 +316,11 @@ int amie_b200_partition_halo(uint64_t r0, uint64_t r1, const uint32_t * row_size
  * (csrc/reorder.cpp; the device half is amie_b200_set_block_map: values scattered through block_to inside K-Repack,
  * the host permutes the vectors).  perm_out[old node] = new node: reverse Cuthill-McKee on the block graph.      */
 int amie_b200_rcm_order(uint64_t nb, const uint32_t * row_size, const uint32_t * column_index, uint32_t * perm_out) ;
+/* Opt-in refinement of a numbering (perm_inout[old node] = new node, e.g. the one above): inside every window of
+ * `window` consecutive nodes of it, the nodes are re-ordered by row length, longest first.  A tile of the row-thread
+ * SpMV costs its longest row; FeatureTree-assembled 3D systems carry a 1.7-1.9x imbalance per tile (csrc/reorder.cpp).
+ * row_size is in the ORIGINAL numbering.  AMIE_B200_ERR_ARG if perm_inout is not a permutation or window == 0.       */
+int amie_b200_group_rows_by_length(uint64_t nb, const uint32_t * row_size, uint64_t window, uint32_t * perm_inout) ;
 /* The structure in the new numbering (columns ascending inside each row) and, for every stored block of it, the
  * stored block of the old structure it is (block_from_out[new k] = old k): array_new block k = array_old block
  * block_from[k].  AMIE_B200_ERR_ARG if perm is not a permutation.                                                  */

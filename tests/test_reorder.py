@@ -83,3 +83,49 @@ def test_gather_of_a_device_slice_under_a_block_map(pkg):
         out = np.zeros((k1 - k0) * per_block)
         L.amie_b200_gather_blocks(arr.ctypes.data, src.ctypes.data, k1 - k0, per_block, out.ctypes.data)
         assert np.array_equal(out.reshape(-1, per_block), want[k0:k1])
+
+
+def tile_imbalance(row_size, rows_per_tile=10):
+    """(rows per tile x longest row, summed over the tiles) / stored blocks: what a lane-per-row tile pays for unequal rows."""
+    rs = np.asarray(row_size, np.int64)
+    pad = (-rs.size) % rows_per_tile
+    t = np.concatenate([rs, np.zeros(pad, np.int64)]).reshape(-1, rows_per_tile)
+    return float((t.max(1) * rows_per_tile).sum() / rs.sum())
+
+
+@pytest.mark.parametrize("name", ["AMIE-3d-s400.npz", "AMIE-2d-s20.npz"])
+def test_rows_grouped_by_length_inside_windows(pkg, ol, name):
+    """amie_b200_group_rows_by_length on top of the Cuthill-McKee numbering of the FeatureTree fixtures: still a permutation,
+    nodes stay inside their window, the per-tile imbalance drops, and the solve of the renumbered system is the
+    renumbered solve (oracle)."""
+    G = np.load(os.path.join(GOLDEN, name))
+    s, nb = int(G["stride"]), int(G["nb"])
+    rs, ci = G["row_size"], G["column_index"]
+    perm = pkg.rcm_order(rs, ci)
+    W = 80
+    perm2 = pkg.group_rows_by_length(rs, perm, W)
+    assert np.array_equal(np.sort(perm2), np.arange(nb))
+    assert np.array_equal(perm // W, perm2 // W)                       # nobody left its window
+    rs1, ci1, _ = pkg.permute_structure(rs, ci, perm)
+    rs2, ci2, frm = pkg.permute_structure(rs, ci, perm2)
+    for w0 in range(0, nb, W):                                         # longest first inside each window
+        assert np.all(np.diff(rs2[w0:w0 + W].astype(np.int64)) <= 0)
+    rows = 10 if s == 3 else 16
+    before, after = tile_imbalance(rs1, rows), tile_imbalance(rs2, rows)
+    print(f"{name}: tile imbalance {tile_imbalance(rs, rows):.2f} (mesher) -> {before:.2f} (RCM) -> {after:.2f} (RCM + window {W})")
+    assert after < before
+    # the renumbered system solves to the renumbered solution
+    cl = s + s % 2
+    arr2 = G["array"].reshape(-1, s * cl)[frm].reshape(-1)
+    b2 = np.empty_like(G["b"])
+    b2.reshape(-1, s)[perm2] = G["b"].reshape(-1, s)
+    S2 = ol.Sys(s, nb, rs2, ci2, arr2, b2)
+    ret, x2, info = ol.oracle_cg(S2, nssor=32)
+    assert ret == bool(G["cg_ok"]) and abs(int(info.nit) - int(G["cg_nit"])) <= 2
+    x_back = x2.reshape(-1, s)[perm2].reshape(-1)
+    assert np.linalg.norm(x_back - G["cg_x"]) <= 1e-8 * np.linalg.norm(G["cg_x"])
+    # error paths
+    with pytest.raises(pkg.AmieB200Error):
+        pkg.group_rows_by_length(rs, np.zeros(nb, np.uint32), W)
+    with pytest.raises(pkg.AmieB200Error):
+        pkg.group_rows_by_length(rs, perm, 0)

@@ -114,6 +114,7 @@ def lib():
         L.amie_b200_partition_rows.argtypes = [u64, vp, ci, vp]
         L.amie_b200_partition_halo.argtypes = [u64, u64, vp, vp, vp, vp]
         L.amie_b200_rcm_order.argtypes = [u64, vp, vp, vp]
+        L.amie_b200_group_rows_by_length.argtypes = [u64, vp, u64, vp]
         L.amie_b200_permute_structure.argtypes = [u64, vp, vp, vp, vp, vp, vp]
         L.amie_b200_nccl_unique_id.argtypes = [vp]
         L.amie_b200_dist_init.argtypes = [vp, ci, ci, vp, vp]
@@ -764,6 +765,17 @@ def rcm_order(row_size, column_index):
     if rc:
         raise AmieB200Error(rc, "rcm_order")
     return perm
+
+
+def group_rows_by_length(row_size, perm, window):
+    """perm refined: inside windows of `window` consecutive nodes of the numbering perm, nodes ordered by row length
+    (longest first); row_size in the original numbering (host only, opt-in: csrc/reorder.cpp)."""
+    rs = np.ascontiguousarray(row_size, np.uint32)
+    out = np.array(perm, np.uint32)
+    rc = lib().amie_b200_group_rows_by_length(rs.size, _ptr(rs), int(window), _ptr(out))
+    if rc:
+        raise AmieB200Error(rc, "group_rows_by_length: perm is not a permutation of the nodes, or window == 0")
+    return out
 
 
 def permute_structure(row_size, column_index, perm):

@@ -122,6 +122,9 @@ amie_b200_ctx * context_for(Amie::Assembly * a)
             e.perm.assign(nb, 0u) ;
             std::vector<uint32_t> rs2(nb), ci2(nnzb), from(nnzb), to(nnzb) ;
             rc = amie_b200_rcm_order(nb, &A.row_size[0], cp, e.perm.data()) ;
+            // AMIE_B200_RENUMBER=2 (opt-in): rows of similar length next to one another inside windows of 80 nodes of the
+            // Cuthill-McKee numbering (a tile of the SpMV costs its longest row; csrc/reorder.cpp)
+            if(!rc && env && atoi(env) == 2) rc = amie_b200_group_rows_by_length(nb, &A.row_size[0], 80, e.perm.data()) ;
             if(!rc) rc = amie_b200_permute_structure(nb, &A.row_size[0], cp, e.perm.data(), rs2.data(), ci2.data(), from.data()) ;
             if(rc) { std::cerr << "amie_b200: renumbering failed (" << rc << ")" << std::endl ; return nullptr ; }
             for(size_t k = 0 ; k < nnzb ; k++) to[from[k]] = (uint32_t)k ;
