@@ -26,6 +26,12 @@
 //                                                   irregular length behind the regular ones.  Elastic phases (the example's
 //                                                   moduli), pockets at fixed positions inside the aggregate, grown to a radius
 //                                                   the mesh resolves (the example grows them step by step from 1e-3).
+//   amie_e2e_* check <0|1|2> <out.bin>              examples/main_check_behaviour.cpp:66-125 for the three behaviours whose golden files
+//                                                   the reference ships (examples/test/check_behaviour_test_stiffness*_base, 1 % bar):
+//                                                   0 test_stiffness.ini (`--steps 1 --maximum-value 1e6 --stress --constant`),
+//                                                   1 test_stiffness_with_imposed_deformation.ini, 2 ..._with_imposed_stress.ini (both
+//                                                   `--steps 1 --free`): the 2-element, 8-unknown sample.  Prints on stderr the line
+//                                                   the example writes to its result file: `check: <time> <strain*1e3> <stress/1e6> <damage%>`.
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -52,6 +58,7 @@
 #include "features/inclusion.h"
 #include "physics/stiffness.h"
 #include "physics/stiffness_with_imposed_deformation.h"
+#include "physics/stiffness_with_imposed_stress.h"
 #include "physics/stiffness_and_fracture.h"
 #include "physics/void_form.h"
 #include "physics/fracturecriteria/vonmises.h"
@@ -227,7 +234,32 @@ int main(int argc, char ** argv)
     if(argc < 4) { fprintf(stderr, "usage: %s 2d|3d <sampling> <out.bin> [dump.bin]\n", argv[0]) ; return 2 ; }
     const std::string mode = argv[1] ;
     const int sampling = atoi(argv[2]) ;
-    if(mode == "2dst")
+    if(mode == "check")
+    {
+        const int which = sampling ;              // argv[2]
+        Form * behaviour = nullptr ;
+        if(which == 0)      behaviour = new Stiffness(10e9, 0.2) ;
+        else if(which == 1) behaviour = new StiffnessWithImposedStrain(10e9, 0.2, 0.001) ;
+        else                behaviour = new StiffnessWithImposedStress(10e9, 0.2, 1e6) ;
+        const bool is_free = which != 0 ;
+        const double val = which == 0 ? 1e6 : 0.001 ;             // --maximum-value (default 0.001)
+        RectangularFeature sample(0.01, 0.01, 0, 0) ;
+        sample.setBehaviour(behaviour) ;
+        FeatureTree F(&sample) ;
+        F.setSamplingNumber(0) ;
+        F.step() ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, BOTTOM_LEFT)) ;
+        // test_stiffness.ini: --stress --constant -> SET_STRESS_ETA on TOP at the full value from the start
+        BoundingBoxDefinedBoundaryCondition * up = new BoundingBoxDefinedBoundaryCondition(which == 0 ? SET_STRESS_ETA : SET_ALONG_ETA, TOP, which == 0 ? val : 0.) ;
+        if(!is_free) F.addBoundaryCondition(up) ;
+        if(is_free) up->setData(val) ;                            // (--steps 1, not --constant: the example sets it, attached or not)
+        F.step() ;
+        fprintf(stderr, "\ncheck: %.10g %.10g %.10g %.10g\n", F.getCurrentTime(), F.getAverageField(TOTAL_STRAIN_FIELD)[1]*1e3,
+                F.getAverageField(REAL_STRESS_FIELD)[1]/1e6, F.getAverageField(SCALAR_DAMAGE_FIELD)[0]*100) ;
+        write_vec(argv[3], F.getDisplacements()) ;
+    }
+    else if(mode == "2dst")
     {
         const double yieldstrain = 0.0005, maxstrain = 0.0001, young = 10e9, radius = 0.01 ;     // the parser defaults (:45-50)
         RectangularFeature sample(nullptr, 0.2, 0.1, 0, 0) ;
