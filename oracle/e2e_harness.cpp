@@ -32,6 +32,11 @@
 //                                                   1 test_stiffness_with_imposed_deformation.ini, 2 ..._with_imposed_stress.ini (both
 //                                                   `--steps 1 --free`): the 2-element, 8-unknown sample.  Prints on stderr the line
 //                                                   the example writes to its result file: `check: <time> <strain*1e3> <stress/1e6> <damage%>`.
+//   amie_e2e_* xfem 0 <out.bin>                     examples/test/main_test_xfem.cpp:35-76, the reference's own XFEM test (golden file
+//                                                   examples/test/test_xfem_base): one ExpansiveZone in a square, its radius grown
+//                                                   twice -- the enrichment, hence the topology the solver sees, changes between the
+//                                                   steps.  Prints `xfem: <time> <3 strains*1e3> <3 stresses/1e6>` per stage on stderr;
+//                                                   out.bin holds one record per stage.
 // out.bin  : uint64 n, n doubles (F.getDisplacements())
 // dump.bin : the assembled system of the last solve in the reference layout
 //            (uint64 stride, nb, nnzb; row_size u32[nb]; column_index u32[nnzb]; array f64; forces f64[N])
@@ -234,7 +239,33 @@ int main(int argc, char ** argv)
     if(argc < 4) { fprintf(stderr, "usage: %s 2d|3d <sampling> <out.bin> [dump.bin]\n", argv[0]) ; return 2 ; }
     const std::string mode = argv[1] ;
     const int sampling = atoi(argv[2]) ;
-    if(mode == "check")
+    if(mode == "xfem")
+    {
+        Matrix C = Tensor::cauchyGreen(10e9, 0.2, SPACE_TWO_DIMENSIONAL, PLANE_STRAIN, YOUNG_POISSON) ;
+        Vector v(3) ; v[0] = 0.01 ; v[1] = 0.01 ;
+        RectangularFeature box(0.1, 0.1, 0, 0) ;
+        box.setBehaviour(new Stiffness(C)) ;
+        FeatureTree F(&box) ;
+        ExpansiveZone * exp = new ExpansiveZone(&box, 0.02, 0, 0, new StiffnessWithImposedStrain(C*2, v)) ;
+        F.addFeature(&box, exp) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_XI, BOTTOM_LEFT)) ;
+        F.addBoundaryCondition(new BoundingBoxDefinedBoundaryCondition(FIX_ALONG_ETA, BOTTOM)) ;
+        F.setSamplingNumber(4) ;
+        F.setDeltaTime(1) ;
+        remove(argv[3]) ;
+        const double radius[3] = { 0.02, 0.03, 0.5 } ;
+        for(int stage = 0 ; stage < 3 ; stage++)
+        {
+            if(stage) exp->setRadius(radius[stage]) ;
+            F.step() ;
+            F.step() ;
+            Vector str = F.getAverageField(TOTAL_STRAIN_FIELD)*1e3 ;
+            Vector sig = F.getAverageField(REAL_STRESS_FIELD)/1e6 ;
+            fprintf(stderr, "\nxfem: %.10g %.10g %.10g %.10g %.10g %.10g %.10g\n", F.getCurrentTime(), str[0], str[1], str[2], sig[0], sig[1], sig[2]) ;
+            write_vec(argv[3], F.getDisplacements(), "ab") ;
+        }
+    }
+    else if(mode == "check")
     {
         const int which = sampling ;              // argv[2]
         Form * behaviour = nullptr ;

@@ -176,3 +176,23 @@ def test_reference_golden_files_through_the_dropin(tmp_path, which):
     assert matches_golden(line_gpu, GOLDEN[which][2]), (line_gpu, GOLDEN[which])
     assert len(cg_ref) == len(cg_gpu) and all(abs(a - b) <= 2 for a, b in zip(cg_ref, cg_gpu)), (cg_ref, cg_gpu)
     assert np.abs(u_gpu - u_ref).max() <= 1e-8 * np.abs(u_ref).max()
+
+
+def test_reference_xfem_test_program_through_the_dropin(tmp_path):
+    """examples/test/main_test_xfem.cpp (the reference's own XFEM test; tests/test_reference_goldens.py) with the drop-in
+    solvers: the enrichment changes between the stages, so the drop-in sees three different topologies (222, 246 and 186
+    unknowns) behind one Assembly and must notice each change.  Displacements of every stage against the reference
+    binary, CG counts, the averaged fields the example prints."""
+    from test_reference_goldens import run_xfem
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("oracle/_ref e2e binaries not prebuilt (no /root/reference at build time)")
+    lines_ref, recs_ref, cg_ref, _ = run_xfem(REF, str(tmp_path))
+    lines_gpu, recs_gpu, cg_gpu, log = run_xfem(B200, str(tmp_path), {"AMIE_B200_SHIM_TRACE": "1"})
+    assert "no CPU fallback" not in log, log[-1500:]
+    assert len(recs_ref) == len(recs_gpu) == 3 and [r.size for r in recs_ref] == [r.size for r in recs_gpu]
+    assert len(cg_ref) == len(cg_gpu) and all(abs(a - b) <= 2 for a, b in zip(cg_ref, cg_gpu)), (cg_ref, cg_gpu)
+    for a, b in zip(recs_ref, recs_gpu):
+        assert rel_l2(b, a) <= 1e-8
+    for a, b in zip(lines_ref, lines_gpu):
+        assert all(abs(x - y) <= max(1e-6 * abs(x), 1e-9) for x, y in zip(a, b)), (a, b)
+    print(f"xfem test program: unknowns {[r.size for r in recs_ref]}, CG {cg_ref} vs {cg_gpu}")

@@ -45,3 +45,42 @@ def test_reference_binary_reproduces_its_own_golden_files(tmp_path, which):
     line, u, cg, _ = run_check(REF, which, str(tmp_path))
     assert matches_golden(line, GOLDEN[which][2]), (line, GOLDEN[which])
     assert u.size == 8 and cg and max(cg) <= 8            # 8 unknowns: CG ends within N iterations
+
+
+# examples/test/test_xfem_base (examples/test/main_test_xfem.cpp): <time> <3 strains*1e3> <3 stresses/1e6> per stage
+XFEM_GOLDEN = [(0, 1.67573, 1.68, -0.00887336, -1.58939e-10, -1.28809e-10, 1.04754e-09),
+               (1, 3.54743, 3.60342, 0.00396261, 1.47408e-10, 6.23418e-12, -1.3737e-09),
+               (2, 10, 10, 1.41021e-11, -3.55667e-11, 3.64058e-11, 2.35035e-10)]
+
+
+def run_xfem(exe, tmp, env_extra=None):
+    """Harness mode `xfem`: ([(time, 3 strains, 3 stresses)], [displacements per stage], CG counts, log)."""
+    out = os.path.join(tmp, f"xfem_{os.path.basename(exe)}.bin")
+    env = dict(os.environ, OMP_NUM_THREADS="1", **(env_extra or {}))
+    p = subprocess.run([exe, "xfem", "0", out], cwd=tmp, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-1500:]
+    lines = [tuple(float(v) for v in m.split()) for m in re.findall(r"^xfem: (.*)$", p.stderr, re.M)]
+    raw = np.fromfile(out, np.uint8)
+    recs, off = [], 0
+    while off + 8 <= raw.size:
+        n = int(raw[off:off + 8].view(np.uint64)[0])
+        recs.append(raw[off + 8:off + 8 + 8 * n].view(np.float64).copy())
+        off += 8 + 8 * n
+    cg = [int(v) for v in re.findall(r"CG \d+ converged after (\d+) iterations", p.stderr)]
+    return lines, recs, cg, p.stderr
+
+
+def test_reference_xfem_test_program(tmp_path):
+    """examples/test/main_test_xfem.cpp, the reference's own XFEM test (one ExpansiveZone whose radius grows twice: the
+    enrichment, and with it the number of unknowns, changes between the stages: 222 -> 246 -> 186).  This build of the
+    reference reproduces the last line of its golden file (the zone covers the sample: strains 10, 10, 0) and is 6 % off
+    the first two (1.58 / 1.58 against 1.676 / 1.68; 3.34 / 3.37 against 3.55 / 3.60) -- the golden file predates the
+    mesher of this revision; its time column (0, 1, 2) is 1, 3, 5 here.  What is pinned: the run completes, three
+    stages with different numbers of unknowns, the last line."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref e2e binaries not prebuilt (no /root/reference at build time)")
+    lines, recs, cg, _ = run_xfem(REF, str(tmp_path))
+    assert len(lines) == len(recs) == 3 and len(cg) == 12        # 2 steps x 2 CG solves per stage
+    assert len({r.size for r in recs}) == 3                      # the enrichment changes the system between the stages
+    assert all(abs(a - b) <= max(0.01 * abs(b), 1e-6) for a, b in zip(lines[2][1:], XFEM_GOLDEN[2][1:]))
+    assert all(0.9 <= a / b <= 1.0 for a, b in zip(lines[0][1:3] + lines[1][1:3], XFEM_GOLDEN[0][1:3] + XFEM_GOLDEN[1][1:3]))
